@@ -1,0 +1,214 @@
+"""Tensor-level wrappers over the C ABI (include/dpf_sm100.h).
+
+PyTorch is used only for device memory and streams: every function takes CUDA tensors, passes raw pointers and the
+current stream to libdpf_sm100.so, and returns tensors it allocated.  No function here has a CPU or eager fallback.
+
+Layouts: features [B,H4,W4,C] bf16; volumes / 3-D activations [B,D,H,W,C] bf16; costs [B,D,H4,W4] fp32;
+disparity [B,H,W] fp32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, check
+
+KIND_3x3x3, KIND_S2, KIND_T2, KIND_1x3x3, KIND_1x1x1 = 0, 1, 2, 3, 4
+_MODES = {"concat": 0, "diff": 1, "gwc": 2}
+
+
+def lib():
+    return _lib.load(check_device=True)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise _lib.DpfError(f"{name}: expected a CUDA tensor (the hot path has no CPU implementation)")
+    if t.dtype != dtype:
+        raise _lib.DpfError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.DpfError(f"{name}: expected a contiguous tensor")
+
+
+def launch_count() -> int:
+    return int(_lib.load().dpf_launch_count())
+
+
+# ----------------------------------------------------------------------------------------------------------
+# cost volume
+# ----------------------------------------------------------------------------------------------------------
+def costvol_channels(mode: str, c: int, groups: int) -> int:
+    return {"concat": 2 * c, "diff": c, "gwc": groups}[mode]
+
+
+def costvol_fwd(ref: torch.Tensor, tgt: torch.Tensor, shifts: Sequence[int], mode: str = "concat", groups: int = 0) -> torch.Tensor:
+    _req(ref, torch.bfloat16, "ref"); _req(tgt, torch.bfloat16, "tgt")
+    b, h, w, c = ref.shape
+    d = len(shifts)
+    vol = torch.empty(b, d, h, w, costvol_channels(mode, c, groups), device=ref.device, dtype=torch.bfloat16)
+    sh = (C.c_int * d)(*[int(s) for s in shifts])
+    check(lib().dpf_costvol_fwd(_MODES[mode], _p(ref), _p(tgt), _p(vol), b, h, w, c, d, groups, sh, _stream()), "dpf_costvol_fwd")
+    return vol
+
+
+def costvol_bwd(ref, tgt, dvol: torch.Tensor, shifts: Sequence[int], mode: str = "concat", groups: int = 0):
+    _req(dvol, torch.bfloat16, "dvol")
+    b, d, h, w, _ = dvol.shape
+    c = ref.shape[-1]
+    dref = torch.empty(b, h, w, c, device=dvol.device, dtype=torch.bfloat16)
+    dtgt = torch.empty_like(dref)
+    sh = (C.c_int * d)(*[int(s) for s in shifts])
+    check(lib().dpf_costvol_bwd(_MODES[mode], _p(ref), _p(tgt), _p(dvol), _p(dref), _p(dtgt), b, h, w, c, d, groups, sh,
+                                _stream()), "dpf_costvol_bwd")
+    return dref, dtgt
+
+
+# ----------------------------------------------------------------------------------------------------------
+# tensor-core convolution
+# ----------------------------------------------------------------------------------------------------------
+def npad_for(cout: int) -> int:
+    return 16 if cout <= 16 else (32 if cout <= 32 else 64)
+
+
+def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None, transposed: bool = False) -> torch.Tensor:
+    """nn.Conv3d weight [Cout,Cin,kd,kh,kw] (or ConvTranspose3d [Cin,Cout,...]) -> packed bf16 [taps][Cin/8][Npad][8].
+
+    Tap order is (kd, kh, kw) row-major; output channels are zero-padded to Npad in {16,32,64}, input channels to cin_pad.
+    """
+    if transposed:
+        w = w.transpose(0, 1)
+    cout, cin = w.shape[:2]
+    cin_pad = cin_pad or cin
+    assert cin_pad % 8 == 0 and cin_pad >= cin
+    taps = w.shape[2] * w.shape[3] * w.shape[4]
+    npad = npad_for(cout)
+    wt = w.detach().float().permute(2, 3, 4, 1, 0).reshape(taps, cin, cout)
+    buf = torch.zeros(taps, cin_pad, npad, device=w.device, dtype=torch.float32)
+    buf[:, :cin, :cout] = wt
+    return buf.reshape(taps, cin_pad // 8, 8, npad).permute(0, 1, 3, 2).contiguous().to(torch.bfloat16)
+
+
+def conv3d(x: torch.Tensor, w_packed: torch.Tensor, kind: int, cout: int, scale: Optional[torch.Tensor] = None,
+           shift: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, relu: bool = False,
+           out: Optional[torch.Tensor] = None, out_f32: bool = False, y_coff: int = 0) -> torch.Tensor:
+    """y = relu?(conv(x) * scale + shift + residual); x [B,D,H,W,Cin] bf16 -> y [B,Do,Ho,Wo,Cstride]."""
+    _req(x, torch.bfloat16, "x"); _req(w_packed, torch.bfloat16, "w_packed")
+    b, d, h, w, cin = x.shape
+    if kind in (KIND_3x3x3, KIND_1x3x3, KIND_1x1x1):
+        do, ho, wo = d, h, w
+    elif kind == KIND_S2:
+        do, ho, wo = (d + 1) // 2, (h + 1) // 2, (w + 1) // 2
+    else:
+        do, ho, wo = 2 * d, 2 * h, 2 * w
+    if out is None:
+        out = torch.empty(b, do, ho, wo, cout, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    assert out.shape[:4] == (b, do, ho, wo) and out.is_contiguous()
+    out_f32 = out.dtype == torch.float32
+    if residual is not None:
+        assert residual.shape == out.shape and residual.dtype == out.dtype and residual.is_contiguous()
+    for t, n in ((scale, "scale"), (shift, "shift")):
+        if t is not None:
+            _req(t, torch.float32, n)
+            assert t.numel() == cout
+    a = ConvArgs(kind=kind, B=b, D=d, H=h, W=w, Cin=cin, Cout=cout, x=x.data_ptr(), w=w_packed.data_ptr(), y=out.data_ptr(),
+                 y_f32=int(out_f32), y_cstride=out.shape[-1], y_coff=y_coff,
+                 scale=scale.data_ptr() if scale is not None else None,
+                 shift=shift.data_ptr() if shift is not None else None,
+                 residual=residual.data_ptr() if residual is not None else None, relu=int(relu), stats=None)
+    check(lib().dpf_conv3d_fwd(C.byref(a), _stream()), "dpf_conv3d_fwd")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# fused upsample + soft-argmin
+# ----------------------------------------------------------------------------------------------------------
+def regress_fwd(cost: torch.Tensor, mindisp: float, step: float, want_prob: bool = False):
+    _req(cost, torch.float32, "cost")
+    b, d, h4, w4 = cost.shape
+    disp = torch.empty(b, 4 * h4, 4 * w4, device=cost.device, dtype=torch.float32)
+    prob = torch.empty(b, 4 * d, 4 * h4, 4 * w4, device=cost.device, dtype=torch.float32) if want_prob else None
+    check(lib().dpf_regress_fwd(_p(cost), _p(disp), _p(prob), b, d, h4, w4, float(mindisp), float(step), _stream()), "dpf_regress_fwd")
+    return disp, prob
+
+
+def regress_bwd(cost: torch.Tensor, ddisp: torch.Tensor, mindisp: float, step: float) -> torch.Tensor:
+    _req(cost, torch.float32, "cost"); _req(ddisp, torch.float32, "ddisp")
+    b, d, h4, w4 = cost.shape
+    dcost = torch.empty_like(cost)
+    check(lib().dpf_regress_bwd(_p(cost), _p(ddisp), _p(dcost), b, d, h4, w4, float(mindisp), float(step), _stream()), "dpf_regress_bwd")
+    return dcost
+
+
+# ----------------------------------------------------------------------------------------------------------
+# ASM sampling / blend
+# ----------------------------------------------------------------------------------------------------------
+def asm_sample(x: torch.Tensor, tables: dict) -> torch.Tensor:
+    """x [B,H4,W4,C] bf16 + device tables (shift_tables.build_tables) -> samples [B,S,H4,W4,C] bf16."""
+    _req(x, torch.bfloat16, "x")
+    b, h, w, c = x.shape
+    s = tables["ri"].shape[0]
+    assert tables["ri"].shape == (s, h, 2) and tables["ci"].shape == (s, w, 2)
+    out = torch.empty(b, s, h, w, c, device=x.device, dtype=torch.bfloat16)
+    check(lib().dpf_asm_sample_fwd(_p(x), _p(out), b, h, w, c, s, _p(tables["ri"]), _p(tables["rw"]), _p(tables["ci"]),
+                                   _p(tables["cw"]), _stream()), "dpf_asm_sample_fwd")
+    return out
+
+
+def channel_stats(x: torch.Tensor) -> torch.Tensor:
+    """x [B,...,C] bf16 -> [B,C,2] fp32 (sum, sum of squares over all positions)."""
+    _req(x, torch.bfloat16, "x")
+    b, c = x.shape[0], x.shape[-1]
+    p = x.numel() // (b * c)
+    stats = torch.empty(b, c, 2, device=x.device, dtype=torch.float32)
+    check(lib().dpf_channel_stats(_p(x), _p(stats), b, p, c, _stream()), "dpf_channel_stats")
+    return stats
+
+
+def asm_blend(samples: torch.Tensor, logits: torch.Tensor, in_a: torch.Tensor, in_d: torch.Tensor, vol: torch.Tensor,
+              d0: int, d_rep: int, ch_off: int) -> None:
+    _req(samples, torch.bfloat16, "samples"); _req(logits, torch.bfloat16, "logits")
+    _req(in_a, torch.float32, "in_a"); _req(in_d, torch.float32, "in_d"); _req(vol, torch.bfloat16, "vol")
+    b, s, h, w, c = samples.shape
+    assert logits.shape == samples.shape and in_a.shape == (b, c) and in_d.shape == (b, c)
+    assert vol.shape[0] == b and vol.shape[2:4] == (h, w)
+    check(lib().dpf_asm_blend_fwd(_p(samples), _p(logits), _p(in_a), _p(in_d), _p(vol), b, h, w, c, s, vol.shape[1], d0, d_rep,
+                                  ch_off, vol.shape[-1], _stream()), "dpf_asm_blend_fwd")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# ANM front end
+# ----------------------------------------------------------------------------------------------------------
+def anm_select(disp: torch.Tensor, kinv: torch.Tensor, abvalue: torch.Tensor, levels: Sequence[float], k: int):
+    """disp [B,H,W] fp32 -> idx [B,K,H4,W4] int32, coord [B,K,H4,W4,3] fp32 (un-normalised), minmax [B,2] fp32."""
+    _req(disp, torch.float32, "disp"); _req(kinv, torch.float32, "kinv"); _req(abvalue, torch.float32, "abvalue")
+    b, h, w = disp.shape
+    h4, w4 = h // 4, w // 4
+    d = len(levels)
+    idx = torch.empty(b, k, h4, w4, device=disp.device, dtype=torch.int32)
+    coord = torch.empty(b, k, h4, w4, 3, device=disp.device, dtype=torch.float32)
+    minmax = torch.tensor([[float("inf"), float("-inf")]], device=disp.device).repeat(b, 1).contiguous()
+    lv = (C.c_float * d)(*[float(v) for v in levels])
+    check(lib().dpf_anm_select(_p(disp), _p(kinv), _p(abvalue), lv, _p(idx), _p(coord), _p(minmax), b, d, k, h4, w4, _stream()),
+          "dpf_anm_select")
+    return idx, coord, minmax
+
+
+def anm_gather(out3: torch.Tensor, idx: torch.Tensor, coord: torch.Tensor, minmax: torch.Tensor, cpad: int = 64) -> torch.Tensor:
+    """out3 [B,D,H4,W4,C] bf16 -> feature volume [B,K,H4,W4,Cpad] bf16 (C cost channels, 3 coords, zero pad)."""
+    _req(out3, torch.bfloat16, "out3")
+    b, d, h4, w4, c = out3.shape
+    k = idx.shape[1]
+    fv = torch.empty(b, k, h4, w4, cpad, device=out3.device, dtype=torch.bfloat16)
+    check(lib().dpf_anm_gather(_p(out3), _p(idx), _p(coord), _p(minmax), _p(fv), b, d, k, h4, w4, c, cpad, _stream()), "dpf_anm_gather")
+    return fv

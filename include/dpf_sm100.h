@@ -1,0 +1,144 @@
+/* dpf_sm100.h -- C ABI of libdpf_sm100.so: the B200 (sm_100a) stereo hot path of DualPixelFace.
+ *
+ * The reference has exactly one native boundary on this path, the pybind11 module `DCN`
+ * (src/module/dcn3d/src/vision.cpp:4-7; deform_conv_forward / deform_conv_backward,
+ * src/module/dcn3d/src/deform_conv.h:10-29,49-69).  Everything else on the path is stock PyTorch called from
+ * src/model/<name>/modules.py.  This header is the C-ABI a maintainer binds instead (ctypes stub in
+ * INTEGRATION.md); each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all buffers,
+ *     nothing is allocated behind the ABI; 16-byte alignment is required for tensors.
+ *   - activations are bf16, channels-last: features [B,H4,W4,C], volumes / 3-D activations [B,D,H,W,C];
+ *     head costs, disparities, statistics are fp32.
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, no global mutable
+ *     state except the per-thread last-error string.
+ *   - return 0 on success, non-zero on error (message via dpf_last_error()); no exceptions cross the ABI.
+ *   - sm_100a only: dpf_device_check() fails on any other device.  There is no CPU path.
+ */
+#ifndef DPF_SM100_H
+#define DPF_SM100_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPF_ABI_VERSION 1
+
+int dpf_abi_version(void);
+const char* dpf_last_error(void);
+/* 0 iff the current CUDA device is compute capability 10.x with >= 200 KB opt-in shared memory. */
+int dpf_device_check(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches evidence). */
+long long dpf_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (1) Integer-shift cost volume.  Replaces CostVolume.build_concat_volume / build_gwc_volume
+ *     (src/model/psmnet/modules.py:223-262) and the difference volume of src/model/stereonet/mainmodel.py:100-114.
+ *     vol[b,i,h,w,:] = f(ref[b,h,w,:], tgt[b,h+s_i,w,:]) if 0 <= h+s_i < H4 else 0, s_i = shifts_host[i].
+ *     mode 0 concat (Cv = 2C: ref | tgt), 1 difference (Cv = C: ref - tgt), 2 group-wise correlation
+ *     (Cv = G: -mean over C/G channels of ref*tgt).  C % 8 == 0, G | C, D <= 16.
+ * ------------------------------------------------------------------------------------------------- */
+int dpf_costvol_fwd(int mode, const void* ref, const void* tgt, void* vol, int B, int H4, int W4, int C, int D, int G,
+                    const int* shifts_host, void* stream);
+/* gradient of the above wrt ref / tgt (gather form, no atomics).  dvol has the layout of vol. */
+int dpf_costvol_bwd(int mode, const void* ref, const void* tgt, const void* dvol, void* dref, void* dtgt, int B, int H4,
+                    int W4, int C, int D, int G, const int* shifts_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (2) ASM sampling + blend (StereoDPNet volume).  Replaces subpixel_shift.forward (src/module/asm/asm.py:87-127)
+ *     and the softmax-blend tail of MaskingAttention.forward (asm.py:160-171) + the volume writes of
+ *     CostVolume.build_concat_volume (src/model/stereodpnet/modules.py:181-197).
+ *
+ *     dpf_asm_sample_fwd: out[s,b,h,w,:] = sum_{i,j in {0,1}} rw[s,h,i]*cw[s,w,j] * x[b, ri[s,h,i], ci[s,w,j], :]
+ *     (index < 0 contributes 0).  Tables are built on the host with the reference's own op sequence so that
+ *     sampling coordinates are bit-exact; layout ri/rw [S,H4,2], ci/cw [S,W4,2] (int32 / fp32, device).
+ *
+ *     dpf_asm_blend_fwd: y[b,h,w,c] = mean_s( x_s * softmax_s( sigmoid( logit_s * a[b,c] + d[b,c] ) ) ) written to
+ *     vol[b, d0..d0+D_rep-1, h, w, ch_off + c] of a [B,D_vol,H4,W4,Cvol] volume (a,d = folded InstanceNorm3d
+ *     affine, fp32 [B,C]).  D_rep = D_vol reproduces the reference's cached-first-level behaviour in one pass.
+ * ------------------------------------------------------------------------------------------------- */
+int dpf_asm_sample_fwd(const void* x, void* out, int B, int H4, int W4, int C, int S, const int* ri, const float* rw,
+                       const int* ci, const float* cw, void* stream);
+int dpf_asm_blend_fwd(const void* samples, const void* logits, const float* in_a, const float* in_d, void* vol, int B,
+                      int H4, int W4, int C, int S, int D_vol, int d0, int D_rep, int ch_off, int Cvol, void* stream);
+/* per-(b,c) sum and sum of squares over all positions of x [B,P,C] bf16 -> stats [B,C,2] fp32 (zeroed by the call). */
+int dpf_channel_stats(const void* x, float* stats, int B, long long P, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (3) 3-D convolution, implicit GEMM on tcgen05 tensor cores (fp32 accumulation in TMEM), with the
+ *     per-channel affine (folded BatchNorm / bias), residual add and ReLU fused in the epilogue.
+ *     Replaces every nn.Conv3d / nn.ConvTranspose3d + BatchNorm3d + ReLU (+ add) of PSMNetHGAggregation
+ *     (src/model/stereodpnet/modules.py:204-337, convbn_3d src/module/asm/basics.py:32-36) and the mask
+ *     convolutions of MaskingAttention (src/module/asm/asm.py:141-146).
+ *       y = relu?( conv(x, w) * scale[c] + shift[c] + residual )
+ *     kind: 0 = 3x3x3 stride 1 pad 1; 1 = 3x3x3 stride 2 pad 1; 2 = transposed 3x3x3 stride 2 pad 1 out_pad 1;
+ *           3 = 1x3x3 (per-plane) pad (0,1,1); 4 = 1x1x1.
+ *     x [B,D,H,W,Cin] bf16; w packed by dpf_conv3d_weight_elems / the host packer (layout [tap][Cin/8][Npad][8]);
+ *     y [B,Do,Ho,Wo,y_cstride] bf16 (or fp32 when y_f32), written at channel offset y_coff;
+ *     residual has y's layout (bf16, or fp32 when y_f32).  scale/shift may be NULL (1 / 0).
+ *     stats (optional, fp32 [2*Cout], NOT zeroed by the call) accumulates sum / sum-of-squares of the raw
+ *     convolution output per channel (training-mode BatchNorm).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct dpf_conv3d_args {
+  int kind;
+  int B, D, H, W;          /* input grid */
+  int Cin, Cout;           /* Cin in {32,64}; Cout in {1..64} */
+  const void* x;
+  const void* w;
+  void* y;
+  int y_f32, y_cstride, y_coff;
+  const float* scale;
+  const float* shift;
+  const void* residual;
+  int relu;
+  float* stats;
+} dpf_conv3d_args;
+int dpf_conv3d_fwd(const dpf_conv3d_args* args, void* stream);
+/* number of bf16 elements of the packed weight buffer for (kind, Cin, Cout) */
+long long dpf_conv3d_weight_elems(int kind, int Cin, int Cout);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (4) Fused trilinear x4 upsample (align_corners) + softmax over 4*D bins + soft-argmin.
+ *     Replaces F.interpolate(..., 'trilinear') (src/model/stereodpnet/modules.py:327-334) + disp_regression.forward
+ *     (modules.py:352-362) without materialising the [B,4D,H,W] tensor.
+ *     cost [B,D,H4,W4] fp32 -> disp [B,4*H4,4*W4] fp32; prob (optional, may be NULL) [B,4D,4*H4,4*W4] fp32.
+ *     bin k has value mindisp + k*step.
+ * ------------------------------------------------------------------------------------------------- */
+int dpf_regress_fwd(const float* cost, float* disp, float* prob, int B, int D, int H4, int W4, float mindisp, float step,
+                    void* stream);
+/* dcost [B,D,H4,W4] (zeroed by the call) from ddisp [B,H,W]; recomputes the softmax. */
+int dpf_regress_bwd(const float* cost, const float* ddisp, float* dcost, int B, int D, int H4, int W4, float mindisp,
+                    float step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (5) ANM front end.  Replaces the nearest x0.25 down-sample, sample_with_sort and grid_maker_3d of
+ *     src/model/stereodpnet/normal_module.py:120-138,80-118,156-167.
+ *     dpf_anm_select: per quarter-res pixel take d = disp[b,4h,4w]*0.25, pick the K levels nearest to d
+ *       (ties -> lower level index; documented rule), sorted ascending -> idx [B,K,H4,W4] int32,
+ *       ray-scaled depth coordinates coord [B,K,H4,W4,3] fp32 (un-normalised) and per-sample min/max [B,2] fp32
+ *       (minmax must be initialised to +inf/-inf by the caller).
+ *     dpf_anm_gather: fv[b,k,h,w,0:C] = out3[b,idx,h,w,:], fv[..., C:C+3] = (coord-min)/(max-min+1e-6),
+ *       fv[..., C+3:Cpad] = 0.   out3 [B,D,H4,W4,C] bf16; fv [B,K,H4,W4,Cpad] bf16.
+ * ------------------------------------------------------------------------------------------------- */
+int dpf_anm_select(const float* disp, const float* kinv, const float* abvalue, const float* levels_host, int* idx,
+                   float* coord, float* minmax, int B, int D, int K, int H4, int W4, void* stream);
+int dpf_anm_gather(const void* out3, const int* idx, const float* coord, const float* minmax, void* fv, int B, int D,
+                   int K, int H4, int W4, int C, int Cpad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (6) 3-D deformable convolution (D3D), 3x3x3 stride 1 pad 1, groups 1.  Replaces DCN.deform_conv_forward
+ *     (src/module/dcn3d/src/deform_conv.h:10-29 -> src/cuda/deform_conv_cuda.cu:18-126 and the im2col kernel
+ *     src/cuda/deform_im2col_cuda.cuh:192-265) without the [27*Cin, B*D*H*W] column buffer.
+ *     x [B,D,H,W,Cin_pad] bf16, offset [B,D,H,W,81] fp32 ((d,h,w) per tap), w packed like kind 0 with Cin_pad,
+ *     y = relu?( dconv * scale + shift ) -> [B,D,H,W,Cout] bf16.
+ * ------------------------------------------------------------------------------------------------- */
+int dpf_dcn3d_fwd(const void* x, const float* offset, const void* w, const float* scale, const float* shift, void* y,
+                  int B, int D, int H, int W, int Cin_pad, int Cout, int relu, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPF_SM100_H */

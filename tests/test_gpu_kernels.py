@@ -1,0 +1,216 @@
+"""GPU parity: each sm_100a kernel, called through the C ABI, against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import dpf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CR = O.cost_range(-4, 12, 8)
+SHIFTS = [int(c) for c in CR]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from dualpixelface_b200 import ops as _ops
+    _ops.lib()
+    return _ops
+
+
+def feat(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.relu(torch.randn(*shape, generator=g)).to(torch.bfloat16)
+
+
+def nhwc(x):      # [B,C,H,W] -> [B,H,W,C] contiguous
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def ndhwc(x):     # [B,C,D,H,W] -> [B,D,H,W,C]
+    return x.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def from_ndhwc(y):
+    return y.permute(0, 4, 1, 2, 3).contiguous()
+
+
+def rel_err(got, want):
+    got, want = got.float().cpu(), want.float().cpu()
+    return ((got - want).abs().max() / want.abs().max().clamp_min(1e-6)).item()
+
+
+# ---------------------------------------------------------------------------------------------------- volume
+@pytest.mark.parametrize("shape", [(2, 32, 12, 10), (1, 32, 37, 75), (2, 32, 112, 112)])
+def test_costvol_concat_diff_exact(ops, shape):
+    ref, tgt = feat(shape, 21), feat(shape, 22)
+    want_c = O.psm_concat_volume(ref.float(), tgt.float(), CR)
+    want_d = O.diff_volume(ref.float(), tgt.float(), CR).to(torch.bfloat16)
+    got_c = ops.costvol_fwd(nhwc(ref).cuda(), nhwc(tgt).cuda(), SHIFTS, "concat")
+    got_d = ops.costvol_fwd(nhwc(ref).cuda(), nhwc(tgt).cuda(), SHIFTS, "diff")
+    assert torch.equal(from_ndhwc(got_c).float().cpu(), want_c)                      # bit-exact copy semantics
+    assert torch.equal(from_ndhwc(got_d).cpu(), want_d)                               # one bf16 rounding of an fp32 difference
+
+
+@pytest.mark.parametrize("groups", [8, 16, 32])
+def test_costvol_gwc(ops, groups):
+    ref, tgt = feat((2, 32, 20, 33), 23), feat((2, 32, 20, 33), 24)
+    want = O.psm_gwc_volume(ref.float(), tgt.float(), CR, groups)
+    got = ops.costvol_fwd(nhwc(ref).cuda(), nhwc(tgt).cuda(), SHIFTS, "gwc", groups)
+    assert rel_err(from_ndhwc(got), want) < 1e-2                                      # 1 bf16 ulp of the output
+
+
+@pytest.mark.parametrize("mode,groups", [("concat", 0), ("diff", 0), ("gwc", 8)])
+def test_costvol_bwd(ops, mode, groups):
+    ref, tgt = feat((2, 32, 14, 19), 25), feat((2, 32, 14, 19), 26)
+    r, t = ref.float().requires_grad_(True), tgt.float().requires_grad_(True)
+    vol = {"concat": lambda: O.psm_concat_volume(r, t, CR), "diff": lambda: O.diff_volume(r, t, CR),
+           "gwc": lambda: O.psm_gwc_volume(r, t, CR, groups)}[mode]()
+    g = torch.Generator().manual_seed(27)
+    dvol = torch.randn(vol.shape, generator=g).to(torch.bfloat16)
+    vol.backward(dvol.float())
+    dref, dtgt = ops.costvol_bwd(nhwc(ref).cuda(), nhwc(tgt).cuda(), ndhwc(dvol).cuda(), SHIFTS, mode, groups)
+    assert rel_err(dref.permute(0, 3, 1, 2), r.grad) < 1e-2
+    assert rel_err(dtgt.permute(0, 3, 1, 2), t.grad) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------- regression
+@pytest.mark.parametrize("shape", [(2, 8, 20, 28), (1, 8, 70, 105)])
+def test_regress_fwd_bwd(ops, shape):
+    g = torch.Generator().manual_seed(51)
+    cost = (torch.randn(*shape, generator=g) * 2.0).requires_grad_(True)
+    bins = O.disparity_bins(-4, 12, 8)
+    full = O.upsample_cost(cost.unsqueeze(1))
+    want_d, want_p = O.regression(full, bins)
+    disp, prob = ops.regress_fwd(cost.detach().cuda(), -4.0, 0.5, want_prob=True)
+    assert (disp.cpu() - want_d).abs().max().item() < 1e-3 * 11.5
+    assert (prob.cpu() - want_p).abs().max().item() < 1e-4
+    gd = torch.randn(want_d.shape, generator=g)
+    want_d.backward(gd)
+    dcost = ops.regress_bwd(cost.detach().cuda(), gd.cuda(), -4.0, 0.5)
+    assert rel_err(dcost, cost.grad) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ convolution
+def conv_case(ops, cin, cout, kind, shape, seed, with_affine=True, residual=False, relu=True, out_f32=False):
+    b, d, h, w = shape
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(b, cin, d, h, w, generator=g).to(torch.bfloat16)
+    ks = {0: (3, 3, 3), 3: (1, 3, 3), 4: (1, 1, 1)}[kind]
+    wt = (torch.randn(cout, cin, *ks, generator=g) * (2.0 / (cin * ks[0] * ks[1] * ks[2])) ** 0.5).to(torch.bfloat16)
+    scale = (torch.rand(cout, generator=g) + 0.5) if with_affine else None
+    shift = (torch.randn(cout, generator=g) * 0.2) if with_affine else None
+    res = torch.randn(b, cout, d, h, w, generator=g) if residual else None
+    if res is not None and not out_f32:
+        res = res.to(torch.bfloat16)
+    want = F.conv3d(x.float(), wt.float(), padding=tuple(k // 2 for k in ks))
+    if with_affine:
+        want = want * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
+    if residual:
+        want = want + res.float()
+    if relu:
+        want = F.relu(want)
+    got = ops.conv3d(ndhwc(x).cuda(), ops.pack_conv_weight(wt.cuda()), kind, cout,
+                     scale.cuda() if with_affine else None, shift.cuda() if with_affine else None,
+                     ndhwc(res).cuda() if residual else None, relu, out_f32=out_f32)
+    torch.cuda.synchronize()
+    return rel_err(from_ndhwc(got), want)
+
+
+def test_conv_pointwise_is_plain_gemm(ops):
+    """1x1x1 conv == one GEMM: isolates the UMMA descriptor / TMEM plumbing from the tap addressing."""
+    assert conv_case(ops, 32, 32, 4, (1, 2, 16, 24), 1, with_affine=False, relu=False) < 1e-2
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 32), (64, 32), (32, 64), (32, 16), (64, 16)])
+def test_conv_3x3x3(ops, cin, cout):
+    assert conv_case(ops, cin, cout, 0, (1, 4, 16, 24), 2) < 1e-2
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 37, 53), (1, 2, 70, 105), (1, 1, 5, 7), (3, 3, 16, 8)])
+def test_conv_ragged_shapes(ops, shape):
+    assert conv_case(ops, 32, 32, 0, shape, 3, residual=True) < 1e-2
+    assert conv_case(ops, 64, 32, 0, shape, 4, residual=False) < 1e-2
+
+
+def test_conv_head_fp32_out(ops):
+    assert conv_case(ops, 32, 1, 0, (2, 8, 20, 30), 5, with_affine=False, residual=True, relu=False, out_f32=True) < 1e-2
+
+
+@pytest.mark.parametrize("kind", [3, 4])
+def test_conv_planar_pointwise(ops, kind):
+    assert conv_case(ops, 32, 32, kind, (2, 3, 21, 35), 6) < 1e-2
+
+
+def test_conv_many_tiles_persistent(ops):
+    """More tiles than SMs: exercises the ring / TMEM phase wrap-around of the persistent CTAs."""
+    assert conv_case(ops, 32, 32, 0, (2, 8, 112, 112), 7, residual=True) < 1e-2
+
+
+# --------------------------------------------------------------------------------------------------------- ASM
+@pytest.mark.parametrize("direction", ["forward", "backward"])
+def test_asm_sample(ops, direction):
+    from dualpixelface_b200.shift_tables import build_tables
+    x = feat((2, 32, 16, 24), 11)
+    want = torch.stack(O.subpixel_samples(x.float(), -1.0, direction), 1)           # [B,S,C,H,W]
+    tb = {k: v.cuda() for k, v in build_tables(16, 24, -1.0, direction).items()}
+    got = ops.asm_sample(nhwc(x).cuda(), tb)                                          # [B,S,H,W,C]
+    err = (got.permute(0, 1, 4, 2, 3).float().cpu() - want).abs().max().item()
+    assert err < 2e-2 * want.abs().max().item()
+
+
+def test_channel_stats_and_blend(ops):
+    g = torch.Generator().manual_seed(91)
+    b, s, h, w, c = 2, 3, 13, 17, 32
+    smp = torch.randn(b, s, h, w, c, generator=g).to(torch.bfloat16)
+    lg = torch.randn(b, s, h, w, c, generator=g).to(torch.bfloat16)
+    st = ops.channel_stats(lg.cuda()).cpu()
+    lf = lg.float().reshape(b, -1, c)
+    assert torch.allclose(st[..., 0], lf.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[..., 1], (lf * lf).sum(1), rtol=1e-4, atol=1e-2)
+    a = torch.rand(b, c, generator=g) + 0.5
+    dd = torch.randn(b, c, generator=g) * 0.3
+    vol = torch.zeros(b, 8, h, w, 64, dtype=torch.bfloat16, device="cuda")
+    ops.asm_blend(smp.cuda(), lg.cuda(), a.cuda(), dd.cuda(), vol, 0, 8, 32)
+    gate = torch.sigmoid(lg.float() * a.view(b, 1, 1, 1, c) + dd.view(b, 1, 1, 1, c))
+    want = (smp.float() * torch.softmax(gate, dim=1)).mean(1)
+    for d in (0, 7):
+        assert (vol[:, d, :, :, 32:].float().cpu() - want).abs().max().item() < 2e-2
+    assert vol[..., :32].abs().max().item() == 0
+
+
+# --------------------------------------------------------------------------------------------------------- ANM
+def test_anm_select_gather(ops):
+    g = torch.Generator().manual_seed(61)
+    b, h4, w4, c = 2, 10, 12, 32
+    out3 = torch.randn(b, c, 8, h4, w4, generator=g).to(torch.bfloat16)
+    disp = torch.rand(b, 4 * h4, 4 * w4, generator=g) * 14.0 - 4.5
+    from dualpixelface_b200.synthetic import synthetic_batch
+    batch = synthetic_batch(b, 4 * h4, 4 * w4, seed=3)
+    kq = batch["K"].clone()
+    kq[:, :2] = kq[:, :2] / 4.0
+    kinv = torch.inverse(kq).contiguous()
+    idx, coord, minmax = ops.anm_select(disp.cuda(), kinv.cuda(), batch["abvalue"].cuda(), [float(v) for v in CR], 4)
+    fv = ops.anm_gather(ndhwc(out3).cuda(), idx, coord, minmax, 64)
+    dq = F.interpolate(disp.unsqueeze(1), scale_factor=0.25, mode="nearest") * 0.25
+    crt = torch.as_tensor(CR, dtype=torch.float32).view(1, -1, 1, 1)
+    want_idx = O.anm_select_levels(dq, crt, 4)
+    assert torch.equal(idx.cpu().long(), want_idx)                                    # generic (off-level) disparities: exact
+    sel_disp = torch.gather(crt.expand(b, 8, h4, w4), 1, want_idx)
+    want_coord = O.anm_coord_volume(sel_disp, batch["K"], batch["abvalue"])          # [B,K,3,H,W]
+    got_coord = fv[..., 32:35].float().cpu().permute(0, 1, 4, 2, 3)
+    assert (got_coord - want_coord).abs().max().item() < 1e-2
+    want_cost = torch.gather(out3.permute(0, 2, 1, 3, 4), 1, want_idx.unsqueeze(2).expand(-1, -1, c, -1, -1))
+    assert torch.equal(fv[..., :32].cpu().permute(0, 1, 4, 2, 3), want_cost)
+    assert fv[..., 35:].abs().max().item() == 0
+
+
+def test_anm_select_tie_rule(ops):
+    """d exactly on a level: the K-th pick is a two-way tie; the documented rule is 'lower level index wins'."""
+    b, h4, w4 = 1, 4, 4
+    disp = torch.full((b, 16, 16), 4.0)            # quarter-res 1.0 == level 4 -> candidates {3,4,5} + tie {2,6}
+    kinv = torch.eye(3).unsqueeze(0).contiguous()
+    ab = torch.tensor([[32.98, -26996.49]])
+    idx, _, _ = ops.anm_select(disp.cuda(), kinv.cuda(), ab.cuda(), [float(v) for v in CR], 4)
+    assert idx[0, :, 0, 0].cpu().tolist() == [2, 3, 4, 5]
