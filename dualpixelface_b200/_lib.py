@@ -25,6 +25,7 @@ class ConvArgs(C.Structure):
         ("y_f32", c_int), ("y_cstride", c_int), ("y_coff", c_int),
         ("scale", c_void_p), ("shift", c_void_p), ("residual", c_void_p),
         ("relu", c_int), ("stats", c_void_p),
+        ("x_cstride", c_int), ("x_coff", c_int), ("res_pre", c_int),
     ]
 
 
@@ -45,7 +46,7 @@ SIGNATURES = {
     "dpf_regress_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "dpf_anm_select": (c_int, [c_void_p, c_void_p, c_void_p, c_float_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dpf_anm_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "dpf_dcn3d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dpf_dcn3d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

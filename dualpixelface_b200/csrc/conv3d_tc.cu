@@ -1,28 +1,37 @@
 // 3-D convolution as an implicit GEMM on tcgen05 tensor cores (sm_100a), BN / bias / residual / ReLU fused.
 //
-// Replaces nn.Conv3d + BatchNorm3d (+ReLU)(+add) of the reference's PSMNetHGAggregation
+// Replaces nn.Conv3d / nn.ConvTranspose3d + BatchNorm3d (+ReLU)(+add) of the reference's PSMNetHGAggregation
 // (src/model/stereodpnet/modules.py:204-337; convbn_3d in src/module/asm/basics.py:32-36) and the mask convolutions of
 // MaskingAttention (src/module/asm/asm.py:141-146).
 //
-// GEMM view per tap: D[128 voxels x Cout] += A[128 voxels x Cin] * W_tap[Cin x Cout], 27 taps (x Cin/16 k-steps)
+// GEMM view per tap: D[128 voxels x Cout] += A[128 voxels x Cin] * W_tap[Cin x Cout]; taps (x Cin/16 k-steps)
 // accumulate into one TMEM tile.  Activations are bf16 NDHWC.
 //
-// Shared-memory layout (the point of the design).  An output block is 16 rows (h) x 8 columns (w) of ONE depth
-// plane = 128 GEMM rows.  Input planes are staged per (tile, depth plane) as a halo window of 18 x (WT+2) voxels,
-// stored channel-chunk-planar:   slot[chunk c8][row][col][8 channels] (16 B per voxel per chunk).  In the UMMA
-// no-swizzle K-major canonical layout a row of the A operand is 16 B, 8 consecutive rows are contiguous (= 8
-// consecutive w), and consecutive 8-row groups are SBO apart (= the window row pitch), k-chunks are LBO apart
-// (= the chunk-plane pitch).  Every one of the 27 taps is then just a different START ADDRESS into the same
-// staged window: no im2col, no per-tap copies, no padding waste -- each input voxel is loaded once per tile
-// (plus halo) with 16-byte LDGSTS (zero-filled outside the image, which implements the conv padding), and is
-// read 27 times by the tensor core straight from shared memory.
+// Shared-memory layout (the point of the design).  A GEMM block is 16 rows (h) x 8 columns (w) of ONE depth plane
+// = 128 GEMM rows.  Input planes are staged per (tile, depth plane) as a halo window, stored channel-chunk-planar:
+//   slot[chunk c8][sub-plane][row][col][8 channels]   (16 B per voxel per chunk).
+// In the UMMA no-swizzle K-major canonical layout a row of the A operand is 16 B, 8 consecutive rows are contiguous
+// (= 8 consecutive w), consecutive 8-row groups are SBO apart (= the window row pitch) and k-chunks are LBO apart
+// (= the chunk-plane pitch).  Every tap is then just a different START ADDRESS into the same staged window: no
+// im2col, no per-tap copies, no padding waste -- each input voxel is loaded once per tile (plus halo) with 16-byte
+// LDGSTS (zero-filled outside the image, which implements the conv padding) and read by the tensor core straight
+// from shared memory for every tap.
+//   stride 1      : window 18 x (WT+2), tap (kd,kh,kw) -> plane d+kd-1, offset (kh, kw).
+//   stride 2      : the producer de-interleaves the 33 x (2WT+1) window into 4 parity sub-planes, so that the rows
+//                   2*ho+kh-1 of consecutive outputs are again consecutive: tap -> sub-plane (kh&1, kw&1), offset
+//                   (kh>>1, kw>>1), plane 2*do+kd-1.
+//   transposed s2 : GEMM rows are INPUT voxels q; the 8 output parity classes (rd,rh,rw) are 8 sub-convolutions with
+//                   1/2/2/4/2/4/4/8 live taps (27 in total): out[2q+r] += in[q + (r==1 && k==0)] * W[k], k in
+//                   {1} (r=0) or {0,2} (r=1).  One work item = one output plane (rd fixed), 4 (rh,rw) accumulators.
 //
-// Pipeline: 4 producer warps (cp.async) -> ring of NS plane slots (full/empty mbarriers) -> 1 MMA thread
-// (tcgen05.mma, accumulators double-buffered in TMEM) -> 4 epilogue warps (tcgen05.ld, scale/shift, residual, ReLU,
-// bf16 pack, 128-bit stores).  Persistent CTAs, one per SM; weights of all taps stay resident in shared memory.
+// Pipeline: 4 producer warps (cp.async) -> ring of NS plane slots (full/empty mbarriers) -> MMA warp (one elected
+// lane issues tcgen05.mma, all operands warp-uniform; accumulators double-buffered in TMEM) -> 4 epilogue warps
+// (tcgen05.ld, scale/shift, residual, ReLU, bf16 pack, 128-bit stores).  Persistent CTAs, one per SM; the weights of
+// all taps stay resident in shared memory.
 #include "../../include/dpf_sm100.h"
 #include "dpf_common.cuh"
 #include "dpf_ptx.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -32,8 +41,17 @@ constexpr int kEpiWarps = 4;
 constexpr int kProdWarps = 4;
 constexpr int kMmaWarp = kEpiWarps;                                   // warp 4
 constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;          // 288
-constexpr int kRows = 18;                                             // 16 output rows + halo
 constexpr int kMaxTaps = 27;
+
+enum { GEO_S1 = 0, GEO_S2 = 1, GEO_T2 = 2 };
+
+struct Tap {
+  signed char dd;        // input plane relative to the work item's base plane
+  unsigned char cls;     // accumulator class (transposed: rh*2+rw; else 0)
+  unsigned short aoff;   // start offset inside a slot chunk-plane, in 16-byte units
+  unsigned short widx;   // weight tile index
+  unsigned short pad;
+};
 
 struct ConvKParams {
   const __nv_bfloat16* x;
@@ -42,21 +60,28 @@ struct ConvKParams {
   const float* scale;
   const float* shift;
   const void* residual;
-  float* stats;
-  int B, D, H, W;
-  int cout, y_f32, y_cstride, y_coff, relu;
-  int ntaps, min_dd;
+  int B, D, H, W;                 // input grid
+  int Do, Ho, Wo;                 // output grid
+  int Mh, Mw, items;              // GEMM-row grid (h, w) and work items (planes) per tile
+  int x_cstride, x_coff;          // channel stride / offset of the input tensor
+  int cout, y_f32, y_cstride, y_coff, relu, res_pre;
+  int nw;                         // number of weight tiles resident
   int tiles_h, tiles_w, ntiles;
-  signed char tap_dd[kMaxTaps];
-  signed char tap_dh[kMaxTaps];
-  signed char tap_dw[kMaxTaps];
+  int debug;                      // DPF_CONV_DEBUG bits: 1 skip loads, 2 skip MMAs, 4 skip stores (timing experiments)
+  int ntaps[2];
+  Tap taps[2][kMaxTaps];          // program per work-item parity (only the transposed kind uses program 1)
 };
 
-template <int CIN, int NPAD, int WT, int NS>
+template <int GEO, int CIN, int NPAD, int WT, int NS>
 struct Cfg {
   static constexpr int NCH = CIN / 8;
-  static constexpr int WP = WT + 2;
-  static constexpr int PLANE_BYTES = kRows * WP * 16;
+  static constexpr int RWIN = (GEO == GEO_S1) ? 18 : (GEO == GEO_S2 ? 33 : 17);          // window rows loaded
+  static constexpr int CWIN = (GEO == GEO_S1) ? WT + 2 : (GEO == GEO_S2 ? 2 * WT + 1 : WT + 1);
+  static constexpr int NSUB = (GEO == GEO_S2) ? 4 : 1;
+  static constexpr int RS = (GEO == GEO_S1) ? 18 : 17;                                     // rows per sub-plane
+  static constexpr int WPS = (GEO == GEO_S1) ? WT + 2 : WT + 1;                            // row pitch (positions)
+  static constexpr int SUB_POS = RS * WPS;
+  static constexpr int PLANE_BYTES = NSUB * SUB_POS * 16;
   // chunk-plane pitch: 16-B multiple whose residue mod 128 spreads a quarter-warp's cp.async writes over all banks
   static constexpr int WANT = (NCH == 4) ? 32 : 16;
   static constexpr int CH_STRIDE = PLANE_BYTES + ((WANT - (PLANE_BYTES % 128)) + 128) % 128;
@@ -64,18 +89,29 @@ struct Cfg {
   static constexpr int W_TAP_BYTES = NCH * NPAD * 16;
   static constexpr int W_BYTES = kMaxTaps * W_TAP_BYTES;
   static constexpr int NBLK = WT / 8;
-  static constexpr int ACC_COLS = NBLK * NPAD;
+  static constexpr int NCLS = (GEO == GEO_T2) ? 4 : 1;
+  static constexpr int ACC_COLS = NCLS * NBLK * NPAD;
   static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
   static constexpr int KSTEPS = CIN / 16;
+  static constexpr int LO_OFF = (GEO == GEO_T2) ? 0 : -1;       // lowest input plane of a work item, relative to its base
   static constexpr int SMEM_BYTES = W_BYTES + NS * SLOT_BYTES + 2 * NPAD * 4 + (2 * NS + 4) * 8 + 16 + 128;
   static_assert(2 * ACC_COLS <= 512, "accumulators do not fit TMEM");
   static_assert(CH_STRIDE % 16 == 0, "chunk pitch must be a 16-byte multiple");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+  static_assert(SLOT_BYTES / 16 < 65536, "tap offsets are 16-bit");
 };
 
-template <int CIN, int NPAD, int WT, int NS>
+// Base input plane and tap program of a work item (= one output plane of the tile), per geometry.
+template <int GEO>
+__device__ __forceinline__ void item_planes(int item, int& base, int& prog) {
+  if (GEO == GEO_S1) { base = item; prog = 0; }
+  else if (GEO == GEO_S2) { base = 2 * item; prog = 0; }
+  else { base = item >> 1; prog = item & 1; }
+}
+
+template <int GEO, int CIN, int NPAD, int WT, int NS>
 __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_constant__ ConvKParams p) {
-  using C = Cfg<CIN, NPAD, WT, NS>;
+  using C = Cfg<GEO, CIN, NPAD, WT, NS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
   uint8_t* s_w = smem;
@@ -93,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
 
   // ---- one-time setup ---------------------------------------------------------------------------------
   {
-    const int nbytes = p.ntaps * C::W_TAP_BYTES;
+    const int nbytes = p.nw * C::W_TAP_BYTES;
     const uint4* src = reinterpret_cast<const uint4*>(p.w);
     uint4* dst = reinterpret_cast<uint4*>(s_w);
     for (int i = threadIdx.x; i < nbytes / 16; i += kThreads) dst[i] = __ldg(src + i);
@@ -128,21 +164,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   if (warp > kMmaWarp) {
     // =================================== producers: global -> shared ring ===================================
     const int ptid = threadIdx.x - (kMmaWarp + 1) * 32;          // 0..127
-    constexpr int PIECES_PER_ROW = C::WP * C::NCH;
-    constexpr int PIECES = kRows * PIECES_PER_ROW;
+    constexpr int PIECES_PER_ROW = C::CWIN * C::NCH;
+    constexpr int PIECES = C::RWIN * PIECES_PER_ROW;
     uint32_t g = 0;
     int prev_slot = -1;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int tw = tile % p.tiles_w;
       const int th = (tile / p.tiles_w) % p.tiles_h;
       const int b = tile / (p.tiles_w * p.tiles_h);
-      const int h0 = th * 16 - 1, w0 = tw * WT - 1;              // window origin (with halo)
+      // window origin in input coordinates
+      const int h0 = (GEO == GEO_S1) ? th * 16 - 1 : (GEO == GEO_S2 ? th * 32 - 1 : th * 16);
+      const int w0 = (GEO == GEO_S1) ? tw * WT - 1 : (GEO == GEO_S2 ? tw * 2 * WT - 1 : tw * WT);
       for (int pl = 0; pl < D; ++pl, ++g) {
         const int slot = g % NS;
         const uint32_t ph = (g / NS) & 1u;
         mbar_wait(&bar_empty[slot], ph ^ 1u);
         const uint32_t sbase = smem_u32(s_slots + slot * C::SLOT_BYTES);
-        const __nv_bfloat16* xplane = p.x + (static_cast<size_t>(b) * D + pl) * H * static_cast<size_t>(W) * CIN;
+        const __nv_bfloat16* xplane = p.x + (static_cast<size_t>(b) * D + pl) * H * static_cast<size_t>(W) * p.x_cstride + p.x_coff;
 #pragma unroll 4
         for (int q = ptid; q < PIECES; q += kProdWarps * 32) {
           const int row = q / PIECES_PER_ROW;
@@ -151,8 +189,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           const int c8 = rem - col * C::NCH;
           const int h = h0 + row, w = w0 + col;
           const bool ok = (h >= 0) && (h < H) && (w >= 0) && (w < W);
-          const __nv_bfloat16* src = ok ? (xplane + (static_cast<size_t>(h) * W + w) * CIN + c8 * 8) : p.x;
-          cp_async16_zfill(sbase + c8 * C::CH_STRIDE + (row * C::WP + col) * 16, src, ok);
+          const __nv_bfloat16* src = ok ? (xplane + (static_cast<size_t>(h) * W + w) * p.x_cstride + c8 * 8) : p.x;
+          int pos;
+          if (GEO == GEO_S2) pos = ((row & 1) * 2 + (col & 1)) * C::SUB_POS + (row >> 1) * C::WPS + (col >> 1);
+          else pos = row * C::WPS + col;
+          if (!(p.debug & 1)) cp_async16_zfill(sbase + c8 * C::CH_STRIDE + pos * 16, src, ok);
         }
         cp_async_commit();
         if (prev_slot >= 0) {                                    // complete the previous plane (one group of lag)
@@ -171,118 +212,147 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       if (lane == 0) mbar_arrive(&bar_full[prev_slot]);
     }
   } else if (warp == kMmaWarp) {
-    // =================================== MMA issuer (one thread) ==========================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(128, NPAD);
-      const uint32_t wbase = smem_u32(s_w);
-      uint32_t g_base = 0, it = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const int tw = tile % p.tiles_w;
-        const int nblk = min(C::NBLK, (W - tw * WT + 7) >> 3);
-        int waited = -1;
-        for (int d = 0; d < D; ++d, ++it) {
-          const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
-          mbar_wait(&bar_tempty[as], aph ^ 1u);
-          tc_fence_after_sync();
-          bool first = true;
-          for (int t = 0; t < p.ntaps; ++t) {
-            const int pin = d + p.tap_dd[t];
-            if (pin < 0 || pin >= D) continue;
-            const uint32_t gp = g_base + pin;
-            const uint32_t slot = gp % NS;
-            if (pin > waited) {
-              mbar_wait(&bar_full[slot], (gp / NS) & 1u);
-              tc_fence_after_sync();
-              waited = pin;
-            }
-            const uint32_t a0 = smem_u32(s_slots + slot * C::SLOT_BYTES) + (p.tap_dh[t] * C::WP + p.tap_dw[t]) * 16;
-            const uint32_t b0 = wbase + t * C::W_TAP_BYTES;
+    // ============ MMA issuer: the whole warp runs the (warp-uniform) control flow, one elected lane issues ============
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(128, NPAD);
+    const uint32_t wbase = smem_u32(s_w);
+    const uint32_t sbase0 = smem_u32(s_slots);
+    // descriptor templates: everything but the 14-bit start address
+    const uint64_t adesc_hi = umma_desc_nosw(0, C::CH_STRIDE, C::WPS * 16);
+    const uint64_t bdesc_hi = umma_desc_nosw(0, NPAD * 16, 128);
+    const bool leader = elect_one();
+    uint32_t g_base = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int tw = tile % p.tiles_w;
+      const int nblk = min(C::NBLK, (p.Mw - tw * WT + 7) >> 3);
+      int waited = -1;
+      for (int item = 0; item < p.items; ++item, ++it) {
+        const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+        mbar_wait(&bar_tempty[as], aph ^ 1u);
+        tc_fence_after_sync();
+        int base, prog;
+        item_planes<GEO>(item, base, prog);
+        uint32_t started = 0u;                                   // per accumulator class: has it been written yet?
+        const int nt = p.ntaps[prog];
+        for (int t = 0; t < nt; ++t) {
+          const Tap tp = p.taps[prog][t];
+          const int pin = base + tp.dd;
+          if (pin < 0 || pin >= D) continue;
+          const uint32_t gp = g_base + pin;
+          const uint32_t slot = gp % NS;
+          if (pin > waited) {
+            mbar_wait(&bar_full[slot], (gp / NS) & 1u);
+            tc_fence_after_sync();
+            waited = pin;
+          }
+          const uint32_t a0 = ((sbase0 + slot * C::SLOT_BYTES) >> 4) + tp.aoff;
+          const uint32_t b0 = (wbase + tp.widx * C::W_TAP_BYTES) >> 4;
+          const uint32_t acc0 = tmem_base + (as * C::NCLS + tp.cls) * C::NBLK * NPAD;
+          const bool fresh = ((started >> tp.cls) & 1u) == 0u;
+          if (leader && !(p.debug & 2)) {
 #pragma unroll
             for (int ks = 0; ks < C::KSTEPS; ++ks) {
-              const uint64_t bdesc = umma_desc_nosw(b0 + ks * 2 * NPAD * 16, NPAD * 16, 128);
-              for (int blk = 0; blk < nblk; ++blk) {
-                const uint64_t adesc = umma_desc_nosw(a0 + ks * 2 * C::CH_STRIDE + blk * 128, C::CH_STRIDE, C::WP * 16);
-                umma_bf16(tmem_base + (as * C::NBLK + blk) * NPAD, adesc, bdesc, idesc, !(first && ks == 0));
+              const uint64_t bdesc = bdesc_hi | static_cast<uint64_t>((b0 + ks * 2 * NPAD) & 0x3FFF);
+#pragma unroll
+              for (int blk = 0; blk < C::NBLK; ++blk) {
+                if (blk < nblk) {
+                  const uint64_t adesc = adesc_hi | static_cast<uint64_t>((a0 + ks * 2 * (C::CH_STRIDE >> 4) + blk * 8) & 0x3FFF);
+                  umma_bf16(acc0 + blk * NPAD, adesc, bdesc, idesc, !(fresh && ks == 0));
+                }
               }
             }
-            first = false;
           }
-          umma_commit(&bar_tfull[as]);
-          // input planes no later output plane of this tile needs
-          const int rel = d + p.min_dd;
-          if (d == D - 1) {
-            for (int q = max(rel, 0); q < D; ++q) umma_commit(&bar_empty[(g_base + q) % NS]);
-          } else if (rel >= 0) {
-            umma_commit(&bar_empty[(g_base + rel) % NS]);
-          }
+          started |= 1u << tp.cls;
         }
-        g_base += D;
+        // release the input planes that no later work item of this tile needs
+        const int lo_cur = max(base + C::LO_OFF, 0);
+        int lo_next = D;
+        if (item + 1 < p.items) {
+          int nb, np;
+          item_planes<GEO>(item + 1, nb, np);
+          lo_next = min(max(nb + C::LO_OFF, 0), D);
+        }
+        if (leader) {
+          umma_commit(&bar_tfull[as]);
+          for (int q = lo_cur; q < lo_next; ++q) umma_commit(&bar_empty[(g_base + q) % NS]);
+        }
+        __syncwarp();
       }
+      g_base += D;
     }
-    __syncwarp();
   } else {
     // =================================== epilogue: TMEM -> registers -> global ============================
     uint32_t it = 0;
     const int m = warp * 32 + lane;
     const int hrow = m >> 3, wcol = m & 7;
+    constexpr int OS = (GEO == GEO_T2) ? 2 : 1;                  // output stride of the GEMM-row grid
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int tw = tile % p.tiles_w;
       const int th = (tile / p.tiles_w) % p.tiles_h;
       const int b = tile / (p.tiles_w * p.tiles_h);
-      const int nblk = min(C::NBLK, (W - tw * WT + 7) >> 3);
-      const int h = th * 16 + hrow;
-      for (int d = 0; d < D; ++d, ++it) {
+      const int nblk = min(C::NBLK, (p.Mw - tw * WT + 7) >> 3);
+      const int mh = th * 16 + hrow;
+      for (int item = 0; item < p.items; ++item, ++it) {
         const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
         mbar_wait(&bar_tfull[as], aph);
         tc_fence_after_sync();
-        for (int blk = 0; blk < nblk; ++blk) {
-          const int w = tw * WT + blk * 8 + wcol;
-          const bool ok = (h < H) && (w < W);
-          const size_t vox = ((static_cast<size_t>(b) * D + d) * H + h) * static_cast<size_t>(W) + w;
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + (as * C::NBLK + blk) * NPAD;
+#pragma unroll 1
+        for (int cls = 0; cls < C::NCLS; ++cls) {
+          const int oh = mh * OS + (cls >> 1);
+#pragma unroll 1
+          for (int blk = 0; blk < nblk; ++blk) {
+            const int mw = tw * WT + blk * 8 + wcol;
+            const int ow = mw * OS + (cls & 1);
+            const bool ok = (mh < p.Mh) && (mw < p.Mw) && (oh < p.Ho) && (ow < p.Wo);
+            const size_t vox = ((static_cast<size_t>(b) * p.Do + item) * p.Ho + oh) * static_cast<size_t>(p.Wo) + ow;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + ((as * C::NCLS + cls) * C::NBLK + blk) * NPAD;
 #pragma unroll
-          for (int c0 = 0; c0 < NPAD; c0 += 16) {
-            uint32_t v[16];
-            __syncwarp();                                        // tcgen05.ld is .sync.aligned: keep the warp converged
-            tmem_ld16(taddr + c0, v);
-            tmem_ld_wait();
-            if (!ok || c0 >= p.cout) continue;
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * s_scale[c0 + j] + s_shift[c0 + j];
-            if (p.y_f32) {
-              float* yo = reinterpret_cast<float*>(p.y) + vox * p.y_cstride + p.y_coff + c0;
-              const float* ro = p.residual ? reinterpret_cast<const float*>(p.residual) + vox * p.y_cstride + p.y_coff + c0 : nullptr;
+            for (int c0 = 0; c0 < NPAD; c0 += 16) {
+              uint32_t v[16];
+              __syncwarp();                                      // tcgen05.ld is .sync.aligned: keep the warp converged
+              tmem_ld16(taddr + c0, v);
+              tmem_ld_wait();
+              if (!ok || c0 >= p.cout || (p.debug & 4)) continue;
               const int n = min(16, p.cout - c0);
-              for (int j = 0; j < n; ++j) {
-                float val = f[j] + (ro ? ro[j] : 0.f);
-                if (p.relu) val = fmaxf(val, 0.f);
-                yo[j] = val;
-              }
-            } else {
-              __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + vox * p.y_cstride + p.y_coff + c0;
-              const int n = min(16, p.cout - c0);                // multiple of 8 (checked on the host)
-              if (p.residual) {
-                const __nv_bfloat16* ro = reinterpret_cast<const __nv_bfloat16*>(p.residual) + vox * p.y_cstride + p.y_coff + c0;
-                for (int j8 = 0; j8 < n; j8 += 8) {
-                  const uint4 r = *reinterpret_cast<const uint4*>(ro + j8);
-                  f[j8 + 0] += bf16_lo(r.x); f[j8 + 1] += bf16_hi(r.x);
-                  f[j8 + 2] += bf16_lo(r.y); f[j8 + 3] += bf16_hi(r.y);
-                  f[j8 + 4] += bf16_lo(r.z); f[j8 + 5] += bf16_hi(r.z);
-                  f[j8 + 6] += bf16_lo(r.w); f[j8 + 7] += bf16_hi(r.w);
-                }
-              }
-              if (p.relu) {
+              float f[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-              }
-              for (int j8 = 0; j8 < n; j8 += 8) {
-                uint4 o;
-                o.x = pack_bf16x2(f[j8 + 0], f[j8 + 1]);
-                o.y = pack_bf16x2(f[j8 + 2], f[j8 + 3]);
-                o.z = pack_bf16x2(f[j8 + 4], f[j8 + 5]);
-                o.w = pack_bf16x2(f[j8 + 6], f[j8 + 7]);
-                *reinterpret_cast<uint4*>(yo + j8) = o;
+              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+              if (p.y_f32) {
+                float* yo = reinterpret_cast<float*>(p.y) + vox * p.y_cstride + p.y_coff + c0;
+                const float* ro = p.residual ? reinterpret_cast<const float*>(p.residual) + vox * p.y_cstride + p.y_coff + c0 : nullptr;
+                for (int j = 0; j < n; ++j) {
+                  float val = f[j];
+                  if (ro && p.res_pre) val += ro[j];
+                  val = val * s_scale[c0 + j] + s_shift[c0 + j];
+                  if (ro && !p.res_pre) val += ro[j];
+                  if (p.relu) val = fmaxf(val, 0.f);
+                  yo[j] = val;
+                }
+              } else {
+                __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + vox * p.y_cstride + p.y_coff + c0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = f[j] * s_scale[c0 + j] + s_shift[c0 + j];
+                if (p.residual) {
+                  const __nv_bfloat16* ro = reinterpret_cast<const __nv_bfloat16*>(p.residual) + vox * p.y_cstride + p.y_coff + c0;
+                  for (int j8 = 0; j8 < n; j8 += 8) {
+                    const uint4 r = *reinterpret_cast<const uint4*>(ro + j8);
+                    f[j8 + 0] += bf16_lo(r.x); f[j8 + 1] += bf16_hi(r.x);
+                    f[j8 + 2] += bf16_lo(r.y); f[j8 + 3] += bf16_hi(r.y);
+                    f[j8 + 4] += bf16_lo(r.z); f[j8 + 5] += bf16_hi(r.z);
+                    f[j8 + 6] += bf16_lo(r.w); f[j8 + 7] += bf16_hi(r.w);
+                  }
+                }
+                if (p.relu) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                for (int j8 = 0; j8 < n; j8 += 8) {              // n is a multiple of 8 (checked on the host)
+                  uint4 o;
+                  o.x = pack_bf16x2(f[j8 + 0], f[j8 + 1]);
+                  o.y = pack_bf16x2(f[j8 + 2], f[j8 + 3]);
+                  o.z = pack_bf16x2(f[j8 + 4], f[j8 + 5]);
+                  o.w = pack_bf16x2(f[j8 + 6], f[j8 + 7]);
+                  *reinterpret_cast<uint4*>(yo + j8) = o;
+                }
               }
             }
           }
@@ -303,14 +373,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   }
 }
 
-template <int CIN, int NPAD, int WT, int NS>
-int launch(const ConvKParams& kp_in, cudaStream_t st) {
-  using C = Cfg<CIN, NPAD, WT, NS>;
-  ConvKParams kp = kp_in;
-  kp.tiles_h = (kp.H + 15) / 16;
-  kp.tiles_w = (kp.W + WT - 1) / WT;
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+template <int GEO, int CIN, int NPAD, int WT, int NS>
+int launch(ConvKParams kp, cudaStream_t st) {
+  using C = Cfg<GEO, CIN, NPAD, WT, NS>;
+  // tap start offsets inside a slot chunk-plane (16-byte units); the builders stash (dh << 8 | dw) in aoff
+  for (int pr = 0; pr < 2; ++pr)
+    for (int t = 0; t < kp.ntaps[pr]; ++t) {
+      Tap& tp = kp.taps[pr][t];
+      const int dh = tp.aoff >> 8, dw = tp.aoff & 0xFF;
+      int off;
+      if (GEO == GEO_S2) off = ((dh & 1) * 2 + (dw & 1)) * C::SUB_POS + (dh >> 1) * C::WPS + (dw >> 1);
+      else off = dh * C::WPS + dw;
+      tp.aoff = static_cast<unsigned short>(off);
+    }
+  kp.tiles_h = (kp.Mh + 15) / 16;
+  kp.tiles_w = (kp.Mw + WT - 1) / WT;
   kp.ntiles = kp.B * kp.tiles_h * kp.tiles_w;
-  auto kern = conv3d_tc_kernel<CIN, NPAD, WT, NS>;
+  auto kern = conv3d_tc_kernel<GEO, CIN, NPAD, WT, NS>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -324,6 +406,16 @@ int launch(const ConvKParams& kp_in, cudaStream_t st) {
 
 int npad_for(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : 64); }
 
+inline Tap mk_tap(int dd, int cls, int dh, int dw, int widx) {
+  Tap t;
+  t.dd = static_cast<signed char>(dd);
+  t.cls = static_cast<unsigned char>(cls);
+  t.aoff = static_cast<unsigned short>((dh << 8) | dw);
+  t.widx = static_cast<unsigned short>(widx);
+  t.pad = 0;
+  return t;
+}
+
 }  // namespace
 
 extern "C" long long dpf_conv3d_weight_elems(int kind, int Cin, int Cout) {
@@ -335,14 +427,16 @@ extern "C" int dpf_conv3d_fwd(const dpf_conv3d_args* a, void* stream) {
   DPF_REQUIRE(a != nullptr, "dpf_conv3d_fwd: null args");
   DPF_REQUIRE(a->x && a->w && a->y, "dpf_conv3d_fwd: null tensor pointer");
   DPF_REQUIRE(DPF_ALIGNED16(a->x) && DPF_ALIGNED16(a->w) && DPF_ALIGNED16(a->y), "dpf_conv3d_fwd: pointers must be 16-byte aligned");
-  DPF_REQUIRE(a->kind == 0 || a->kind == 3 || a->kind == 4, "dpf_conv3d_fwd: kind %d not built yet (0, 3, 4 are)", a->kind);
-  DPF_REQUIRE(a->Cin == 32 || a->Cin == 64, "dpf_conv3d_fwd: Cin=%d must be 32 or 64", a->Cin);
+  DPF_REQUIRE(a->kind >= 0 && a->kind <= 4, "dpf_conv3d_fwd: kind %d not in 0..4", a->kind);
+  DPF_REQUIRE(a->Cin == 32 || a->Cin == 64, "dpf_conv3d_fwd: Cin=%d must be 32 or 64 (per launch)", a->Cin);
   DPF_REQUIRE(a->Cout >= 1 && a->Cout <= 64, "dpf_conv3d_fwd: Cout=%d must be in [1,64] (split wider layers on the host)", a->Cout);
-  DPF_REQUIRE(a->Cin == 32 || a->Cout <= 32, "dpf_conv3d_fwd: Cin=64 supports Cout<=32 per launch (split on the host)");
   DPF_REQUIRE(a->B > 0 && a->D > 0 && a->D <= 64 && a->H > 0 && a->W > 0, "dpf_conv3d_fwd: bad shape");
   DPF_REQUIRE(a->y_f32 || (a->Cout % 8 == 0 && a->y_cstride % 8 == 0 && a->y_coff % 8 == 0),
               "dpf_conv3d_fwd: bf16 output needs Cout, y_cstride, y_coff multiples of 8");
   DPF_REQUIRE(a->y_cstride >= a->y_coff + a->Cout, "dpf_conv3d_fwd: y_cstride too small");
+  const int x_cstride = a->x_cstride > 0 ? a->x_cstride : a->Cin;
+  DPF_REQUIRE(x_cstride % 8 == 0 && a->x_coff % 8 == 0 && a->x_coff + a->Cin <= x_cstride, "dpf_conv3d_fwd: bad input channel window");
+  DPF_REQUIRE(a->stats == nullptr, "dpf_conv3d_fwd: fused batch statistics are not built yet");
   ConvKParams kp{};
   kp.x = reinterpret_cast<const __nv_bfloat16*>(a->x);
   kp.w = reinterpret_cast<const __nv_bfloat16*>(a->w);
@@ -350,40 +444,79 @@ extern "C" int dpf_conv3d_fwd(const dpf_conv3d_args* a, void* stream) {
   kp.scale = a->scale;
   kp.shift = a->shift;
   kp.residual = a->residual;
-  kp.stats = a->stats;
   kp.B = a->B; kp.D = a->D; kp.H = a->H; kp.W = a->W;
+  kp.x_cstride = x_cstride; kp.x_coff = a->x_coff;
   kp.cout = a->Cout; kp.y_f32 = a->y_f32; kp.y_cstride = a->y_cstride; kp.y_coff = a->y_coff; kp.relu = a->relu;
+  kp.res_pre = a->res_pre;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("DPF_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
+    kp.debug = dbg;
+  }
+  int geo = GEO_S1;
   int t = 0;
-  if (a->kind == 0) {
+  if (a->kind == 0 || a->kind == 3 || a->kind == 4) {
+    kp.Do = a->D; kp.Ho = a->H; kp.Wo = a->W;
+    if (a->kind == 0) {
+      for (int kd = 0; kd < 3; ++kd)
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw, ++t) kp.taps[0][t] = mk_tap(kd - 1, 0, kh, kw, t);
+    } else if (a->kind == 3) {
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw, ++t) kp.taps[0][t] = mk_tap(0, 0, kh, kw, t);
+    } else {
+      kp.taps[0][t] = mk_tap(0, 0, 1, 1, 0);
+      t = 1;
+    }
+    kp.ntaps[0] = t; kp.nw = t;
+    kp.Mh = kp.Ho; kp.Mw = kp.Wo; kp.items = kp.Do;
+  } else if (a->kind == 1) {
+    geo = GEO_S2;
+    kp.Do = (a->D + 1) / 2; kp.Ho = (a->H + 1) / 2; kp.Wo = (a->W + 1) / 2;
     for (int kd = 0; kd < 3; ++kd)
       for (int kh = 0; kh < 3; ++kh)
-        for (int kw = 0; kw < 3; ++kw, ++t) {
-          kp.tap_dd[t] = static_cast<signed char>(kd - 1);
-          kp.tap_dh[t] = static_cast<signed char>(kh);
-          kp.tap_dw[t] = static_cast<signed char>(kw);
-        }
-    kp.min_dd = -1;
-  } else if (a->kind == 3) {
-    for (int kh = 0; kh < 3; ++kh)
-      for (int kw = 0; kw < 3; ++kw, ++t) {
-        kp.tap_dd[t] = 0;
-        kp.tap_dh[t] = static_cast<signed char>(kh);
-        kp.tap_dw[t] = static_cast<signed char>(kw);
-      }
-    kp.min_dd = 0;
+        for (int kw = 0; kw < 3; ++kw, ++t) kp.taps[0][t] = mk_tap(kd - 1, 0, kh, kw, t);
+    kp.ntaps[0] = 27; kp.nw = 27;
+    kp.Mh = kp.Ho; kp.Mw = kp.Wo; kp.items = kp.Do;
   } else {
-    kp.tap_dd[0] = 0; kp.tap_dh[0] = 1; kp.tap_dw[0] = 1;
-    t = 1;
-    kp.min_dd = 0;
+    geo = GEO_T2;
+    kp.Do = 2 * a->D; kp.Ho = 2 * a->H; kp.Wo = 2 * a->W;
+    // out[2q+r] += in[q + o] * W[k]:  r=0 -> (k=1,o=0);  r=1 -> (k=0,o=1), (k=2,o=0)
+    const int ks[2][2] = {{1, -1}, {0, 2}};
+    const int os[2][2] = {{0, 0}, {1, 0}};
+    const int nk[2] = {1, 2};
+    for (int rd = 0; rd < 2; ++rd) {
+      int n = 0;
+      for (int id = 0; id < nk[rd]; ++id)
+        for (int rh = 0; rh < 2; ++rh)
+          for (int ih = 0; ih < nk[rh]; ++ih)
+            for (int rw = 0; rw < 2; ++rw)
+              for (int iw = 0; iw < nk[rw]; ++iw, ++n) {
+                const int kd = ks[rd][id], kh = ks[rh][ih], kw = ks[rw][iw];
+                kp.taps[rd][n] = mk_tap(os[rd][id], rh * 2 + rw, os[rh][ih], os[rw][iw], (kd * 3 + kh) * 3 + kw);
+              }
+      kp.ntaps[rd] = n;
+    }
+    kp.nw = 27;
+    kp.Mh = a->H; kp.Mw = a->W; kp.items = kp.Do;
   }
-  kp.ntaps = t;
-  DPF_REQUIRE(a->stats == nullptr, "dpf_conv3d_fwd: fused batch statistics are not built yet");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int npad = npad_for(a->Cout);
-  if (a->Cin == 32 && npad == 32) return launch<32, 32, 24, 5>(kp, st);
-  if (a->Cin == 32 && npad == 16) return launch<32, 16, 24, 5>(kp, st);
-  if (a->Cin == 32 && npad == 64) return launch<32, 64, 8, 6>(kp, st);
-  if (a->Cin == 64 && npad == 32) return launch<64, 32, 8, 5>(kp, st);
-  if (a->Cin == 64 && npad == 16) return launch<64, 16, 8, 5>(kp, st);
-  return dpf::fail("dpf_conv3d_fwd: no kernel for Cin=%d Cout=%d", a->Cin, a->Cout);
+  if (geo == GEO_S1) {
+    DPF_REQUIRE(a->Cin == 32 || a->Cout <= 32, "dpf_conv3d_fwd: Cin=64 supports Cout<=32 per launch (split on the host)");
+    if (a->Cin == 32 && npad == 32) return launch<GEO_S1, 32, 32, 24, 5>(kp, st);
+    if (a->Cin == 32 && npad == 16) return launch<GEO_S1, 32, 16, 24, 5>(kp, st);
+    if (a->Cin == 32 && npad == 64) return launch<GEO_S1, 32, 64, 8, 6>(kp, st);
+    if (a->Cin == 64 && npad == 32) return launch<GEO_S1, 64, 32, 8, 5>(kp, st);
+    if (a->Cin == 64 && npad == 16) return launch<GEO_S1, 64, 16, 8, 5>(kp, st);
+  } else if (geo == GEO_S2) {
+    DPF_REQUIRE(a->Cin == 32 && a->Cout <= 32, "dpf_conv3d_fwd: stride-2 kind supports Cin=32, Cout<=32 per launch (split on the host)");
+    if (npad == 32) return launch<GEO_S2, 32, 32, 8, 4>(kp, st);
+    if (npad == 16) return launch<GEO_S2, 32, 16, 8, 4>(kp, st);
+  } else {
+    DPF_REQUIRE(a->Cout <= 32, "dpf_conv3d_fwd: transposed kind supports Cout<=32 per launch (split on the host)");
+    if (a->Cin == 64 && npad == 32) return launch<GEO_T2, 64, 32, 8, 4>(kp, st);
+    if (a->Cin == 32 && npad == 32) return launch<GEO_T2, 32, 32, 8, 4>(kp, st);
+  }
+  return dpf::fail("dpf_conv3d_fwd: no kernel for kind=%d Cin=%d Cout=%d", a->kind, a->Cin, a->Cout);
 }

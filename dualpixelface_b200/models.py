@@ -1,0 +1,151 @@
+"""STEREODPNET / PSMNET with the reference's model-class contract on the sm_100a hot path.
+
+Contract kept (src/model/stereodpnet/mainmodel.py:21-177, src/model/psmnet/mainmodel.py:31-181 of the reference):
+``CLS(option)``; sub-module names ``feature_extraction, cost_volume, aggregation, normal_estimator, regression_layer``
+(=> identical state_dict keys); ``forward(batch: dict) -> dict`` with ``pred_depth [B,n,H,W]``, ``prob_depth``,
+``pred_normal [B,1,3,H,W] | None``, ``ref_feature [B,H4,W4]``; the Lightning-style hooks used by main.py.
+pytorch_lightning is not available here, so ``runner.LightningModule`` supplies the few hooks the repo uses.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import modules as M
+from .runner import LightningModule, optimizer_selector, scheduler_selector
+from .synthetic import synthetic_batch
+
+
+class _StereoBase(LightningModule):
+    predict_normal = False
+
+    def _common_init(self, option):
+        self.option = option
+        self.mindisp = option.model.mindisp
+        self.maxdisp = option.model.maxdisp
+        self.level = option.model.level
+        self.encoder_autocast = True          # bf16 autocast for the cuDNN encoder; tests switch it off to isolate the hot path
+
+    # ---- the hot path -------------------------------------------------------------------------------------
+    def _select_views(self, batch):
+        """reference / target image selection, mainmodel.py:70-83."""
+        if "groupname" in batch and not self.training:
+            swap = batch["groupname"][0] == "2020-2-9_group20"
+        else:
+            swap = bool(self.option.dataset.flip_lr)
+        return (batch["right"], batch["left"]) if swap else (batch["left"], batch["right"])
+
+    def _features(self, ref_img, tgt_img):
+        b = ref_img.shape[0]
+        x = torch.cat([ref_img, tgt_img], 0)
+        if self.encoder_autocast:
+            x = x.contiguous(memory_format=torch.channels_last)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                f = self.feature_extraction(x)
+        else:
+            f = self.feature_extraction(x.float())
+        f = f.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()      # [2B,H4,W4,C] channels-last bf16
+        return f[:b], f[b:]
+
+    def _mark(self, name):
+        """Optional per-stage CUDA events (bench.py sets self.stage_events = [] to collect them)."""
+        ev = getattr(self, "stage_events", None)
+        if ev is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.append((name, e))
+
+    def forward(self, batch):
+        if not batch["left"].is_cuda:
+            raise RuntimeError("the sm_100a hot path needs CUDA tensors; there is no CPU implementation")
+        if self.training:
+            raise NotImplementedError("the sm_100a training path (batch-statistics BatchNorm, aggregation backward) is not "
+                                      "built yet; call .eval().  There is deliberately no fallback.")
+        ref_img, tgt_img = self._select_views(batch)
+        self._mark("start")
+        ref_fea, tgt_fea = self._features(ref_img, tgt_img)
+        self._mark("encoder")
+        cost = self.cost_volume(ref_fea, tgt_fea)
+        self._mark("cost_volume")
+        cost_i, cost = self.aggregation(cost)
+        self._mark("aggregation")
+        cost_f, cost_p = self.regression_layer(cost_i)
+        self._mark("regression")
+        normal = None
+        if self.predict_normal:
+            normals, _, _ = self.normal_estimator([cost[0]], [cost_f[0]], batch)
+            normal = torch.stack(normals, 1)                             # 'n b c h w -> b n c h w'
+            self._mark("normal_branch")
+        results = {"pred_depth": torch.stack(cost_f, 1),
+                   "prob_depth": torch.stack(cost_p, 1) if cost_p[0] is not None else None,
+                   "pred_normal": normal,
+                   "ref_feature": ref_fea.float().max(-1)[0]}
+        return results
+
+    def refresh(self):
+        """Re-pack kernel-layout weights after parameters changed (load_state_dict calls it)."""
+        for m in self.modules():
+            if m is not self and hasattr(m, "refresh"):
+                m.refresh()
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        sd = dict(state_dict)
+        sd.pop("normal_estimator.grid", None)       # lazily registered by the reference (normal_module.py:91-99)
+        out = super().load_state_dict(sd, strict=strict, **kw)
+        self.refresh()
+        return out
+
+    # ---- Lightning-style hooks used by main.py ------------------------------------------------------------
+    def _synthetic_loader(self, training, batch_size):
+        h, w = getattr(self.option, "synthetic_size", (448, 448))
+        n = int(getattr(self.option, "synthetic_batches", 2))
+        return [synthetic_batch(batch_size, h, w, training=training, seed=i) for i in range(n)]
+
+    def train_dataloader(self):
+        return self._synthetic_loader(True, self.option.batch_size)
+
+    def val_dataloader(self):
+        return self._synthetic_loader(False, 1)
+
+    def test_dataloader(self):
+        return self._synthetic_loader(False, self.option.batch_size)
+
+    def training_step(self, batch, batch_idx):
+        results = self.forward(batch)
+        losses = {k: v for k, v in results.items() if "loss" in k and k != "final_loss"}
+        for k, v in losses.items():
+            self.log(k, v, prog_bar=True)
+        return {"loss": results["final_loss"], "log": losses}
+
+    def validation_step(self, batch, batch_idx):
+        return self.forward(batch)
+
+    def test_step(self, batch, batch_idx):
+        return self.forward(batch)
+
+    def configure_optimizers(self):
+        opt = optimizer_selector(self.parameters(), self.option)
+        sch = scheduler_selector(opt, self.option)
+        return [opt], ([sch] if sch is not None else [])
+
+
+class STEREODPNET(_StereoBase):
+    def __init__(self, option):
+        super().__init__()
+        self._common_init(option)
+        self.predict_normal = bool(option.model.predict_normal)
+        self.feature_extraction = M.SDPFeatureExtraction(option)
+        self.cost_volume = M.CostVolumeSDP(option, self.mindisp, self.maxdisp)
+        self.aggregation = M.PSMNetHGAggregation(option.model.inplanes)
+        self.normal_estimator = M.ANM(option, self.mindisp, self.maxdisp) if self.predict_normal else None
+        self.regression_layer = M.disp_regression(self.mindisp, self.maxdisp, self.level)
+
+
+class PSMNET(_StereoBase):
+    def __init__(self, option):
+        super().__init__()
+        self._common_init(option)
+        self.feature_extraction = M.PSMFeatureExtraction(option)
+        self.cost_volume = M.CostVolumePSM(option, self.mindisp, self.maxdisp)
+        self.aggregation = M.PSMNetHGAggregation(option)
+        self.regression_layer = M.disp_regression(self.mindisp, self.maxdisp, self.level)

@@ -1,0 +1,503 @@
+"""Host-side mirror of the reference's stage modules for StereoDPNet and PSMNet.
+
+Every class keeps the reference's constructor arguments, sub-module attribute names and therefore its
+``state_dict`` key layout (checkpoints load unchanged), but ``forward`` runs the hot path through libdpf_sm100.so:
+
+  CostVolume            src/model/stereodpnet/modules.py:137-200, src/model/psmnet/modules.py:174-275
+  PSMNetHGAggregation   src/model/stereodpnet/modules.py:204-337 (PSMNet twin: psmnet/modules.py:279-416)
+  disp_regression       src/model/stereodpnet/modules.py:341-362
+  ANM                   src/model/stereodpnet/normal_module.py:32-194
+
+The 2-D encoders (feature_extraction) are adjacent to the hot path and stay PyTorch / cuDNN.
+Hot-path activations are bf16, channels-last ([B,D,H,W,C]); parameters stay fp32 nn.Parameters and are folded / packed
+into kernel layout on first use (``refresh()`` after a weight update).  There is no CPU path: calling ``forward`` on CPU
+tensors raises.  Training-mode forward (batch-statistics BatchNorm) and the backward kernels of the aggregation are not
+built yet -- ``forward`` raises in train mode rather than silently using another implementation.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import layers, ops, shift_tables
+from .layers import KIND_1x1x1, KIND_1x3x3, KIND_3x3x3, KIND_S2, KIND_T2, TCConv3d, fold_bn
+
+
+def _require_eval(m: nn.Module):
+    if m.training:
+        raise NotImplementedError(f"{type(m).__name__}: the sm_100a training path (batch-statistics BatchNorm, backward "
+                                  "kernels) is not built yet; call .eval().  There is deliberately no fallback.")
+
+
+def _cb2(cin, cout, k, stride, pad, dil):
+    """conv + BN pair with the reference's padding rule (src/module/asm/basics.py:17-22)."""
+    return nn.Sequential(nn.Conv2d(cin, cout, k, stride, dil if dil > 1 else pad, dil, bias=False), nn.BatchNorm2d(cout))
+
+
+def _cb3(cin, cout, stride=1):
+    return nn.Sequential(nn.Conv3d(cin, cout, 3, stride, 1, bias=False), nn.BatchNorm3d(cout))
+
+
+def _tb3(cin, cout):
+    return nn.Sequential(nn.ConvTranspose3d(cin, cout, 3, padding=1, output_padding=1, stride=2, bias=False), nn.BatchNorm3d(cout))
+
+
+def cost_range(mindisp, maxdisp, level) -> np.ndarray:
+    return np.arange(int(level), dtype=np.float64) * ((maxdisp / 4.0 - mindisp / 4.0) / float(level)) + mindisp / 4.0
+
+
+# ======================================================================================================
+# 2-D encoders (PyTorch / cuDNN; adjacent to the hot path)
+# ======================================================================================================
+class _SepConv(nn.Module):
+    """depthwise 3x3 + pointwise + BN + PReLU (reference: src/module/asm/basics.py:39-60)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.depthwise = nn.Conv2d(c, c, 3, padding=1, groups=c, bias=False)
+        self.pointwise = nn.Conv2d(c, c, 1, bias=False)
+        self.bn = nn.BatchNorm2d(c)
+        self.prelu = nn.PReLU(init=0.05)
+
+    def forward(self, x):
+        return self.prelu(self.bn(self.pointwise(self.depthwise(x))))
+
+
+class DPBlock(nn.Module):
+    """src/model/stereodpnet/modules.py:21-54."""
+
+    def __init__(self, c, ratio_s, ratio_t, reluw=0.05):
+        super().__init__()
+        self.conv1 = nn.Sequential(_cb2(c, c, 3, 1, 1, 1), nn.PReLU(init=reluw))
+        self.conv2 = nn.Sequential(_cb2(c, c, 3, 1, 1, 1), nn.PReLU(init=reluw))
+        self.conv_dilate = nn.ModuleList([_cb2(c, c, 3, 1, 2 * i + 1, 2 * i + 1) for i in range(3)])
+        self.conv3 = _cb2(3 * c, c, 3, 1, 1, 1)
+        self.conv4 = nn.Sequential(_cb2(c, ratio_t * c, 3, ratio_s, ratio_s, 2), nn.PReLU(init=reluw))
+        self.conv5 = _SepConv(ratio_t * c)
+        self.conv_skip = nn.Conv2d(c, ratio_t * c, 1, ratio_s)
+        self.prelu = nn.PReLU(init=reluw)
+
+    def forward(self, x):
+        a = self.conv1(x)
+        y = self.conv2(a)
+        y = self.conv3(torch.cat([m(y) for m in self.conv_dilate], 1))
+        y = self.conv5(self.conv4(self.prelu(y + a)))
+        return y + self.conv_skip(x)
+
+
+class SDPFeatureExtraction(nn.Module):
+    """feature_extraction of StereoDPNet, src/model/stereodpnet/modules.py:58-134 -> [B,32,H/4,W/4]."""
+
+    def __init__(self, option):
+        super().__init__()
+        from torchvision.ops import FeaturePyramidNetwork
+        c, n = option.model.inplanes, option.model.block_stack
+        self.blockstack = n
+        self.firstconv = nn.Sequential(_cb2(option.model.input_channel, c, 3, 2, 1, 1), nn.ReLU(inplace=True),
+                                       _cb2(c, c, 3, 1, 1, 1), nn.ReLU(inplace=True),
+                                       _cb2(c, c, 3, 1, 1, 1), nn.ReLU(inplace=True))
+        self.block1 = DPBlock(c, 2, 1)
+        self.interblock1 = nn.ModuleList([DPBlock(c, 1, 1) for _ in range(n)])
+        self.block2 = DPBlock(c, 2, 2)
+        self.interblock2 = nn.ModuleList([DPBlock(2 * c, 1, 1) for _ in range(n)])
+        self.block3 = DPBlock(2 * c, 2, 2)
+        self.fpn = FeaturePyramidNetwork([c, 2 * c, 4 * c], c, extra_blocks=None)
+        self.lastconv = nn.Sequential(_cb2(3 * c, 2 * c, 3, 1, 1, 1), nn.ReLU(inplace=True),
+                                      _cb2(2 * c, c, 3, 1, 1, 1), nn.ReLU(inplace=True))
+
+    def forward(self, x):
+        o1 = self.block1(self.firstconv(x))
+        o2 = o1
+        for m in self.interblock1:
+            o2 = m(o2)
+        o2 = self.block2(o2)
+        o3 = o2
+        for m in self.interblock2:
+            o3 = m(o3)
+        o3 = self.block3(o3)
+        f = self.fpn(OrderedDict(layer1=o1, layer2=o2, layer3=o3))
+        up = lambda t, s: F.interpolate(t, scale_factor=s, mode="bilinear", align_corners=True)
+        return self.lastconv(torch.cat([f["layer1"], up(f["layer2"], 2), up(f["layer3"], 4)], 1))
+
+
+class _ResBlock(nn.Module):
+    """BasicBlock of the PSMNet encoder, src/model/psmnet/modules.py:14-34."""
+
+    def __init__(self, cin, c, stride, downsample, pad, dil):
+        super().__init__()
+        self.conv1 = nn.Sequential(_cb2(cin, c, 3, stride, pad, dil), nn.ReLU(inplace=True))
+        self.conv2 = _cb2(c, c, 3, 1, pad, dil)
+        self.downsample = downsample
+
+    def forward(self, x):
+        y = self.conv2(self.conv1(x))
+        return y + (self.downsample(x) if self.downsample is not None else x)
+
+
+class PSMFeatureExtraction(nn.Module):
+    """feature_extraction of PSMNet (SPP), src/model/psmnet/modules.py:64-171 -> [B,32,H/4,W/4]."""
+
+    def __init__(self, option):
+        super().__init__()
+        c = option.model.inplanes
+        self._in = c
+        self.firstconv = nn.Sequential(_cb2(3, c, 3, 2, 1, 1), nn.ReLU(inplace=True), _cb2(c, c, 3, 1, 1, 1),
+                                       nn.ReLU(inplace=True), _cb2(c, c, 3, 1, 1, 1), nn.ReLU(inplace=True))
+        self.layer1 = self._stack(c, 3, 1, 1, 1)
+        self.layer2 = self._stack(2 * c, c // 2, 2, 1, 1)
+        self.layer3 = self._stack(4 * c, 3, 1, 1, 1)
+        self.layer4 = self._stack(4 * c, 3, 1, 1, 2)
+        for i, k in enumerate((2 * c, c, c // 2, c // 4), start=1):
+            setattr(self, f"branch{i}", nn.Sequential(nn.AvgPool2d((k, k), stride=(k, k)), _cb2(4 * c, c, 1, 1, 0, 1),
+                                                       nn.ReLU(inplace=True)))
+        self.lastconv = nn.Sequential(_cb2(10 * c, 4 * c, 3, 1, 1, 1), nn.ReLU(inplace=True),
+                                      nn.Conv2d(4 * c, c, 1, bias=False))
+
+    def _stack(self, planes, blocks, stride, pad, dil):
+        down = None
+        if stride != 1 or self._in != planes:
+            down = nn.Sequential(nn.Conv2d(self._in, planes, 1, stride, bias=False), nn.BatchNorm2d(planes))
+        mods = [_ResBlock(self._in, planes, stride, down, pad, dil)]
+        self._in = planes
+        mods += [_ResBlock(planes, planes, 1, None, pad, dil) for _ in range(1, blocks)]
+        return nn.Sequential(*mods)
+
+    def forward(self, x):
+        raw = self.layer2(self.layer1(self.firstconv(x)))
+        skip = self.layer4(self.layer3(raw))
+        size = skip.shape[-2:]
+        br = [F.interpolate(getattr(self, f"branch{i}")(skip), size=size, mode="bilinear", align_corners=True) for i in (1, 2, 3, 4)]
+        return self.lastconv(torch.cat([raw, skip, br[3], br[2], br[1], br[0]], 1))
+
+
+# ======================================================================================================
+# cost volumes
+# ======================================================================================================
+class MaskingAttention(nn.Module):
+    """Parameter container with the reference's names (src/module/asm/asm.py:131-156); evaluated by CostVolumeSDP."""
+
+    def __init__(self, nin, act="sigmoid", feature_fetch=False):
+        super().__init__()
+        self.normalize = nn.InstanceNorm3d(nin, affine=True)
+        self.mask_convs = nn.Sequential(nn.Conv3d(nin, nin, (1, 3, 3), 1, (0, 1, 1), bias=False), nn.BatchNorm3d(nin),
+                                        nn.ReLU(inplace=True),
+                                        nn.Sequential(nn.Conv3d(nin, nin, 1, bias=False), self.normalize))
+        if act != "sigmoid" or feature_fetch:
+            raise NotImplementedError("only asm_activation='sigmoid', feature_fetch=false (the shipped config) is built")
+        self.activation = nn.Sigmoid()
+
+
+class _ShiftLayer(nn.Module):
+    """Stands in for subpixel_shift (no parameters); keeps the attribute name `shifting_layer`."""
+
+    def __init__(self, option):
+        super().__init__()
+        self.modes = (bool(option.model.nearest), bool(option.model.bilinear), bool(option.model.phase))
+
+
+class CostVolumeSDP(nn.Module):
+    """CostVolume of StereoDPNet (ASM), src/model/stereodpnet/modules.py:137-200 -> [B,D,H4,W4,2C] bf16.
+
+    ``cached_first_level=True`` (default) reproduces the reference as shipped: subpixel_shift.make_grid caches the grids
+    of its first call (src/module/asm/asm.py:29-30,56-57), so every level is sampled with costrange[0]; all D slices
+    are identical and are produced by ONE sample / attention / blend pass that writes all D slices.
+    """
+
+    def __init__(self, option, mindisp, maxdisp):
+        super().__init__()
+        self.level = int(option.model.level)
+        self.costrange = cost_range(mindisp, maxdisp, self.level)
+        self.shifting_layer = _ShiftLayer(option)
+        self.attention_layer = MaskingAttention(option.model.inplanes, act=option.model.asm_activation,
+                                                feature_fetch=option.model.feature_fetch)
+        self.cached_first_level = True
+        self._tables: Dict[tuple, dict] = {}
+        self._packed = None
+
+    def refresh(self):
+        self._packed = None
+
+    def _tab(self, h, w, disp, direction, device):
+        key = (h, w, float(disp), direction, str(device))
+        if key not in self._tables:
+            t = shift_tables.build_tables(h, w, disp, direction, self.shifting_layer.modes)
+            self._tables[key] = {k: v.to(device) for k, v in t.items()}
+        return self._tables[key]
+
+    def _pack(self):
+        if self._packed is None:
+            mc = self.attention_layer.mask_convs
+            bn = mc[1]
+            self._packed = dict(conv1=TCConv3d(mc[0].weight, KIND_1x3x3), conv2=TCConv3d(mc[3][0].weight, KIND_1x1x1),
+                                bn=fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps))
+        return self._packed
+
+    def _attend(self, samples: torch.Tensor):
+        """samples [N,S,H,W,C] -> (logits [N,S,H,W,C] bf16, IN affine a,d [N,C])."""
+        pk = self._pack()
+        m = pk["conv1"](samples, pk["bn"][0], pk["bn"][1], relu=True)
+        logits = pk["conv2"](m)
+        st = ops.channel_stats(logits)                                  # [N,C,2]
+        n = float(logits.shape[1] * logits.shape[2] * logits.shape[3])
+        mean = st[..., 0] / n
+        var = (st[..., 1] / n - mean * mean).clamp_min(0.0)
+        inorm = self.attention_layer.normalize
+        a = inorm.weight.float().unsqueeze(0) / torch.sqrt(var + inorm.eps)
+        d = inorm.bias.float().unsqueeze(0) - mean * a
+        return logits, a.contiguous(), d.contiguous()
+
+    def forward(self, ref_feat: torch.Tensor, tar_feat: torch.Tensor) -> torch.Tensor:
+        """ref/tar [B,H4,W4,C] bf16 (channels-last)."""
+        _require_eval(self)
+        b, h, w, c = ref_feat.shape
+        vol = torch.empty(b, self.level, h, w, 2 * c, device=ref_feat.device, dtype=torch.bfloat16)
+        levels = [(0, self.level, self.costrange[0])] if self.cached_first_level else \
+            [(i, 1, d) for i, d in enumerate(self.costrange)]
+        for d0, rep, disp in levels:
+            sf = ops.asm_sample(ref_feat, self._tab(h, w, disp, "forward", ref_feat.device))
+            sb = ops.asm_sample(tar_feat, self._tab(h, w, disp, "backward", ref_feat.device))
+            smp = torch.cat([sf, sb], 0)                                # [2B,S,H,W,C]
+            logits, a, dd = self._attend(smp)
+            ops.asm_blend(smp[:b], logits[:b], a[:b].contiguous(), dd[:b].contiguous(), vol, d0, rep, 0)
+            ops.asm_blend(smp[b:], logits[b:], a[b:].contiguous(), dd[b:].contiguous(), vol, d0, rep, c)
+        return vol
+
+
+class CostVolumePSM(nn.Module):
+    """CostVolume of PSMNet, src/model/psmnet/modules.py:174-275: integer shifts int(costrange) -> bf16 NDHWC volume."""
+
+    def __init__(self, option, mindisp, maxdisp):
+        super().__init__()
+        self.style = option.model.cost_volume
+        self.level = int(option.model.level)
+        self.group_num = option.model.group_num
+        self.costrange = cost_range(mindisp, maxdisp, self.level)
+        self.shifts = [int(d) for d in self.costrange]                   # truncation toward zero, modules.py:229
+        if self.style not in ("psmnet", "gwcnet", "difference"):
+            raise NotImplementedError(f"cost volume style is not defined : {self.style}")
+
+    def forward(self, ref_feat, tar_feat):
+        if self.style == "psmnet":
+            return ops.costvol_fwd(ref_feat, tar_feat, self.shifts, "concat")
+        if self.style == "difference":
+            return ops.costvol_fwd(ref_feat, tar_feat, self.shifts, "diff")
+        c = ref_feat.shape[-1]
+        assert c % self.group_num == 0, "group_num must divide the feature channels (psmnet/modules.py:217)"
+        raise NotImplementedError("gwcnet style (concat | gwc, 2C+G input channels) needs a Cin=2C+G first layer; "
+                                  "ops.costvol_fwd(..., 'gwc', G) builds the correlation volume itself")
+
+
+# ======================================================================================================
+# 3-D aggregation
+# ======================================================================================================
+class PSMNetHourglass(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv1 = nn.Sequential(_cb3(c, 2 * c, 2), nn.ReLU(inplace=True))
+        self.conv2 = _cb3(2 * c, 2 * c, 1)
+        self.conv3 = nn.Sequential(_cb3(2 * c, 2 * c, 2), nn.ReLU(inplace=True))
+        self.conv4 = nn.Sequential(_cb3(2 * c, 2 * c, 1), nn.ReLU(inplace=True))
+        self.conv5 = _tb3(2 * c, 2 * c)
+        self.conv6 = _tb3(2 * c, c)
+
+
+class PSMNetHGAggregation(nn.Module):
+    """22 Conv3d + 6 ConvTranspose3d on the tcgen05 engine, BN/ReLU/residual fused into each epilogue.
+
+    Accepts the reference's two constructor forms: StereoDPNet passes the channel count
+    (src/model/stereodpnet/modules.py:267), PSMNet the option object (src/model/psmnet/modules.py:342-349).
+    forward(volume [B,D,H4,W4,2C] bf16) -> ([cost3(,cost2,cost1)] each [B,D,H4,W4] fp32 at QUARTER resolution,
+    [out3(,out2,out1)] each [B,D,H4,W4,C] bf16); the x4 trilinear upsample is fused into disp_regression.
+    """
+
+    def __init__(self, option_or_channels):
+        super().__init__()
+        if isinstance(option_or_channels, int):
+            c, first = option_or_channels, 2 * option_or_channels
+        else:
+            o = option_or_channels
+            c = o.model.inplanes
+            first = 2 * c if o.model.cost_volume == "psmnet" else 2 * c + o.model.group_num
+        self.multiplier = 4
+        self.dres0 = nn.Sequential(_cb3(first, c), nn.ReLU(inplace=True), _cb3(c, c), nn.ReLU(inplace=True))
+        self.dres1 = nn.Sequential(_cb3(c, c), nn.ReLU(inplace=True), _cb3(c, c))
+        self.dres2, self.dres3, self.dres4 = PSMNetHourglass(c), PSMNetHourglass(c), PSMNetHourglass(c)
+        for k in (1, 2, 3):
+            setattr(self, f"classif{k}", nn.Sequential(_cb3(c, c), nn.ReLU(inplace=True), nn.Conv3d(c, 1, 3, 1, 1, bias=False)))
+        self._plan = None
+
+    def refresh(self):
+        self._plan = None
+
+    def _layer(self, seq: nn.Sequential, kind, transposed=False):
+        conv, bn = seq[0], seq[1]
+        return TCConv3d(conv.weight, kind, transposed), fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+
+    def _build(self):
+        if self._plan is not None:
+            return self._plan
+        p = {}
+        p["dres0.0"] = self._layer(self.dres0[0], KIND_3x3x3)
+        p["dres0.2"] = self._layer(self.dres0[2], KIND_3x3x3)
+        p["dres1.0"] = self._layer(self.dres1[0], KIND_3x3x3)
+        p["dres1.2"] = self._layer(self.dres1[2], KIND_3x3x3)
+        for name in ("dres2", "dres3", "dres4"):
+            hg = getattr(self, name)
+            p[name + ".conv1"] = self._layer(hg.conv1[0], KIND_S2)
+            p[name + ".conv2"] = self._layer(hg.conv2, KIND_3x3x3)
+            p[name + ".conv3"] = self._layer(hg.conv3[0], KIND_S2)
+            p[name + ".conv4"] = self._layer(hg.conv4[0], KIND_3x3x3)
+            p[name + ".conv5"] = self._layer(hg.conv5, KIND_T2, transposed=True)
+            p[name + ".conv6"] = self._layer(hg.conv6, KIND_T2, transposed=True)
+        for k in (1, 2, 3):
+            cl = getattr(self, f"classif{k}")
+            p[f"classif{k}.0"] = self._layer(cl[0], KIND_3x3x3)
+            p[f"classif{k}.2"] = (TCConv3d(cl[2].weight, KIND_3x3x3), None)
+        self._plan = p
+        return p
+
+    def _run(self, name, x, residual=None, relu=True):
+        conv, (sc, sh) = self._plan[name]
+        return conv(x, sc, sh, residual=residual, relu=relu)
+
+    def _hourglass(self, name, x, presqu, postsqu, cost0):
+        o = self._run(name + ".conv1", x)
+        pre = self._run(name + ".conv2", o, residual=postsqu, relu=True)
+        o = self._run(name + ".conv3", pre)
+        o = self._run(name + ".conv4", o)
+        post = self._run(name + ".conv5", o, residual=presqu if presqu is not None else pre, relu=True)
+        out = self._run(name + ".conv6", post, residual=cost0, relu=False)     # "+ cost0" of modules.py:315,318,321 fused
+        return out, pre, post
+
+    def forward(self, cost: torch.Tensor, all_heads: Optional[bool] = None):
+        _require_eval(self)
+        self._build()
+        c0 = self._run("dres0.0", cost)
+        c0 = self._run("dres0.2", c0)
+        r = self._run("dres1.0", c0)
+        cost0 = self._run("dres1.2", r, residual=c0, relu=False)
+        out1, pre1, post1 = self._hourglass("dres2", cost0, None, None, cost0)
+        out2, _pre2, post2 = self._hourglass("dres3", out1, pre1, post1, cost0)
+        out3, _pre3, _post3 = self._hourglass("dres4", out2, pre1, post2, cost0)
+        costs, prev = [], None
+        for k, o in ((1, out1), (2, out2), (3, out3)):
+            hfeat = self._run(f"classif{k}.0", o)
+            head, _ = self._plan[f"classif{k}.2"]
+            prev = head(hfeat, residual=prev, relu=False, out_f32=True)      # [B,D,H4,W4,1] fp32, cumulative adds
+            costs.append(prev)
+        costs = [c.squeeze(-1) for c in costs]
+        if all_heads if all_heads is not None else self.training:
+            return [costs[2], costs[1], costs[0]], [out3, out2, out1]
+        return [costs[2]], [out3]
+
+
+class disp_regression(nn.Module):
+    """Fused x4 trilinear upsample + softmax + soft-argmin (src/model/stereodpnet/modules.py:327-334,341-362).
+
+    forward(list of quarter-res costs [B,D,H4,W4] fp32) -> (disparities [B,H,W], probabilities [B,4D,H,W] or None).
+    `prob_depth` is consumed by no loss or metric of the reference; it is materialised only when want_prob is set.
+    """
+
+    def __init__(self, mindisp, maxdisp, level):
+        super().__init__()
+        self.mindisp, self.step = float(mindisp), (maxdisp - mindisp) / float(4 * level)
+        self.want_prob = False
+
+    def forward(self, x: Sequence[torch.Tensor]):
+        disps, probs = [], []
+        for cost in x:
+            assert cost.dim() == 4
+            d, p = ops.regress_fwd(cost.contiguous(), self.mindisp, self.step, self.want_prob)
+            disps.append(d)
+            probs.append(p)
+        return disps, probs
+
+
+# ======================================================================================================
+# normal branch
+# ======================================================================================================
+class DeformConvPack(nn.Module):
+    """Parameter container of DeformConvPack_dv2 (src/module/dcn3d/modules/deform_conv.py:295-321)."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin, 3, 3, 3))
+        self.bias = nn.Parameter(torch.zeros(cout))
+        nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+        self.conv_offset = nn.Conv3d(cin, 81, 3, 1, 1, bias=True)
+        nn.init.zeros_(self.conv_offset.weight)
+        nn.init.zeros_(self.conv_offset.bias)
+
+
+def _convtext(cin, cout, dil):
+    return nn.Sequential(nn.Conv2d(cin, cout, 3, 1, dil, dil, bias=False), nn.LeakyReLU(0.1, inplace=True))
+
+
+class ANM(nn.Module):
+    """Normal branch, src/model/stereodpnet/normal_module.py:32-194 (use_sampling, use_deform: the shipped config)."""
+
+    def __init__(self, option, mindisp, maxdisp):
+        super().__init__()
+        c = option.model.inplanes
+        if not (option.model.use_deform and option.model.use_sampling):
+            raise NotImplementedError("only use_deform=true, use_sampling=true (the shipped config) is built")
+        self.k = int(option.model.dsample_num)
+        self.levels = [float(v) for v in cost_range(mindisp, maxdisp, option.model.level).astype(np.float32)]
+        self.deform_conv1 = DeformConvPack(c + 3, 2 * c)
+        self.act1 = nn.Sequential(nn.BatchNorm3d(2 * c), nn.ReLU(inplace=True))
+        self.deform_conv2 = DeformConvPack(2 * c, 2 * c)
+        self.act2 = nn.Sequential(nn.BatchNorm3d(2 * c), nn.ReLU(inplace=True))
+        self.n_convs = nn.Sequential(_convtext(2 * c, 3 * c, 1), _convtext(3 * c, 3 * c, 2), _convtext(3 * c, 2 * c, 4),
+                                     _convtext(2 * c, 2 * c, 8), _convtext(2 * c, c, 1), _convtext(c, 3, 1))
+        cr = torch.arange(option.model.level) * ((maxdisp / 4.0 - mindisp / 4.0) / float(option.model.level)) + mindisp / 4.0
+        self.register_parameter("costrange", nn.Parameter(cr.view(1, -1, 1, 1), False))
+        self._plan = None
+
+    def refresh(self):
+        self._plan = None
+
+    def _build(self):
+        if self._plan is None:
+            p = {}
+            for i, (dc, act) in enumerate(((self.deform_conv1, self.act1), (self.deform_conv2, self.act2)), start=1):
+                bn = act[0]
+                cin = dc.weight.shape[1]
+                cpad = 48 if cin <= 48 else 64
+                p[f"off{i}"] = TCConv3d(dc.conv_offset.weight, KIND_3x3x3, cin_pad=64)
+                p[f"offb{i}"] = dc.conv_offset.bias.detach().float().contiguous()
+                p[f"w{i}"] = ops.pack_conv_weight(dc.weight.detach(), cin_pad=cpad)
+                p[f"cpad{i}"] = cpad
+                p[f"aff{i}"] = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, conv_bias=dc.bias)
+            self._plan = p
+        return self._plan
+
+    def forward(self, costs: Sequence[torch.Tensor], disp_maps: Sequence[torch.Tensor], batch: dict):
+        """costs: [out3] as [B,D,H4,W4,C] bf16; disp_maps: [disparity [B,H,W] fp32] -> ([normal [B,3,H,W]], offsets, offsets)."""
+        _require_eval(self)
+        p = self._build()
+        normals, off1s, off2s = [], [], []
+        for out3, disp in zip(costs, disp_maps):
+            b = out3.shape[0]
+            kq = batch["K"].float().clone()
+            kq[:, :2, :] = kq[:, :2, :] / 4.0
+            kinv = torch.inverse(kq).contiguous()
+            idx, coord, minmax = ops.anm_select(disp.contiguous(), kinv, batch["abvalue"].float().contiguous(), self.levels, self.k)
+            fv = ops.anm_gather(out3, idx, coord, minmax, 64)                          # [B,K,H4,W4,64]
+            off1 = p["off1"](fv, shift=p["offb1"], out_f32=True)
+            f1 = ops.dcn3d(fv, off1, p["w1"], p["cpad1"], p["aff1"][0], p["aff1"][1], relu=True)
+            off2 = p["off2"](f1, shift=p["offb2"], out_f32=True)
+            f2 = ops.dcn3d(f1, off2, p["w2"], p["cpad2"], p["aff2"][0], p["aff2"][1], relu=True)
+            # shared 2-D normal convs on (b*k) slices: cuDNN, bf16 channels-last (adjacent op)
+            x = f2.view(b * self.k, f2.shape[2], f2.shape[3], f2.shape[4]).permute(0, 3, 1, 2)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                x = self.n_convs(x)
+            x = torch.sigmoid(F.interpolate(x.float(), scale_factor=4, mode="bilinear", align_corners=True))
+            normals.append(x.view(b, self.k, 3, x.shape[-2], x.shape[-1]).mean(1) * 2.0 - 1.0)
+            off1s.append(off1)
+            off2s.append(off2)
+        return normals, off1s, off2s

@@ -20,8 +20,16 @@ KIND_3x3x3, KIND_S2, KIND_T2, KIND_1x3x3, KIND_1x1x1 = 0, 1, 2, 3, 4
 _MODES = {"concat": 0, "diff": 1, "gwc": 2}
 
 
+_checked = False
+
+
 def lib():
-    return _lib.load(check_device=True)
+    """The loaded library; the sm_100a device check (a slow cudaGetDeviceProperties) runs once per process."""
+    global _checked
+    if not _checked:
+        _lib.load(check_device=True)
+        _checked = True
+    return _lib.load()
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -101,10 +109,15 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None, transposed:
 
 def conv3d(x: torch.Tensor, w_packed: torch.Tensor, kind: int, cout: int, scale: Optional[torch.Tensor] = None,
            shift: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, relu: bool = False,
-           out: Optional[torch.Tensor] = None, out_f32: bool = False, y_coff: int = 0) -> torch.Tensor:
-    """y = relu?(conv(x) * scale + shift + residual); x [B,D,H,W,Cin] bf16 -> y [B,Do,Ho,Wo,Cstride]."""
+           out: Optional[torch.Tensor] = None, out_f32: bool = False, y_coff: int = 0, cin: Optional[int] = None,
+           x_coff: int = 0, res_pre: bool = False) -> torch.Tensor:
+    """One launch: y = relu?(conv(x) * scale + shift + residual); x [B,D,H,W,Cx] bf16 -> y [B,Do,Ho,Wo,Cstride].
+
+    `cin`/`x_coff` select a channel window of x; `y_coff` a channel offset of the output tensor `out`.
+    """
     _req(x, torch.bfloat16, "x"); _req(w_packed, torch.bfloat16, "w_packed")
-    b, d, h, w, cin = x.shape
+    b, d, h, w, cx = x.shape
+    cin = cin or cx
     if kind in (KIND_3x3x3, KIND_1x3x3, KIND_1x1x1):
         do, ho, wo = d, h, w
     elif kind == KIND_S2:
@@ -125,7 +138,8 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, kind: int, cout: int, scale:
                  y_f32=int(out_f32), y_cstride=out.shape[-1], y_coff=y_coff,
                  scale=scale.data_ptr() if scale is not None else None,
                  shift=shift.data_ptr() if shift is not None else None,
-                 residual=residual.data_ptr() if residual is not None else None, relu=int(relu), stats=None)
+                 residual=residual.data_ptr() if residual is not None else None, relu=int(relu), stats=None,
+                 x_cstride=cx, x_coff=x_coff, res_pre=int(res_pre))
     check(lib().dpf_conv3d_fwd(C.byref(a), _stream()), "dpf_conv3d_fwd")
     return out
 
@@ -202,6 +216,18 @@ def anm_select(disp: torch.Tensor, kinv: torch.Tensor, abvalue: torch.Tensor, le
     check(lib().dpf_anm_select(_p(disp), _p(kinv), _p(abvalue), lv, _p(idx), _p(coord), _p(minmax), b, d, k, h4, w4, _stream()),
           "dpf_anm_select")
     return idx, coord, minmax
+
+
+def dcn3d(x: torch.Tensor, offset: torch.Tensor, w_packed: torch.Tensor, cin_pad: int, scale: Optional[torch.Tensor] = None,
+          shift: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """3-D deformable conv 3x3x3 (stride 1, pad 1): x [B,D,H,W,Cs] bf16, offset [B,D,H,W,81] fp32 -> [B,D,H,W,64] bf16."""
+    _req(x, torch.bfloat16, "x"); _req(offset, torch.float32, "offset"); _req(w_packed, torch.bfloat16, "w_packed")
+    b, d, h, w, cs = x.shape
+    assert offset.shape == (b, d, h, w, 81)
+    y = torch.empty(b, d, h, w, 64, device=x.device, dtype=torch.bfloat16)
+    check(lib().dpf_dcn3d_fwd(_p(x), _p(offset), _p(w_packed), _p(scale), _p(shift), _p(y), b, d, h, w, cin_pad, cs, 64,
+                              int(relu), _stream()), "dpf_dcn3d_fwd")
+    return y
 
 
 def anm_gather(out3: torch.Tensor, idx: torch.Tensor, coord: torch.Tensor, minmax: torch.Tensor, cpad: int = 64) -> torch.Tensor:

@@ -81,6 +81,8 @@ int dpf_channel_stats(const void* x, float* stats, int B, long long P, int C, vo
  *     residual has y's layout (bf16, or fp32 when y_f32).  scale/shift may be NULL (1 / 0).
  *     stats (optional, fp32 [2*Cout], NOT zeroed by the call) accumulates sum / sum-of-squares of the raw
  *     convolution output per channel (training-mode BatchNorm).
+ *     Per-launch limits (wider layers are split on the host with y_coff / x_coff): stride-1 kinds Cin=32 -> Cout<=64,
+ *     Cin=64 -> Cout<=32; stride-2 Cin=32, Cout<=32; transposed Cin in {32,64}, Cout<=32.
  * ------------------------------------------------------------------------------------------------- */
 typedef struct dpf_conv3d_args {
   int kind;
@@ -95,6 +97,8 @@ typedef struct dpf_conv3d_args {
   const void* residual;
   int relu;
   float* stats;
+  int x_cstride, x_coff;   /* channel stride / offset of x (0,0 = dense Cin); lets a launch read a channel window */
+  int res_pre;             /* 1: y = relu?((conv + residual) * scale + shift)  (K-split partial sums) */
 } dpf_conv3d_args;
 int dpf_conv3d_fwd(const dpf_conv3d_args* args, void* stream);
 /* number of bf16 elements of the packed weight buffer for (kind, Cin, Cout) */
@@ -132,11 +136,11 @@ int dpf_anm_gather(const void* out3, const int* idx, const float* coord, const f
  * (6) 3-D deformable convolution (D3D), 3x3x3 stride 1 pad 1, groups 1.  Replaces DCN.deform_conv_forward
  *     (src/module/dcn3d/src/deform_conv.h:10-29 -> src/cuda/deform_conv_cuda.cu:18-126 and the im2col kernel
  *     src/cuda/deform_im2col_cuda.cuh:192-265) without the [27*Cin, B*D*H*W] column buffer.
- *     x [B,D,H,W,Cin_pad] bf16, offset [B,D,H,W,81] fp32 ((d,h,w) per tap), w packed like kind 0 with Cin_pad,
+ *     x [B,D,H,W,x_cstride] bf16 (first Cin_pad in {48,64} channels used), offset [B,D,H,W,81] fp32 ((d,h,w) per tap), w packed like kind 0 with Cin_pad,
  *     y = relu?( dconv * scale + shift ) -> [B,D,H,W,Cout] bf16.
  * ------------------------------------------------------------------------------------------------- */
 int dpf_dcn3d_fwd(const void* x, const float* offset, const void* w, const float* scale, const float* shift, void* y,
-                  int B, int D, int H, int W, int Cin_pad, int Cout, int relu, void* stream);
+                  int B, int D, int H, int W, int Cin_pad, int x_cstride, int Cout, int relu, void* stream);
 
 #ifdef __cplusplus
 }

@@ -214,3 +214,59 @@ def test_anm_select_tie_rule(ops):
     ab = torch.tensor([[32.98, -26996.49]])
     idx, _, _ = ops.anm_select(disp.cuda(), kinv.cuda(), ab.cuda(), [float(v) for v in CR], 4)
     assert idx[0, :, 0, 0].cpu().tolist() == [2, 3, 4, 5]
+
+
+# ------------------------------------------------------------------------------ stride-2 / transposed / D3D
+def strided_case(ops, cin, cout, shape, seed, transposed, residual=False):
+    from dualpixelface_b200.layers import KIND_S2, KIND_T2, TCConv3d
+    b, d, h, w = shape
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(b, cin, d, h, w, generator=g).to(torch.bfloat16)
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.2
+    if transposed:
+        wt = (torch.randn(cin, cout, 3, 3, 3, generator=g) * (2.0 / (cin * 27 / 8)) ** 0.5).to(torch.bfloat16)
+        want = F.conv_transpose3d(x.float(), wt.float(), stride=2, padding=1, output_padding=1)
+    else:
+        wt = (torch.randn(cout, cin, 3, 3, 3, generator=g) * (2.0 / (cin * 27)) ** 0.5).to(torch.bfloat16)
+        want = F.conv3d(x.float(), wt.float(), stride=2, padding=1)
+    want = want * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
+    res = None
+    if residual:
+        res = torch.randn(want.shape, generator=g).to(torch.bfloat16)
+        want = want + res.float()
+    want = F.relu(want)
+    layer = TCConv3d(wt.cuda(), KIND_T2 if transposed else KIND_S2, transposed=transposed)
+    got = layer(ndhwc(x).cuda(), scale.cuda(), shift.cuda(), residual=ndhwc(res).cuda() if residual else None, relu=True)
+    torch.cuda.synchronize()
+    assert tuple(got.shape[1:4]) == tuple(want.shape[2:])
+    return rel_err(from_ndhwc(got), want)
+
+
+@pytest.mark.parametrize("cin,cout,shape", [(32, 64, (1, 8, 32, 16)), (32, 64, (2, 8, 36, 52)), (64, 64, (1, 4, 18, 26)),
+                                            (32, 32, (1, 2, 70, 106))])
+def test_conv_stride2(ops, cin, cout, shape):
+    assert strided_case(ops, cin, cout, shape, 11, transposed=False) < 1e-2
+
+
+@pytest.mark.parametrize("cin,cout,shape", [(64, 64, (1, 2, 16, 8)), (64, 32, (2, 4, 18, 26)), (64, 64, (1, 2, 35, 53)),
+                                            (32, 32, (1, 1, 9, 13))])
+def test_conv_transposed(ops, cin, cout, shape):
+    assert strided_case(ops, cin, cout, shape, 12, transposed=True, residual=True) < 1e-2
+
+
+@pytest.mark.parametrize("cin", [35, 64])
+def test_dcn3d(ops, cin):
+    g = torch.Generator().manual_seed(13)
+    b, d, h, w = 2, 4, 10, 13
+    cpad, cs = (48, 64) if cin <= 48 else (64, 64)
+    x = torch.randn(b, cin, d, h, w, generator=g).to(torch.bfloat16)
+    off = (torch.rand(b, 81, d, h, w, generator=g) - 0.5) * 3.0                       # up to +-1.5 voxels, crosses borders
+    wt = (torch.randn(64, cin, 3, 3, 3, generator=g) * (2.0 / (cin * 27)) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(64, generator=g) * 0.1
+    want = F.relu(O.deform_conv3d(x.float(), off, wt.float(), bias))
+    xp = torch.zeros(b, d, h, w, cs, dtype=torch.bfloat16)
+    xp[..., :cin] = ndhwc(x)
+    got = ops.dcn3d(xp.cuda(), off.permute(0, 2, 3, 4, 1).contiguous().cuda(), ops.pack_conv_weight(wt.cuda(), cin_pad=cpad), cpad,
+                    torch.ones(64).cuda(), bias.cuda(), relu=True)
+    torch.cuda.synchronize()
+    assert rel_err(from_ndhwc(got), want) < 2e-2        # the gathered A tile is rounded to bf16 before the MMA
