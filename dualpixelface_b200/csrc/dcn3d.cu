@@ -6,7 +6,7 @@
 //   y[v, o] = relu?( scale[o] * sum_{tap,c} W[o,c,tap] * trilinear(x[:, c], p_v + tap - 1 + offset[v, 3*tap + (0,1,2)]) + shift[o] )
 // x [B,D,H,W,x_cstride] bf16 (the first CINP channels are gathered; zero-padded beyond the real Cin), offset [B,D,H,W,81] fp32 ((d,h,w) per tap), y [B,D,H,W,64] bf16.
 //
-// Work unit: 256 consecutive voxels (2 GEMM blocks of 128 rows).  For every tap, 8 producer warps compute the
+// Work unit: 256 consecutive voxels (2 GEMM blocks of 128 rows).  For every tap, 16 producer warps compute the
 // trilinear sample of all CINP channels (8 threads per voxel, one 16-byte channel chunk each; fp32 blend) and write it
 // as the bf16 A tile in the UMMA no-swizzle K-major layout; the tap's weight tile [CINP x 64] is streamed next to it by a
 // 1-D TMA bulk copy.  One elected lane issues the tcgen05.mma; accumulators are double-buffered in TMEM so the
@@ -21,8 +21,9 @@ using namespace dpf;
 
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
-constexpr int kProdWarps = 8;
-constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;   // 416
+constexpr int kProdWarps = 16;
+constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;   // 672
+constexpr int kVoxPerPass = kProdWarps * 32 / 8;              // 8 threads (one 16-byte channel chunk each) per voxel
 constexpr int kNOut = 64;
 constexpr int kBlocks = 2;                                    // GEMM blocks (128 voxels each) per work unit
 constexpr int kStages = 3;
@@ -44,7 +45,8 @@ template <int CINP>
 struct DCfg {
   static constexpr int NCH = CINP / 8;
   static constexpr int KSTEPS = CINP / 16;
-  static constexpr int A_BLOCK_BYTES = NCH * 128 * 16;               // [chunk][128 rows][16 B]
+  static constexpr int A_CHUNK_BYTES = 128 * 16 + 16;                // chunk pitch (= LBO), +16 B: conflict-free st.shared
+  static constexpr int A_BLOCK_BYTES = NCH * A_CHUNK_BYTES;          // [chunk][128 rows][16 B]
   static constexpr int A_STAGE_BYTES = kBlocks * A_BLOCK_BYTES;
   static constexpr int W_TAP_BYTES = NCH * kNOut * 16;               // [chunk][64 rows][16 B]
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + W_TAP_BYTES;
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&bar_full[i], kProdWarps + 1);       // 8 gather warps + the weight-copy issuer (expect_tx)
+      mbar_init(&bar_full[i], kProdWarps + 1);       // gather warps + the weight-copy issuer (expect_tx)
       mbar_init(&bar_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -97,12 +99,29 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
 
   if (warp > kMmaWarp) {
     // ======================= producers: trilinear gather -> bf16 A tile; weight tile by TMA ==================
-    const int ptid = threadIdx.x - (kMmaWarp + 1) * 32;      // 0..255
+    const int ptid = threadIdx.x - (kMmaWarp + 1) * 32;      // 0..511
     const int c8 = ptid & 7;
-    const int vsub = ptid >> 3;                              // 0..31
+    const int vsub = ptid >> 3;                              // 0..63
+    constexpr int PASSES = kBlocks * 128 / kVoxPerPass;
+    const int HW = H * W;
+    const int cs = p.x_cstride;
+    const __nv_bfloat16* xc = p.x + (c8 < C::NCH ? c8 : 0) * 8;
     uint32_t g = 0;
     for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
       const long long v0 = static_cast<long long>(unit) * (kBlocks * 128);
+      // voxel coordinates of this thread's PASSES rows: decomposed once per unit, reused by all 27 taps
+      int vd[PASSES], vh[PASSES], vw[PASSES], vbase[PASSES];
+      bool vlive[PASSES];
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const long long v = v0 + ps * kVoxPerPass + vsub;
+        vlive[ps] = (v < p.nvox) && (c8 < C::NCH);
+        int t = static_cast<int>(vlive[ps] ? v : 0);               // nvox < 2^31 (checked on the host)
+        vw[ps] = t % W; t /= W;
+        vh[ps] = t % H; t /= H;
+        vd[ps] = t % D;
+        vbase[ps] = (t / D) * D * HW;                               // voxel index of (b, 0, 0, 0)
+      }
       for (int tap = 0; tap < kTaps; ++tap, ++g) {
         const int stage = g % kStages;
         const uint32_t ph = (g / kStages) & 1u;
@@ -112,57 +131,64 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
           mbar_arrive_expect_tx(&bar_full[stage], C::W_TAP_BYTES);
           bulk_g2s(smem_u32(sa + C::A_STAGE_BYTES), p.w + static_cast<size_t>(tap) * (C::W_TAP_BYTES / 2), C::W_TAP_BYTES, &bar_full[stage]);
         }
-        const int ti = tap / 9, tj = (tap / 3) % 3, tk = tap % 3;
-#pragma unroll 2
-        for (int pass = 0; pass < kBlocks * 128 / 32; ++pass) {
-          const int r = pass * 32 + vsub;                    // row inside the work unit (0..255)
-          const long long v = v0 + r;
-          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (v < p.nvox && c8 < C::NCH) {
-            long long t = v;
-            const int w = static_cast<int>(t % W); t /= W;
-            const int h = static_cast<int>(t % H); t /= H;
-            const int d = static_cast<int>(t % D);
-            const int b = static_cast<int>(t / D);
-            const float* op = p.offset + v * 81 + tap * 3;
-            const float pd = static_cast<float>(d - 1 + ti) + __ldg(op + 0);
-            const float phh = static_cast<float>(h - 1 + tj) + __ldg(op + 1);
-            const float pw = static_cast<float>(w - 1 + tk) + __ldg(op + 2);
-            if (pd > -1.f && phh > -1.f && pw > -1.f && pd < static_cast<float>(D) && phh < static_cast<float>(H) && pw < static_cast<float>(W)) {
-              const int d0 = static_cast<int>(floorf(pd)), h0 = static_cast<int>(floorf(phh)), w0 = static_cast<int>(floorf(pw));
-              const float ld = pd - static_cast<float>(d0), lh = phh - static_cast<float>(h0), lw = pw - static_cast<float>(w0);
-              const __nv_bfloat16* xb = p.x + static_cast<size_t>(b) * D * H * W * p.x_cstride + c8 * 8;
+        const int ti = tap / 9 - 1, tj = (tap / 3) % 3 - 1, tk = tap % 3 - 1;
 #pragma unroll
-              for (int cd = 0; cd < 2; ++cd) {
-                const int di = d0 + cd;
-                if (di < 0 || di > D - 1) continue;
-                const float wd = cd ? ld : 1.f - ld;
+        for (int ps = 0; ps < PASSES; ++ps) {
+          const int r = ps * kVoxPerPass + vsub;             // row inside the work unit (0..255)
+          const int vox = vbase[ps] + (vd[ps] * H + vh[ps]) * W + vw[ps];
+          const float* op = p.offset + static_cast<size_t>(vox) * 81 + tap * 3;
+          const float pd = static_cast<float>(vd[ps] + ti) + __ldg(op + 0);
+          const float phh = static_cast<float>(vh[ps] + tj) + __ldg(op + 1);
+          const float pw = static_cast<float>(vw[ps] + tk) + __ldg(op + 2);
+          const bool inside = vlive[ps] && pd > -1.f && phh > -1.f && pw > -1.f && pd < static_cast<float>(D) &&
+                              phh < static_cast<float>(H) && pw < static_cast<float>(W);
+          const float fd = floorf(pd), fh = floorf(phh), fw = floorf(pw);
+          const int d0 = static_cast<int>(fd), h0 = static_cast<int>(fh), w0 = static_cast<int>(fw);
+          const float ld = pd - fd, lh = phh - fh, lw = pw - fw;
+          // branch-free corners: clamp the index, zero the weight when the corner (or the whole sample) is outside,
+          // so that all 8 loads are issued back to back
+          const float wd0 = (inside && d0 >= 0) ? 1.f - ld : 0.f, wd1 = (inside && d0 + 1 <= D - 1) ? ld : 0.f;
+          const float wh0 = (h0 >= 0) ? 1.f - lh : 0.f, wh1 = (h0 + 1 <= H - 1) ? lh : 0.f;
+          const float ww0 = (w0 >= 0) ? 1.f - lw : 0.f, ww1 = (w0 + 1 <= W - 1) ? lw : 0.f;
+          const int dc0 = min(max(d0, 0), D - 1), dc1 = min(max(d0 + 1, 0), D - 1);
+          const int hc0 = min(max(h0, 0), H - 1), hc1 = min(max(h0 + 1, 0), H - 1);
+          const int wc0 = min(max(w0, 0), W - 1), wc1 = min(max(w0 + 1, 0), W - 1);
+          const int r00 = vbase[ps] + dc0 * HW + hc0 * W, r01 = vbase[ps] + dc0 * HW + hc1 * W;
+          const int r10 = vbase[ps] + dc1 * HW + hc0 * W, r11 = vbase[ps] + dc1 * HW + hc1 * W;
+          uint4 u[8];
+          u[0] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r00 + wc0) * cs));
+          u[1] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r00 + wc1) * cs));
+          u[2] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r01 + wc0) * cs));
+          u[3] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r01 + wc1) * cs));
+          u[4] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r10 + wc0) * cs));
+          u[5] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r10 + wc1) * cs));
+          u[6] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r11 + wc0) * cs));
+          u[7] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r11 + wc1) * cs));
+          const float a00 = wd0 * wh0, a01 = wd0 * wh1, a10 = wd1 * wh0, a11 = wd1 * wh1;
+          const float cw[8] = {a00 * ww0, a00 * ww1, a01 * ww0, a01 * ww1, a10 * ww0, a10 * ww1, a11 * ww0, a11 * ww1};
+          // packed bf16 blend (HFMA2.BF16): the blended A tile is rounded to bf16 for the MMA anyway
+          __nv_bfloat162 acc[4];
+          {
+            const __nv_bfloat162 w2 = __float2bfloat162_rn(cw[0]);
+            acc[0] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[0].x));
+            acc[1] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[0].y));
+            acc[2] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[0].z));
+            acc[3] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[0].w));
+          }
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                  const int hi = h0 + ch;
-                  if (hi < 0 || hi > H - 1) continue;
-                  const float wdh = wd * (ch ? lh : 1.f - lh);
-#pragma unroll
-                  for (int cw = 0; cw < 2; ++cw) {
-                    const int wi = w0 + cw;
-                    if (wi < 0 || wi > W - 1) continue;
-                    const float ww = wdh * (cw ? lw : 1.f - lw);
-                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + ((static_cast<size_t>(di) * H + hi) * W + wi) * p.x_cstride));
-                    acc[0] = fmaf(ww, bf16_lo(u.x), acc[0]); acc[1] = fmaf(ww, bf16_hi(u.x), acc[1]);
-                    acc[2] = fmaf(ww, bf16_lo(u.y), acc[2]); acc[3] = fmaf(ww, bf16_hi(u.y), acc[3]);
-                    acc[4] = fmaf(ww, bf16_lo(u.z), acc[4]); acc[5] = fmaf(ww, bf16_hi(u.z), acc[5]);
-                    acc[6] = fmaf(ww, bf16_lo(u.w), acc[6]); acc[7] = fmaf(ww, bf16_hi(u.w), acc[7]);
-                  }
-                }
-              }
-            }
+          for (int c = 1; c < 8; ++c) {
+            const __nv_bfloat162 w2 = __float2bfloat162_rn(cw[c]);
+            acc[0] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[c].x), acc[0]);
+            acc[1] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[c].y), acc[1]);
+            acc[2] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[c].z), acc[2]);
+            acc[3] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[c].w), acc[3]);
           }
           if (c8 < C::NCH) {
             uint4 o;
-            o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
-            o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+            o.x = *reinterpret_cast<uint32_t*>(&acc[0]); o.y = *reinterpret_cast<uint32_t*>(&acc[1]);
+            o.z = *reinterpret_cast<uint32_t*>(&acc[2]); o.w = *reinterpret_cast<uint32_t*>(&acc[3]);
             const int blk = r >> 7, row = r & 127;
-            *reinterpret_cast<uint4*>(sa + blk * C::A_BLOCK_BYTES + (c8 * 128 + row) * 16) = o;
+            *reinterpret_cast<uint4*>(sa + blk * C::A_BLOCK_BYTES + c8 * C::A_CHUNK_BYTES + row * 16) = o;
           }
         }
         fence_proxy_async_smem();
@@ -173,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
   } else if (warp == kMmaWarp) {
     // ======================================= MMA issuer =====================================================
     constexpr uint32_t idesc = umma_idesc_bf16_f32(128, kNOut);
-    const uint64_t adesc_hi = umma_desc_nosw(0, 128 * 16, 128);        // LBO = chunk pitch (2 KB), SBO = 8 rows
+    const uint64_t adesc_hi = umma_desc_nosw(0, C::A_CHUNK_BYTES, 128);   // LBO = chunk pitch, SBO = 8 rows
     const uint64_t bdesc_hi = umma_desc_nosw(0, kNOut * 16, 128);
     const uint32_t sbase = smem_u32(s_stage);
     const bool leader = elect_one();
@@ -194,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
             const uint64_t bdesc = bdesc_hi | static_cast<uint64_t>((b0 + ks * 2 * kNOut) & 0x3FFF);
 #pragma unroll
             for (int blk = 0; blk < kBlocks; ++blk) {
-              const uint64_t adesc = adesc_hi | static_cast<uint64_t>((a0 + blk * (C::A_BLOCK_BYTES >> 4) + ks * 2 * 128) & 0x3FFF);
+              const uint64_t adesc = adesc_hi | static_cast<uint64_t>((a0 + blk * (C::A_BLOCK_BYTES >> 4) + ks * 2 * (C::A_CHUNK_BYTES >> 4)) & 0x3FFF);
               umma_bf16(tmem_base + (as * kBlocks + blk) * kNOut, adesc, bdesc, idesc, !(tap == 0 && ks == 0));
             }
           }
@@ -274,6 +300,7 @@ extern "C" int dpf_dcn3d_fwd(const void* x, const float* offset, const void* w, 
   DPF_REQUIRE(Cout == kNOut, "dpf_dcn3d_fwd: Cout=%d, only 64 is built", Cout);
   DPF_REQUIRE(Cin_pad == 48 || Cin_pad == 64, "dpf_dcn3d_fwd: Cin_pad=%d must be 48 or 64", Cin_pad);
   DPF_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "dpf_dcn3d_fwd: bad shape");
+  DPF_REQUIRE(static_cast<long long>(B) * D * H * W < (1LL << 31) / 128, "dpf_dcn3d_fwd: tensor too large for 32-bit voxel indexing");
   DPF_REQUIRE(x_cstride >= Cin_pad && x_cstride % 8 == 0, "dpf_dcn3d_fwd: x_cstride=%d must be a multiple of 8 >= Cin_pad", x_cstride);
   DcnParams p{};
   p.x = reinterpret_cast<const __nv_bfloat16*>(x);

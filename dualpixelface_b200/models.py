@@ -35,13 +35,36 @@ class _StereoBase(LightningModule):
             swap = bool(self.option.dataset.flip_lr)
         return (batch["right"], batch["left"]) if swap else (batch["left"], batch["right"])
 
+    def _fused_encoder(self):
+        """Eval-mode copy of the cuDNN encoder with every BatchNorm2d folded into its convolution, bf16, channels-last
+        (kept outside the module tree so that the state_dict layout is untouched; rebuilt by refresh())."""
+        enc = self.__dict__.get("_enc_fused")
+        if enc is None:
+            import copy
+            from torch.nn.utils.fusion import fuse_conv_bn_eval
+            enc = copy.deepcopy(self.feature_extraction).eval()
+
+            def walk(mod):
+                for _, child in list(mod.named_children()):
+                    if isinstance(child, nn.Sequential) and len(child) >= 2 and isinstance(child[0], nn.Conv2d) \
+                            and isinstance(child[1], nn.BatchNorm2d):
+                        child[0] = fuse_conv_bn_eval(child[0], child[1])
+                        child[1] = nn.Identity()
+                    if isinstance(child, M._SepConv):
+                        child.pointwise = fuse_conv_bn_eval(child.pointwise, child.bn)
+                        child.bn = nn.Identity()
+                    walk(child)
+
+            walk(enc)
+            enc = enc.to(device=next(self.parameters()).device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+            self.__dict__["_enc_fused"] = enc
+        return enc
+
     def _features(self, ref_img, tgt_img):
         b = ref_img.shape[0]
         x = torch.cat([ref_img, tgt_img], 0)
         if self.encoder_autocast:
-            x = x.contiguous(memory_format=torch.channels_last)
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                f = self.feature_extraction(x)
+            f = self._fused_encoder()(x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
         else:
             f = self.feature_extraction(x.float())
         f = f.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()      # [2B,H4,W4,C] channels-last bf16
@@ -84,6 +107,7 @@ class _StereoBase(LightningModule):
 
     def refresh(self):
         """Re-pack kernel-layout weights after parameters changed (load_state_dict calls it)."""
+        self.__dict__.pop("_enc_fused", None)
         for m in self.modules():
             if m is not self and hasattr(m, "refresh"):
                 m.refresh()

@@ -69,3 +69,20 @@ def test_cpu_input_fails_loudly():
     model = build("psmnet").eval()
     with pytest.raises(RuntimeError):
         model(synthetic_batch(1, 256, 256))
+
+
+def test_model_default_path_bf16_encoder():
+    """The bench configuration: BN-folded bf16 cuDNN encoder in front of the sm_100a hot path."""
+    batch = synthetic_batch(2, 128, 160, training=True, seed=0)
+    st, fwd = calibrated_state("stereodpnet", batch)
+    with torch.no_grad():
+        want = fwd(dict(batch), st, False)
+    model = build("stereodpnet")
+    model.load_state_dict(st, strict=False)
+    model.cuda().eval()
+    with torch.no_grad():
+        got = model(to_cuda(batch))
+    err = (got["pred_depth"].float().cpu() - want["pred_depth"]).abs()
+    n_err = (got["pred_normal"].float().cpu() - want["pred_normal"]).abs()
+    print(f"bf16 encoder: disparity max err {err.max():.4f} mean {err.mean():.5f}; normal mean {n_err.mean():.5f}")
+    assert err.mean().item() < 2e-2 * 16.0 / 4 and n_err.mean().item() < 2e-2
