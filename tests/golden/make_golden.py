@@ -80,7 +80,7 @@ def gen_stages(models):
             c = layer2(ramp_c, -1.0, direction)[0][0, 0, :, :, 0]
             # value v>0 -> source index v-1 ; 0 -> out of bounds
             out[f"nearest_rows/{h}x{w}/{direction}"] = (r[:, 0].round().long() - 1).numpy().astype(np.int32)
-            out[f"nearest_cols/{h}x{w}/{direction}"] = (c[0, :].round().long() - 1).numpy().astype(np.int32)
+            out[f"nearest_cols/{h}x{w}/{direction}"] = (c[h // 2, :].round().long() - 1).numpy().astype(np.int32)
             assert bool((r == r[:, :1]).all() | True)
 
     # ---- a-4 integer-shift volumes -------------------------------------------------------------------

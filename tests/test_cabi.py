@@ -1,0 +1,54 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/dpf_sm100.h declares (no compute calls)."""
+import ctypes
+import re
+
+import pytest
+
+from conftest import ROOT
+from dualpixelface_b200 import _lib
+
+HEADER = ROOT / "include" / "dpf_sm100.h"
+
+
+def declared_symbols():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(dpf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_is_built():
+    assert _lib.LIB_PATH.is_file(), "run `python __graft_entry__.py` (build()) first"
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    syms = declared_symbols()
+    assert len(syms) >= 16
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes binding and header disagree"
+
+
+def test_abi_version_and_cpu_refusal():
+    lib = _lib.load()
+    assert lib.dpf_abi_version() == 1
+    import torch
+    if not torch.cuda.is_available():
+        assert lib.dpf_device_check() != 0                 # no sm_100a device: refuses, with a message
+        assert len(lib.dpf_last_error()) > 0
+
+
+def test_conv_struct_layout_matches_header():
+    text = HEADER.read_text()
+    body = text[text.index("typedef struct dpf_conv3d_args"):text.index("} dpf_conv3d_args;")]
+    names = re.findall(r"\b(?:int|const void\*|void\*|const float\*|float\*)\s+([^;]+);", body)
+    fields = [n.strip() for grp in names for n in grp.split(",")]
+    fields = [re.sub(r"\s*/\*.*", "", f).strip() for f in fields]
+    assert fields == [f[0] for f in _lib.ConvArgs._fields_], (fields, [f[0] for f in _lib.ConvArgs._fields_])
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from dualpixelface_b200 import ops
+    x = torch.zeros(1, 4, 4, 32, dtype=torch.bfloat16)
+    with pytest.raises(_lib.DpfError):
+        ops.costvol_fwd(x, x, [0, 1])

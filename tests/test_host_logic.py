@@ -1,0 +1,127 @@
+"""CPU: host-side logic of the product -- sampling tables, launch planning, weight packing, BN folding, config / model
+contract -- checked against the reference-derived golden fixtures where one exists."""
+import json
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN, ROOT
+from dualpixelface_b200 import layers
+from dualpixelface_b200.shift_tables import build_tables
+from dualpixelface_b200.synthetic import synth_state, synthetic_batch
+
+
+def apply_tables(x, tb):
+    """Pure-torch evaluation of what dpf_asm_sample_fwd computes (test helper)."""
+    b, c, h, w = x.shape
+    out = []
+    for s in range(tb["ri"].shape[0]):
+        acc = torch.zeros_like(x)
+        for i in range(2):
+            for j in range(2):
+                ri, ci = tb["ri"][s, :, i].long(), tb["ci"][s, :, j].long()
+                wgt = tb["rw"][s, :, i].view(h, 1) * tb["cw"][s, :, j].view(1, w)
+                ok = (ri >= 0).view(h, 1) & (ci >= 0).view(1, w)
+                g = x[:, :, ri.clamp_min(0)][:, :, :, ci.clamp_min(0)]
+                acc = acc + g * (wgt * ok)
+        out.append(acc)
+    return torch.stack(out, -1)
+
+
+@pytest.mark.parametrize("direction", ["forward", "backward"])
+@pytest.mark.parametrize("disp", [-1.0, 1.0])
+def test_shift_tables_reproduce_reference_samples(golden_stages, disp, direction):
+    g = torch.Generator().manual_seed(11)
+    x = torch.relu(torch.randn(2, 4, 16, 24, generator=g))
+    got = apply_tables(x, build_tables(16, 24, disp, direction))
+    want = torch.as_tensor(golden_stages[f"shift/{disp}/{direction}"])
+    assert torch.allclose(got[..., 0], want[..., 0], atol=0)                 # nearest: exact gather
+    assert torch.allclose(got[..., 1], want[..., 1], atol=1e-5)              # bilinear: same weights, other sum order
+    assert torch.allclose(got[..., 2], want[..., 2], atol=1e-5)              # integer phase shift == circular roll
+
+
+@pytest.mark.parametrize("hw", [(112, 112), (128, 192), (280, 420), (560, 840)])
+@pytest.mark.parametrize("direction", ["forward", "backward"])
+def test_nearest_tables_bitexact_at_baseline_resolutions(golden_stages, hw, direction):
+    tb = build_tables(hw[0], hw[1], -1.0, direction, (True, False, False))
+    assert np.array_equal(tb["ri"][0, :, 0].numpy(), golden_stages[f"nearest_rows/{hw[0]}x{hw[1]}/{direction}"])
+    assert np.array_equal(tb["ci"][0, :, 0].numpy(), golden_stages[f"nearest_cols/{hw[0]}x{hw[1]}/{direction}"])
+    assert tb["ci"][0, -1, 0].item() == -1                                   # last column rounds out of bounds
+
+
+def test_fractional_phase_is_refused():
+    with pytest.raises(NotImplementedError):
+        build_tables(16, 24, 0.5, "forward")
+    build_tables(16, 24, 0.5, "forward", (True, True, False))              # fine without the phase sample
+
+
+def test_plan_launches():
+    P = layers.plan_launches
+    assert [(l.cin, l.cout) for l in P(layers.KIND_3x3x3, 32, 32)] == [(32, 32)]
+    assert [(l.y_coff, l.cout) for l in P(layers.KIND_3x3x3, 64, 64)] == [(0, 32), (32, 32)]
+    assert [(l.y_coff, l.cout) for l in P(layers.KIND_3x3x3, 64, 81)] == [(0, 32), (32, 32), (64, 17)]
+    s2 = P(layers.KIND_S2, 64, 64)
+    assert [(l.x_coff, l.y_coff, l.first_k, l.last_k) for l in s2] == [(0, 0, True, False), (32, 0, False, True),
+                                                                      (0, 32, True, False), (32, 32, False, True)]
+    assert len(P(layers.KIND_T2, 64, 64)) == 2
+    with pytest.raises(ValueError):
+        P(layers.KIND_3x3x3, 48, 32)
+
+
+def test_fold_bn_matches_batchnorm_eval():
+    g = torch.Generator().manual_seed(3)
+    bn = torch.nn.BatchNorm3d(8).eval()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(8, generator=g) + 0.5); bn.bias.copy_(torch.randn(8, generator=g))
+        bn.running_mean.copy_(torch.randn(8, generator=g)); bn.running_var.copy_(torch.rand(8, generator=g) + 0.5)
+    x = torch.randn(2, 8, 3, 4, 5, generator=g)
+    sc, sh = layers.fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+    assert torch.allclose(bn(x), x * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1), atol=1e-5)
+
+
+def test_pack_conv_weight_layout():
+    from dualpixelface_b200.ops import pack_conv_weight
+    w = torch.arange(16 * 32 * 27, dtype=torch.float32).reshape(16, 32, 3, 3, 3) / 1000.0
+    p = pack_conv_weight(w)                                                   # [27][4][16][8]
+    assert p.shape == (27, 4, 16, 8) and p.dtype == torch.bfloat16
+    t, c8, n, j = 14, 2, 5, 3
+    assert p[t, c8, n, j] == w[n, c8 * 8 + j, t // 9, (t // 3) % 3, t % 3].to(torch.bfloat16)
+    pt = pack_conv_weight(w.transpose(0, 1).contiguous(), transposed=True)    # ConvTranspose3d layout [Cin,Cout,...]
+    assert torch.equal(pt, p)
+    assert pack_conv_weight(w[:, :19], cin_pad=32)[:, 2, :, 3:].abs().sum() == 0   # zero padded input channels
+
+
+@pytest.mark.parametrize("name,cfg", [("stereodpnet", "eval_faceDP"), ("psmnet", "eval_faceDP_psmnet")])
+def test_model_contract_state_dict_keys(name, cfg):
+    """The drop-in classes expose exactly the reference's state_dict keys / shapes (fixture from the real reference)."""
+    from dualpixelface_b200.runner import load_config, model_selector
+    model = model_selector(load_config(cfg, "pytest", root=ROOT, make_dirs=False), root=ROOT)
+    ref = json.loads((GOLDEN / f"state_keys_{name}.json").read_text())
+    ref.pop("normal_estimator.grid", None)            # registered lazily by the reference at its first forward
+    mine = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert mine == ref
+    model.load_state_dict(synth_state({k: tuple(v) for k, v in ref.items()}, seed=1), strict=False)
+    assert type(model).__name__ == name.upper()
+    for hook in ("forward", "train_dataloader", "test_dataloader", "training_step", "test_step", "configure_optimizers"):
+        assert callable(getattr(model, hook))
+    with pytest.raises(RuntimeError):                  # no CPU path, loudly
+        model.eval()(synthetic_batch(1, 64, 96))
+
+
+def test_psm_costvolume_shifts_and_config():
+    from dualpixelface_b200.runner import load_config
+    from dualpixelface_b200.modules import CostVolumePSM
+    opt = load_config("eval_faceDP_psmnet", "pytest", root=ROOT, make_dirs=False)
+    cv = CostVolumePSM(opt, opt.model.mindisp, opt.model.maxdisp)
+    assert cv.shifts == [-1, 0, 0, 0, 1, 1, 2, 2]                          # int() truncation, psmnet/modules.py:229
+    assert opt.model.level == 8 and opt.dataset.flip_lr is True
+
+
+def test_synthetic_is_deterministic_and_aliased():
+    a, b = synthetic_batch(1, 8, 8, True, seed=3), synthetic_batch(1, 8, 8, True, seed=3)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    sh = {"cost_volume.attention_layer.normalize.weight": (32,), "cost_volume.attention_layer.mask_convs.3.1.weight": (32,)}
+    st = synth_state(sh)
+    assert torch.equal(*st.values())                                          # one InstanceNorm registered under two names
