@@ -319,13 +319,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
               if (p.y_f32) {
                 float* yo = reinterpret_cast<float*>(p.y) + vox * p.y_cstride + p.y_coff + c0;
                 const float* ro = p.residual ? reinterpret_cast<const float*>(p.residual) + vox * p.y_cstride + p.y_coff + c0 : nullptr;
-                for (int j = 0; j < n; ++j) {
-                  float val = f[j];
-                  if (ro && p.res_pre) val += ro[j];
-                  val = val * s_scale[c0 + j] + s_shift[c0 + j];
-                  if (ro && !p.res_pre) val += ro[j];
-                  if (p.relu) val = fmaxf(val, 0.f);
-                  yo[j] = val;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {                    // fully unrolled + predicated: keeps f[] in registers
+                  if (j < n) {
+                    float val = f[j];
+                    if (ro && p.res_pre) val += ro[j];
+                    val = val * s_scale[c0 + j] + s_shift[c0 + j];
+                    if (ro && !p.res_pre) val += ro[j];
+                    if (p.relu) val = fmaxf(val, 0.f);
+                    yo[j] = val;
+                  }
                 }
               } else {
                 __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + vox * p.y_cstride + p.y_coff + c0;
@@ -333,25 +336,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                 for (int j = 0; j < 16; ++j) f[j] = f[j] * s_scale[c0 + j] + s_shift[c0 + j];
                 if (p.residual) {
                   const __nv_bfloat16* ro = reinterpret_cast<const __nv_bfloat16*>(p.residual) + vox * p.y_cstride + p.y_coff + c0;
-                  for (int j8 = 0; j8 < n; j8 += 8) {
-                    const uint4 r = *reinterpret_cast<const uint4*>(ro + j8);
-                    f[j8 + 0] += bf16_lo(r.x); f[j8 + 1] += bf16_hi(r.x);
-                    f[j8 + 2] += bf16_lo(r.y); f[j8 + 3] += bf16_hi(r.y);
-                    f[j8 + 4] += bf16_lo(r.z); f[j8 + 5] += bf16_hi(r.z);
-                    f[j8 + 6] += bf16_lo(r.w); f[j8 + 7] += bf16_hi(r.w);
+#pragma unroll
+                  for (int j8 = 0; j8 < 16; j8 += 8) {
+                    if (j8 < n) {
+                      const uint4 r = *reinterpret_cast<const uint4*>(ro + j8);
+                      f[j8 + 0] += bf16_lo(r.x); f[j8 + 1] += bf16_hi(r.x);
+                      f[j8 + 2] += bf16_lo(r.y); f[j8 + 3] += bf16_hi(r.y);
+                      f[j8 + 4] += bf16_lo(r.z); f[j8 + 5] += bf16_hi(r.z);
+                      f[j8 + 6] += bf16_lo(r.w); f[j8 + 7] += bf16_hi(r.w);
+                    }
                   }
                 }
                 if (p.relu) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
                 }
-                for (int j8 = 0; j8 < n; j8 += 8) {              // n is a multiple of 8 (checked on the host)
-                  uint4 o;
-                  o.x = pack_bf16x2(f[j8 + 0], f[j8 + 1]);
-                  o.y = pack_bf16x2(f[j8 + 2], f[j8 + 3]);
-                  o.z = pack_bf16x2(f[j8 + 4], f[j8 + 5]);
-                  o.w = pack_bf16x2(f[j8 + 6], f[j8 + 7]);
-                  *reinterpret_cast<uint4*>(yo + j8) = o;
+#pragma unroll
+                for (int j8 = 0; j8 < 16; j8 += 8) {             // n is a multiple of 8 (checked on the host)
+                  if (j8 < n) {
+                    uint4 o;
+                    o.x = pack_bf16x2(f[j8 + 0], f[j8 + 1]);
+                    o.y = pack_bf16x2(f[j8 + 2], f[j8 + 3]);
+                    o.z = pack_bf16x2(f[j8 + 4], f[j8 + 5]);
+                    o.w = pack_bf16x2(f[j8 + 6], f[j8 + 7]);
+                    *reinterpret_cast<uint4*>(yo + j8) = o;
+                  }
                 }
               }
             }
@@ -371,6 +380,346 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
+}
+
+// ============================================================================================================
+// kd-fused variant for the 3x3x3 stride-1 layers (the bulk of the FLOPs, all with small Cout).
+//
+// With N = Cout = 32 the A operand dominates shared-memory traffic: a 128x32x16 MMA reads 4 KB of A for 1 KB of B.
+// The three depth taps kd = 0,1,2 of one (kh,kw) read the SAME A window of input plane p and contribute to output
+// planes p+1, p, p-1.  Keeping the accumulators of consecutive output planes in CONSECUTIVE TMEM column groups
+// (ring of R stages, stage(Q) = (-Q) mod R) lets ONE tcgen05.mma with N = 3*Cout and B = [W(kd=0) | W(kd=1) | W(kd=2)]
+// do all three at once: A traffic / 3, 9 x Cin/16 MMAs per input plane instead of 27 x.  A side effect: every input plane
+// is consumed in a single pass, so its slot is released immediately (shallow ring).  Since one instruction now
+// mixes "first contribution" and "accumulate" columns, accumulators are zeroed by the epilogue (tcgen05.st) when it
+// drains them, and every MMA accumulates.  When the three stages wrap around the ring the MMA is split in two.
+// ============================================================================================================
+constexpr int kFEpiWarps = 8;                                       // fused kernel: 8 epilogue warps, MMA warp 8, 4 producers
+constexpr int kFMmaWarp = kFEpiWarps;
+constexpr int kFThreads = (kFEpiWarps + 1 + kProdWarps) * 32;       // 416
+
+template <int CIN, int NPAD, int WT, int NS, int R>
+struct FCfg {
+  static constexpr int NCH = CIN / 8;
+  static constexpr int WP = WT + 2;
+  static constexpr int PLANE_BYTES = 18 * WP * 16;
+  static constexpr int WANT = (NCH == 4) ? 32 : 16;
+  static constexpr int CH_STRIDE = PLANE_BYTES + ((WANT - (PLANE_BYTES % 128)) + 128) % 128;
+  static constexpr int SLOT_BYTES = NCH * CH_STRIDE;
+  static constexpr int W_ROWS = 3 * NPAD;                        // B rows per (kh,kw): [kd][co]
+  static constexpr int W_GROUP_BYTES = NCH * W_ROWS * 16;        // one (kh,kw): [c8][kd*NPAD+co][8]
+  static constexpr int W_BYTES = 9 * W_GROUP_BYTES;
+  static constexpr int NBLK = WT / 8;
+  static constexpr int COLS = R * NBLK * NPAD;
+  static constexpr int TMEM_COLS = COLS <= 32 ? 32 : COLS <= 64 ? 64 : COLS <= 128 ? 128 : COLS <= 256 ? 256 : 512;
+  static constexpr int KSTEPS = CIN / 16;
+  static constexpr int SMEM_BYTES = W_BYTES + NS * SLOT_BYTES + 2 * NPAD * 4 + (2 * NS + 2 * R) * 8 + 16 + 128;
+  static_assert(COLS <= 512, "accumulator ring does not fit TMEM");
+  static_assert(R >= 4, "need >= 4 accumulator stages");
+  static_assert(3 * NPAD <= 256, "fused N too large");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+};
+
+template <int CIN, int NPAD, int WT, int NS, int R>
+__global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __grid_constant__ ConvKParams p) {
+  using C = FCfg<CIN, NPAD, WT, NS, R>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  uint8_t* s_w = smem;
+  uint8_t* s_slots = smem + C::W_BYTES;
+  float* s_scale = reinterpret_cast<float*>(s_slots + NS * C::SLOT_BYTES);
+  float* s_shift = s_scale + NPAD;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_shift + NPAD);
+  uint64_t* bar_empty = bar_full + NS;
+  uint64_t* bar_tfull = bar_empty + NS;
+  uint64_t* bar_tempty = bar_tfull + R;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + R);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- one-time setup: weights global [tap=(kd,kh,kw)][c8][NPAD][8] -> smem [khkw][c8][kd*NPAD+n][8] --------------
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.w);
+    uint4* dst = reinterpret_cast<uint4*>(s_w);
+    constexpr int PER_TAP = C::NCH * NPAD;                       // 16-byte rows per tap
+    for (int i = threadIdx.x; i < 27 * PER_TAP; i += kFThreads) {
+      const int tap = i / PER_TAP, rem = i - tap * PER_TAP;
+      const int c8 = rem / NPAD, n = rem - c8 * NPAD;
+      const int kd = tap / 9, khkw = tap - kd * 9;
+      dst[(khkw * C::NCH + c8) * C::W_ROWS + kd * NPAD + n] = __ldg(src + i);
+    }
+    for (int i = threadIdx.x; i < NPAD; i += kFThreads) {
+      s_scale[i] = (p.scale != nullptr && i < p.cout) ? p.scale[i] : 1.0f;
+      s_shift[i] = (p.shift != nullptr && i < p.cout) ? p.shift[i] : 0.0f;
+    }
+    fence_proxy_async_smem();
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&bar_full[i], kProdWarps);
+      mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < R; ++i) {
+      mbar_init(&bar_tfull[i], 1);
+      mbar_init(&bar_tempty[i], kFEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == kFMmaWarp) {
+    tmem_alloc(s_tmem, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  const int D = p.D, H = p.H, W = p.W;
+
+  if (warp > kFMmaWarp) {
+    // =================================== producers (identical to the generic kernel) ======================
+    const int ptid = threadIdx.x - (kFMmaWarp + 1) * 32;
+    constexpr int PIECES_PER_ROW = C::WP * C::NCH;
+    constexpr int PIECES = 18 * PIECES_PER_ROW;
+    uint32_t g = 0;
+    int prev_slot = -1;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int tw = tile % p.tiles_w;
+      const int th = (tile / p.tiles_w) % p.tiles_h;
+      const int b = tile / (p.tiles_w * p.tiles_h);
+      const int h0 = th * 16 - 1, w0 = tw * WT - 1;
+      for (int pl = 0; pl < D; ++pl, ++g) {
+        const int slot = g % NS;
+        mbar_wait(&bar_empty[slot], ((g / NS) & 1u) ^ 1u);
+        const uint32_t sbase = smem_u32(s_slots + slot * C::SLOT_BYTES);
+        const __nv_bfloat16* xplane = p.x + (static_cast<size_t>(b) * D + pl) * H * static_cast<size_t>(W) * p.x_cstride + p.x_coff;
+#pragma unroll 4
+        for (int q = ptid; q < PIECES; q += kProdWarps * 32) {
+          const int row = q / PIECES_PER_ROW;
+          const int rem = q - row * PIECES_PER_ROW;
+          const int col = rem / C::NCH;
+          const int c8 = rem - col * C::NCH;
+          const int h = h0 + row, w = w0 + col;
+          const bool ok = (h >= 0) && (h < H) && (w >= 0) && (w < W);
+          const __nv_bfloat16* src = ok ? (xplane + (static_cast<size_t>(h) * W + w) * p.x_cstride + c8 * 8) : p.x;
+          if (!(p.debug & 1)) cp_async16_zfill(sbase + c8 * C::CH_STRIDE + (row * C::WP + col) * 16, src, ok);
+        }
+        cp_async_commit();
+        if (prev_slot >= 0) {
+          cp_async_wait<1>();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_full[prev_slot]);
+        }
+        prev_slot = slot;
+      }
+    }
+    if (prev_slot >= 0) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[prev_slot]);
+    }
+  } else if (warp == kFMmaWarp) {
+    // =================================== MMA issuer =======================================================
+    const uint32_t wbase = smem_u32(s_w) >> 4;
+    const uint32_t sbase0 = smem_u32(s_slots);
+    const uint64_t adesc_hi = umma_desc_nosw(0, C::CH_STRIDE, C::WP * 16);
+    const uint64_t bdesc_hi = umma_desc_nosw(0, C::W_ROWS * 16, 128);
+    const bool leader = elect_one();
+    uint32_t g_base = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int tw = tile % p.tiles_w;
+      const int nblk = min(C::NBLK, (p.Mw - tw * WT + 7) >> 3);
+      for (int pl = 0; pl < D; ++pl) {
+        const uint32_t P = g_base + pl;
+        const uint32_t slot = P % NS;
+        // accumulator stages touched for the first time by this input plane must have been drained (and zeroed)
+        if (pl == 0) mbar_wait(&bar_tempty[(R - P % R) % R], (P / R) & 1u);
+        if (pl + 1 < D) mbar_wait(&bar_tempty[(R - (P + 1) % R) % R], ((P + 1) / R) & 1u);
+        mbar_wait(&bar_full[slot], (P / NS) & 1u);
+        tc_fence_after_sync();
+        const int kd_lo = (pl + 1 < D) ? 0 : 1, kd_hi = (pl >= 1) ? 2 : 1;
+        const int n_kd = kd_hi - kd_lo + 1;
+        const uint32_t s_first = (R - (P + 1 - kd_lo) % R) % R;     // stage of output plane P+1-kd_lo; next kd -> next stage
+        const int run1 = min(n_kd, static_cast<int>(R - s_first)), run2 = n_kd - run1;
+        const uint32_t idesc1 = umma_idesc_bf16_f32(128, run1 * NPAD);
+        const uint32_t idesc2 = umma_idesc_bf16_f32(128, (run2 > 0 ? run2 : 1) * NPAD);
+        const uint32_t a_slot = (sbase0 + slot * C::SLOT_BYTES) >> 4;
+        if (leader && !(p.debug & 2)) {
+#pragma unroll 1
+          for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const uint32_t a0 = a_slot + kh * C::WP + kw;
+              const uint32_t b0 = wbase + (kh * 3 + kw) * (C::W_GROUP_BYTES >> 4) + kd_lo * NPAD;
+#pragma unroll
+              for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                const uint64_t bd1 = bdesc_hi | static_cast<uint64_t>((b0 + ks * 2 * C::W_ROWS) & 0x3FFF);
+                const uint64_t bd2 = bdesc_hi | static_cast<uint64_t>((b0 + ks * 2 * C::W_ROWS + run1 * NPAD) & 0x3FFF);
+#pragma unroll
+                for (int blk = 0; blk < C::NBLK; ++blk) {
+                  if (blk < nblk) {
+                    const uint64_t adesc = adesc_hi | static_cast<uint64_t>((a0 + ks * 2 * (C::CH_STRIDE >> 4) + blk * 8) & 0x3FFF);
+                    const uint32_t col = tmem_base + blk * (R * NPAD);
+                    umma_bf16(col + s_first * NPAD, adesc, bd1, idesc1, true);
+                    if (run2 > 0) umma_bf16(col, adesc, bd2, idesc2, true);
+                  }
+                }
+              }
+            }
+          }
+        }
+        if (leader) {
+          umma_commit(&bar_empty[slot]);                               // this input plane is fully consumed
+          if (pl >= 1) umma_commit(&bar_tfull[(R - (P - 1) % R) % R]);  // output plane pl-1 complete
+          if (pl == D - 1) umma_commit(&bar_tfull[(R - P % R) % R]);    // last plane of the tile complete
+        }
+        __syncwarp();
+      }
+      g_base += D;
+    }
+  } else {
+    // =================================== epilogue (8 warps: 2 per TMEM lane quarter) =======================
+    // A warp may only touch TMEM lanes 32*(warp%4)..+31; the two warps of a quarter split the (block, 16-column chunk)
+    // items of an output plane.  All of a warp's TMEM loads are issued before the single wait.
+    constexpr int CHUNKS = NPAD / 16;
+    constexpr int ITEMS = C::NBLK * CHUNKS;
+    constexpr int PER = (ITEMS + 1) / 2;
+    const int quarter = warp & 3, half = warp >> 2;
+    const int m = quarter * 32 + lane;
+    const int hrow = m >> 3, wcol = m & 7;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    // zero the accumulator ring once (each half its share of the columns), then publish every stage as free
+    for (int c0 = half * 16; c0 < C::COLS; c0 += 32) tmem_zero16(lane_base + c0);
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0)
+      for (int s = 0; s < R; ++s) mbar_arrive(&bar_tempty[s]);
+    uint32_t g_base = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int tw = tile % p.tiles_w;
+      const int th = (tile / p.tiles_w) % p.tiles_h;
+      const int b = tile / (p.tiles_w * p.tiles_h);
+      const int nblk = min(C::NBLK, (p.Mw - tw * WT + 7) >> 3);
+      const int h = th * 16 + hrow;
+      for (int d = 0; d < D; ++d) {
+        const uint32_t Q = g_base + d;
+        const uint32_t st = (R - Q % R) % R;
+        mbar_wait(&bar_tfull[st], (Q / R) & 1u);
+        tc_fence_after_sync();
+        uint32_t v[PER][16];
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          const int item = i * 2 + half;
+          const int blk = item / CHUNKS, c0 = (item % CHUNKS) * 16;
+          if (item < ITEMS && blk < nblk) tmem_ld16(lane_base + blk * (R * NPAD) + st * NPAD + c0, v[i]);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {                              // leave the stage zeroed for its next output plane
+          const int item = i * 2 + half;
+          const int blk = item / CHUNKS, c0 = (item % CHUNKS) * 16;
+          if (item < ITEMS && blk < nblk) tmem_zero16(lane_base + blk * (R * NPAD) + st * NPAD + c0);
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          const int item = i * 2 + half;
+          const int blk = item / CHUNKS, c0 = (item % CHUNKS) * 16;
+          const int w = tw * WT + blk * 8 + wcol;
+          const bool ok = (item < ITEMS) && (blk < nblk) && (h < H) && (w < W);
+          if (!ok || c0 >= p.cout || (p.debug & 4)) continue;
+          const size_t vox = ((static_cast<size_t>(b) * D + d) * H + h) * static_cast<size_t>(W) + w;
+          const int n = min(16, p.cout - c0);
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[i][j]);
+          if (p.y_f32) {
+            float* yo = reinterpret_cast<float*>(p.y) + vox * p.y_cstride + p.y_coff + c0;
+            const float* ro = p.residual ? reinterpret_cast<const float*>(p.residual) + vox * p.y_cstride + p.y_coff + c0 : nullptr;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {                        // fully unrolled + predicated: keeps f[] in registers
+              if (j < n) {
+                float val = f[j];
+                if (ro && p.res_pre) val += ro[j];
+                val = val * s_scale[c0 + j] + s_shift[c0 + j];
+                if (ro && !p.res_pre) val += ro[j];
+                if (p.relu) val = fmaxf(val, 0.f);
+                yo[j] = val;
+              }
+            }
+          } else {
+            __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + vox * p.y_cstride + p.y_coff + c0;
+            if (p.scale != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = f[j] * s_scale[c0 + j] + s_shift[c0 + j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] += s_shift[c0 + j];
+            }
+            const bool wide = (n == 16) && (((p.y_cstride | p.y_coff) & 15) == 0);   // 32-byte aligned full chunk
+            if (p.residual) {
+              const __nv_bfloat16* ro = reinterpret_cast<const __nv_bfloat16*>(p.residual) + vox * p.y_cstride + p.y_coff + c0;
+              uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+              if (wide) ld_global_v8(ro, r0, r1);
+              else {
+                r0 = *reinterpret_cast<const uint4*>(ro);
+                if (n > 8) r1 = *reinterpret_cast<const uint4*>(ro + 8);
+              }
+              f[0] += bf16_lo(r0.x); f[1] += bf16_hi(r0.x); f[2] += bf16_lo(r0.y); f[3] += bf16_hi(r0.y);
+              f[4] += bf16_lo(r0.z); f[5] += bf16_hi(r0.z); f[6] += bf16_lo(r0.w); f[7] += bf16_hi(r0.w);
+              f[8] += bf16_lo(r1.x); f[9] += bf16_hi(r1.x); f[10] += bf16_lo(r1.y); f[11] += bf16_hi(r1.y);
+              f[12] += bf16_lo(r1.z); f[13] += bf16_hi(r1.z); f[14] += bf16_lo(r1.w); f[15] += bf16_hi(r1.w);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            uint4 o0, o1;
+            o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]); o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
+            o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]); o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+            if (wide) st_global_v8(yo, o0, o1);
+            else {
+              *reinterpret_cast<uint4*>(yo) = o0;
+              if (n > 8) *reinterpret_cast<uint4*>(yo + 8) = o1;
+            }
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[st]);
+      }
+      g_base += D;
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kFMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int CIN, int NPAD, int WT, int NS, int R>
+int launch_fused(ConvKParams kp, cudaStream_t st) {
+  using C = FCfg<CIN, NPAD, WT, NS, R>;
+  kp.tiles_h = (kp.Mh + 15) / 16;
+  kp.tiles_w = (kp.Mw + WT - 1) / WT;
+  kp.ntiles = kp.B * kp.tiles_h * kp.tiles_w;
+  auto kern = conv3d_kdfused_kernel<CIN, NPAD, WT, NS, R>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return dpf::fail("dpf_conv3d_fwd: cannot opt in to %d B shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  const int grid = std::min(kp.ntiles, dpf::sm_count());
+  kern<<<grid, kFThreads, C::SMEM_BYTES, st>>>(kp);
+  return dpf::after_launch("dpf_conv3d_fwd");
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -504,6 +853,14 @@ extern "C" int dpf_conv3d_fwd(const dpf_conv3d_args* a, void* stream) {
   const int npad = npad_for(a->Cout);
   if (geo == GEO_S1) {
     DPF_REQUIRE(a->Cin == 32 || a->Cout <= 32, "dpf_conv3d_fwd: Cin=64 supports Cout<=32 per launch (split on the host)");
+    static int fused = -1;
+    if (fused < 0) { const char* e = getenv("DPF_CONV_FUSED"); fused = e ? atoi(e) : 1; }
+    if (a->kind == 0 && fused && npad <= 32) {                     // kd-fused issue for the 3x3x3 stride-1 layers
+      if (a->Cin == 32 && npad == 32) return launch_fused<32, 32, 16, 4, 8>(kp, st);
+      if (a->Cin == 32 && npad == 16) return launch_fused<32, 16, 16, 4, 8>(kp, st);
+      if (a->Cin == 64 && npad == 32) return launch_fused<64, 32, 8, 4, 16>(kp, st);
+      if (a->Cin == 64 && npad == 16) return launch_fused<64, 16, 8, 4, 16>(kp, st);
+    }
     if (a->Cin == 32 && npad == 32) return launch<GEO_S1, 32, 32, 24, 5>(kp, st);
     if (a->Cin == 32 && npad == 16) return launch<GEO_S1, 32, 16, 24, 5>(kp, st);
     if (a->Cin == 32 && npad == 64) return launch<GEO_S1, 32, 64, 8, 6>(kp, st);
