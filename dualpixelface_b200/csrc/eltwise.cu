@@ -1,0 +1,112 @@
+// Fused per-channel bias + residual + activation for channels-last bf16 tensors (memory-bound, one pass).
+//
+// Used around the cuDNN 2-D convolutions that stay in PyTorch (encoders, ANM normal convs): with BatchNorm folded into
+// the convolution, "conv -> +bias -> (+skip) -> PReLU/ReLU/LeakyReLU" is one read and one write instead of the three
+// elementwise passes PyTorch launches (aten::add_, aten::add, aten::prelu).  The output may be a channel window of a
+// wider tensor (y_cstride / y_coff), which also replaces torch.cat of the DPBlock dilated branches
+// (src/model/stereodpnet/modules.py:42-44 of the reference).
+//   y[p, y_coff + c] = act( x[p, c] + bias[c] + res[p, c] ),  act(v) = v > 0 ? v : slope * v   (slope 0 = ReLU, 1 = none)
+#include "../../include/dpf_sm100.h"
+#include "dpf_common.cuh"
+#include "dpf_ptx.cuh"
+
+namespace {
+
+using namespace dpf;
+
+__global__ void __launch_bounds__(256) bias_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ bias,
+                                                       const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y,
+                                                       long long npix, int C, int y_cstride, int y_coff, float slope) {
+  const int c8n = C >> 3;
+  const long long total = npix * c8n;
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < total;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(q % c8n);
+    const long long pix = q / c8n;
+    const uint4 u = ld_nc_v4(x + pix * C + c8 * 8);
+    float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+    if (bias != nullptr) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8 + 4));
+      f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+    }
+    if (res != nullptr) {
+      const uint4 r = ld_nc_v4(res + pix * C + c8 * 8);
+      f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x); f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+      f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z); f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = f[k] > 0.f ? f[k] : slope * f[k];
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(y + pix * y_cstride + y_coff + c8 * 8) = o;
+  }
+}
+
+}  // namespace
+
+extern "C" int dpf_bias_act(const void* x, const float* bias, const void* res, void* y, long long npix, int C, int y_cstride,
+                            int y_coff, float slope, void* stream) {
+  DPF_REQUIRE(x && y, "dpf_bias_act: null pointer");
+  DPF_REQUIRE(DPF_ALIGNED16(x) && DPF_ALIGNED16(y) && (res == nullptr || DPF_ALIGNED16(res)) && (bias == nullptr || DPF_ALIGNED16(bias)),
+              "dpf_bias_act: pointers must be 16-byte aligned");
+  DPF_REQUIRE(C >= 8 && C % 8 == 0 && y_cstride % 8 == 0 && y_coff % 8 == 0 && y_coff + C <= y_cstride && npix > 0,
+              "dpf_bias_act: bad channel layout C=%d y_cstride=%d y_coff=%d", C, y_cstride, y_coff);
+  const long long total = npix * (C / 8);
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(dpf::sm_count()) * 16));
+  bias_act_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), bias, reinterpret_cast<const __nv_bfloat16*>(res),
+      reinterpret_cast<__nv_bfloat16*>(y), npix, C, y_cstride, y_coff, slope);
+  return dpf::after_launch("dpf_bias_act");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// ANM tail: bilinear x4 upsample (align_corners=True) -> sigmoid -> mean over the K sampled planes -> *2-1, fused.
+// Replaces final_layer (upsampler + Sigmoid) and the mean / rescale of ANM.forward
+// (src/model/stereodpnet/normal_module.py:69-72,185-190): reads [B*K,H4,W4,3] bf16 once, writes [B,3,H,W] fp32 once
+// (the reference materialises the [B*K,3,H,W] tensor twice).
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) anm_tail_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int K,
+                                                       int H4, int W4) {
+  const int H = 4 * H4, W = 4 * W4;
+  const int xo = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int yo = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.z;
+  if (xo >= W || yo >= H) return;
+  const float sh = static_cast<float>(H4 - 1) / static_cast<float>(H - 1);
+  const float sw = static_cast<float>(W4 - 1) / static_cast<float>(W - 1);
+  const float sy = sh * static_cast<float>(yo), sx = sw * static_cast<float>(xo);
+  const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+  const int y1 = y0 + (y0 < H4 - 1 ? 1 : 0), x1 = x0 + (x0 < W4 - 1 ? 1 : 0);
+  const float ly = sy - static_cast<float>(y0), lx = sx - static_cast<float>(x0);
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int k = 0; k < K; ++k) {
+    const __nv_bfloat16* p = x + static_cast<size_t>(b * K + k) * H4 * W4 * 3;
+    const __nv_bfloat16* p00 = p + (static_cast<size_t>(y0) * W4 + x0) * 3;
+    const __nv_bfloat16* p01 = p + (static_cast<size_t>(y0) * W4 + x1) * 3;
+    const __nv_bfloat16* p10 = p + (static_cast<size_t>(y1) * W4 + x0) * 3;
+    const __nv_bfloat16* p11 = p + (static_cast<size_t>(y1) * W4 + x1) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = w00 * __bfloat162float(p00[c]) + w01 * __bfloat162float(p01[c]) + w10 * __bfloat162float(p10[c]) +
+                      w11 * __bfloat162float(p11[c]);
+      acc[c] += 1.0f / (1.0f + __expf(-v));
+    }
+  }
+  const float inv = 2.0f / static_cast<float>(K);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[((static_cast<size_t>(b) * 3 + c) * H + yo) * W + xo] = acc[c] * inv - 1.0f;
+}
+
+}  // namespace
+
+extern "C" int dpf_anm_tail(const void* x, float* out, int B, int K, int H4, int W4, void* stream) {
+  DPF_REQUIRE(x && out, "dpf_anm_tail: null pointer");
+  DPF_REQUIRE(B > 0 && B <= 65535 && K >= 1 && H4 > 1 && W4 > 1, "dpf_anm_tail: bad shape");
+  dim3 grid((4 * W4 + 31) / 32, (4 * H4 + 7) / 8, B);
+  anm_tail_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, K, H4, W4);
+  return dpf::after_launch("dpf_anm_tail");
+}

@@ -1,0 +1,99 @@
+"""Eval-mode execution plan of the StereoDPNet 2-D encoder (adjacent to the hot path).
+
+The convolutions stay cuDNN (bf16, channels-last) but every BatchNorm2d is folded into its convolution and each
+"+bias (+skip) -> PReLU/ReLU" tail runs as ONE pass of ``dpf_bias_act`` instead of the aten::add_ / aten::add /
+aten::prelu kernels PyTorch would launch; the three dilated DPBlock branches are written straight into the channel
+windows of one 96-channel buffer (no torch.cat).  Mirrors feature_extraction.forward / DPBlock.forward of the reference
+(src/model/stereodpnet/modules.py:21-134) -- parameters are read from the module that owns them, nothing is registered.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.utils.fusion import fuse_conv_bn_weights
+
+from . import ops
+
+
+def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d | None):
+    """(weight bf16 channels_last, bias fp32 | None, conv hyper-parameters)."""
+    w, b = conv.weight, conv.bias
+    if bn is not None:
+        w, b = fuse_conv_bn_weights(w, b, bn.running_mean, bn.running_var, bn.eps, bn.weight, bn.bias)
+    w = w.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    b = b.detach().float().contiguous() if b is not None else None
+    return dict(w=w, b=b, stride=conv.stride, pad=conv.padding, dil=conv.dilation, groups=conv.groups)
+
+
+def _conv(x, f):
+    return F.conv2d(x, f["w"], None, f["stride"], f["pad"], f["dil"], f["groups"])
+
+
+def _slope(m) -> float:
+    if isinstance(m, nn.PReLU):
+        assert m.weight.numel() == 1
+        return float(m.weight.detach())
+    if isinstance(m, nn.ReLU):
+        return 0.0
+    raise TypeError(type(m))
+
+
+class _Block:
+    def __init__(self, blk):
+        self.c1, self.s1 = _fold(blk.conv1[0][0], blk.conv1[0][1]), _slope(blk.conv1[1])
+        self.c2, self.s2 = _fold(blk.conv2[0][0], blk.conv2[0][1]), _slope(blk.conv2[1])
+        self.dil = [_fold(m[0], m[1]) for m in blk.conv_dilate]
+        self.c3, self.s3 = _fold(blk.conv3[0], blk.conv3[1]), _slope(blk.prelu)
+        self.c4, self.s4 = _fold(blk.conv4[0][0], blk.conv4[0][1]), _slope(blk.conv4[1])
+        self.dw = _fold(blk.conv5.depthwise, None)
+        self.pw, self.s5 = _fold(blk.conv5.pointwise, blk.conv5.bn), _slope(blk.conv5.prelu)
+        self.skip = _fold(blk.conv_skip, None)
+
+    def __call__(self, x):
+        a = ops.bias_act(_conv(x, self.c1), self.c1["b"], self.s1)
+        y = ops.bias_act(_conv(a, self.c2), self.c2["b"], self.s2)
+        n, c, h, w = y.shape
+        cat = torch.empty(n, h, w, 3 * c, device=y.device, dtype=torch.bfloat16)
+        for i, f in enumerate(self.dil):
+            ops.bias_act(_conv(y, f), f["b"], 1.0, out=cat, y_coff=i * c)
+        t = ops.bias_act(_conv(cat.permute(0, 3, 1, 2), self.c3), self.c3["b"], self.s3, res=a)       # prelu(conv3 + a)
+        u = ops.bias_act(_conv(t, self.c4), self.c4["b"], self.s4)
+        v = ops.bias_act(_conv(_conv(u, self.dw), self.pw), self.pw["b"], self.s5)
+        return ops.bias_act(_conv(x, self.skip), self.skip["b"], 1.0, res=v)                         # + weighted skip
+
+
+class FusedSDPEncoder:
+    def __init__(self, enc):
+        fc = enc.firstconv
+        self.first = [_fold(fc[i][0], fc[i][1]) for i in (0, 2, 4)]
+        self.block1 = _Block(enc.block1)
+        self.inter1 = [_Block(b) for b in enc.interblock1]
+        self.block2 = _Block(enc.block2)
+        self.inter2 = [_Block(b) for b in enc.interblock2]
+        self.block3 = _Block(enc.block3)
+        import copy
+        self.fpn = copy.deepcopy(enc.fpn).eval().to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        self.last = [_fold(enc.lastconv[i][0], enc.lastconv[i][1]) for i in (0, 2)]
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        """x [N,3,H,W] -> features [N,C,H/4,W/4] bf16, channels-last memory format."""
+        from collections import OrderedDict
+        x = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        for f in self.first:
+            x = ops.bias_act(_conv(x, f), f["b"], 0.0)
+        o1 = self.block1(x)
+        o2 = o1
+        for b in self.inter1:
+            o2 = b(o2)
+        o2 = self.block2(o2)
+        o3 = o2
+        for b in self.inter2:
+            o3 = b(o3)
+        o3 = self.block3(o3)
+        f = self.fpn(OrderedDict(layer1=o1, layer2=o2, layer3=o3))
+        up = lambda t, s: F.interpolate(t, scale_factor=s, mode="bilinear", align_corners=True)
+        y = torch.cat([f["layer1"], up(f["layer2"], 2), up(f["layer3"], 4)], 1).contiguous(memory_format=torch.channels_last)
+        for fl in self.last:
+            y = ops.bias_act(_conv(y, fl), fl["b"], 0.0)
+        return y

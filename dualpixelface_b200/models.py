@@ -39,6 +39,10 @@ class _StereoBase(LightningModule):
         """Eval-mode copy of the cuDNN encoder with every BatchNorm2d folded into its convolution, bf16, channels-last
         (kept outside the module tree so that the state_dict layout is untouched; rebuilt by refresh())."""
         enc = self.__dict__.get("_enc_fused")
+        if enc is None and isinstance(self.feature_extraction, M.SDPFeatureExtraction):
+            from .encoder_fused import FusedSDPEncoder
+            enc = FusedSDPEncoder(self.feature_extraction)      # cuDNN convs + dpf_bias_act tails, no torch.cat
+            self.__dict__["_enc_fused"] = enc
         if enc is None:
             import copy
             from torch.nn.utils.fusion import fuse_conv_bn_eval

@@ -473,6 +473,8 @@ class ANM(nn.Module):
                 p[f"w{i}"] = ops.pack_conv_weight(dc.weight.detach(), cin_pad=cpad)
                 p[f"cpad{i}"] = cpad
                 p[f"aff{i}"] = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, conv_bias=dc.bias)
+            p["nconv"] = [(m[0].weight.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
+                           m[0].dilation[0]) for m in self.n_convs]
             self._plan = p
         return self._plan
 
@@ -494,10 +496,12 @@ class ANM(nn.Module):
             f2 = ops.dcn3d(f1, off2, p["w2"], p["cpad2"], p["aff2"][0], p["aff2"][1], relu=True)
             # shared 2-D normal convs on (b*k) slices: cuDNN, bf16 channels-last (adjacent op)
             x = f2.view(b * self.k, f2.shape[2], f2.shape[3], f2.shape[4]).permute(0, 3, 1, 2)
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                x = self.n_convs(x)
-            x = torch.sigmoid(F.interpolate(x.float(), scale_factor=4, mode="bilinear", align_corners=True))
-            normals.append(x.view(b, self.k, 3, x.shape[-2], x.shape[-1]).mean(1) * 2.0 - 1.0)
+            for w2d, dil in p["nconv"]:
+                x = F.conv2d(x, w2d, None, 1, dil, dil)                                # cuDNN, bf16 channels-last
+                x = ops.bias_act(x, None, 0.1) if x.shape[1] % 8 == 0 else F.leaky_relu(x, 0.1)   # LeakyReLU(0.1)
+            # fused x4 bilinear upsample + sigmoid + mean over the k sampled planes + rescale to [-1, 1]
+            from .ops_tail import anm_tail
+            normals.append(anm_tail(x.permute(0, 2, 3, 1).contiguous(), b, self.k))
             off1s.append(off1)
             off2s.append(off2)
         return normals, off1s, off2s

@@ -238,3 +238,29 @@ def anm_gather(out3: torch.Tensor, idx: torch.Tensor, coord: torch.Tensor, minma
     fv = torch.empty(b, k, h4, w4, cpad, device=out3.device, dtype=torch.bfloat16)
     check(lib().dpf_anm_gather(_p(out3), _p(idx), _p(coord), _p(minmax), _p(fv), b, d, k, h4, w4, c, cpad, _stream()), "dpf_anm_gather")
     return fv
+
+
+# ----------------------------------------------------------------------------------------------------------
+# fused bias + residual + activation (channels-last bf16)
+# ----------------------------------------------------------------------------------------------------------
+def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], slope: float, res: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None, y_coff: int = 0) -> torch.Tensor:
+    """y[..., y_coff:y_coff+C] = act(x + bias + res); x is an NCHW-shaped tensor in channels_last memory format (or any
+    [...,C]-contiguous bf16 tensor).  slope: 0 = ReLU, 1 = identity, else PReLU / LeakyReLU slope.  In place when out is None."""
+    if x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
+        c = x.shape[1]
+    elif x.is_contiguous():
+        c = x.shape[-1] if x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last) else x.shape[1]
+    else:
+        raise _lib.DpfError("bias_act: expected a dense channels-last bf16 tensor")
+    if x.dtype != torch.bfloat16 or not x.is_cuda:
+        raise _lib.DpfError("bias_act: expected a CUDA bf16 tensor")
+    npix = x.numel() // c
+    if out is None:
+        out, cstride = x, c
+    else:
+        cstride = out.numel() // npix
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+    check(lib().dpf_bias_act(_p(x), _p(bias), _p(res), _p(out), npix, c, cstride, y_coff, float(slope), _stream()), "dpf_bias_act")
+    return out

@@ -142,6 +142,22 @@ int dpf_anm_gather(const void* out3, const int* idx, const float* coord, const f
 int dpf_dcn3d_fwd(const void* x, const float* offset, const void* w, const float* scale, const float* shift, void* y,
                   int B, int D, int H, int W, int Cin_pad, int x_cstride, int Cout, int relu, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * (7) Fused per-channel bias + residual + activation on channels-last bf16 (one memory pass).  Replaces the
+ *     aten::add_ (conv bias) / aten::add (skip) / aten::prelu|relu|leaky_relu chains around the cuDNN 2-D convolutions of
+ *     the encoders (src/model/stereodpnet/modules.py:21-134) and of ANM's n_convs (normal_module.py:59-66); writing into
+ *     a channel window of a wider tensor also replaces torch.cat of the DPBlock dilated branches (modules.py:42-44).
+ *       y[p, y_coff + c] = act(x[p,c] + bias[c] + res[p,c]),  act(v) = v > 0 ? v : slope*v  (0 = ReLU, 1 = identity)
+ *     x, res [npix, C] bf16; y [npix, y_cstride] bf16; bias fp32 [C]; bias / res may be NULL.
+ * ------------------------------------------------------------------------------------------------- */
+int dpf_bias_act(const void* x, const float* bias, const void* res, void* y, long long npix, int C, int y_cstride,
+                 int y_coff, float slope, void* stream);
+
+/* ANM tail: bilinear x4 upsample (align_corners) -> sigmoid -> mean over K -> *2-1 in one pass.  Replaces final_layer and
+ * the mean / rescale of ANM.forward (src/model/stereodpnet/normal_module.py:69-72,185-190).
+ * x [B*K,H4,W4,3] bf16 (channels-last) -> out [B,3,4*H4,4*W4] fp32. */
+int dpf_anm_tail(const void* x, float* out, int B, int K, int H4, int W4, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
