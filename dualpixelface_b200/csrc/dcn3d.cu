@@ -6,8 +6,9 @@
 //   y[v, o] = relu?( scale[o] * sum_{tap,c} W[o,c,tap] * trilinear(x[:, c], p_v + tap - 1 + offset[v, 3*tap + (0,1,2)]) + shift[o] )
 // x [B,D,H,W,x_cstride] bf16 (the first CINP channels are gathered; zero-padded beyond the real Cin), offset [B,D,H,W,81] fp32 ((d,h,w) per tap), y [B,D,H,W,64] bf16.
 //
-// Work unit: 256 consecutive voxels (2 GEMM blocks of 128 rows).  For every tap, 16 producer warps compute the
-// trilinear sample of all CINP channels (8 threads per voxel, one 16-byte channel chunk each; fp32 blend) and write it
+// Work unit: a 16 x 16 spatial tile of one depth plane = 256 voxels (2 GEMM blocks of 128 rows); every CTA owns a
+// contiguous range of units so that the planes a tap gathers from stay hot in L1 / L2 across taps and units.  For every tap, 16 producer warps compute the
+// trilinear sample of all CINP channels (4 threads per voxel, 32 bytes each; packed-bf16 blend) and write it
 // as the bf16 A tile in the UMMA no-swizzle K-major layout; the tap's weight tile [CINP x 64] is streamed next to it by a
 // 1-D TMA bulk copy.  One elected lane issues the tcgen05.mma; accumulators are double-buffered in TMEM so the
 // epilogue of a unit overlaps the gather of the next.
@@ -23,7 +24,7 @@ constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kProdWarps = 16;
 constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;   // 672
-constexpr int kVoxPerPass = kProdWarps * 32 / 8;              // 8 threads (one 16-byte channel chunk each) per voxel
+constexpr int kVoxPerPass = kProdWarps * 32 / 4;              // 4 threads (32 bytes = two channel chunks each) per voxel
 constexpr int kNOut = 64;
 constexpr int kBlocks = 2;                                    // GEMM blocks (128 voxels each) per work unit
 constexpr int kStages = 3;
@@ -38,7 +39,7 @@ struct DcnParams {
   __nv_bfloat16* y;
   int B, D, H, W, relu, x_cstride;
   long long nvox;
-  int nunits;
+  int nunits, tiles_h, tiles_w;
 };
 
 template <int CINP>
@@ -54,6 +55,16 @@ struct DCfg {
   static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 2 * kNOut * 4 + (2 * kStages + 4) * 8 + 16 + 128;
   static_assert(CINP % 16 == 0, "CINP must be a multiple of 16");
 };
+
+// unit -> (d, h0, w0, b): depth fastest, so that consecutive units of a CTA share two of their three input planes
+__device__ __forceinline__ void unit_coords(int unit, const DcnParams& p, int& d, int& h0, int& w0, int& b) {
+  d = unit % p.D;
+  int t = unit / p.D;
+  w0 = (t % p.tiles_w) * 16;
+  t /= p.tiles_w;
+  h0 = (t % p.tiles_h) * 16;
+  b = t / p.tiles_h;
+}
 
 template <int CINP>
 __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constant__ DcnParams p) {
@@ -96,31 +107,41 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
   tc_fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
   const int D = p.D, H = p.H, W = p.W;
+  // contiguous unit range per CTA (neighbouring tiles / depth planes back to back: L1 / L2 reuse of the gathered planes)
+  const int per_cta = (p.nunits + gridDim.x - 1) / gridDim.x;
+  const int unit_lo = min(static_cast<int>(blockIdx.x) * per_cta, p.nunits), unit_hi = min(unit_lo + per_cta, p.nunits);
 
   if (warp > kMmaWarp) {
     // ======================= producers: trilinear gather -> bf16 A tile; weight tile by TMA ==================
     const int ptid = threadIdx.x - (kMmaWarp + 1) * 32;      // 0..511
-    const int c8 = ptid & 7;
-    const int vsub = ptid >> 3;                              // 0..63
+    const int cq = ptid & 3;                                  // which pair of 16-byte channel chunks
+    const int vsub = ptid >> 2;                              // 0..127
+    // 4 lanes per voxel, 32 bytes (two 16-byte channel chunks) each: one LDG.256 per corner per lane, a voxel's 128-byte
+    // line is touched exactly once per corner, and the per-(voxel,tap) coordinate / weight arithmetic is replicated
+    // 4x instead of 8x.  All addresses are 32-bit byte offsets from the (uniform) tensor base.
     constexpr int PASSES = kBlocks * 128 / kVoxPerPass;
+    static_assert(C::NCH % 2 == 0, "channel chunks are handled in pairs");
     const int HW = H * W;
-    const int cs = p.x_cstride;
-    const __nv_bfloat16* xc = p.x + (c8 < C::NCH ? c8 : 0) * 8;
+    const uint32_t cs2 = static_cast<uint32_t>(p.x_cstride) * 2u;            // bytes per voxel
+    const bool lane_live = (2 * cq) < C::NCH;
+    const char* xbytes = reinterpret_cast<const char*>(p.x);
+    const uint32_t lane_off = (lane_live ? cq : 0) * 32u;
     uint32_t g = 0;
-    for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
-      const long long v0 = static_cast<long long>(unit) * (kBlocks * 128);
-      // voxel coordinates of this thread's PASSES rows: decomposed once per unit, reused by all 27 taps
-      int vd[PASSES], vh[PASSES], vw[PASSES], vbase[PASSES];
+    for (int unit = unit_lo; unit < unit_hi; ++unit) {
+      // unit = 16 x 16 spatial tile of one depth plane; row r of the unit -> (h0 + r/16, w0 + r%16).  Voxel
+      // coordinates of this thread's PASSES rows are decoded once per unit and reused by all 27 taps.
+      int ud, uh0, uw0, ub;
+      unit_coords(unit, p, ud, uh0, uw0, ub);
+      int vh[PASSES], vw[PASSES];
       bool vlive[PASSES];
+      const int vbase = ub * D * HW;                                  // voxel index of (b, 0, 0, 0); < 2^31 (host check)
 #pragma unroll
       for (int ps = 0; ps < PASSES; ++ps) {
-        const long long v = v0 + ps * kVoxPerPass + vsub;
-        vlive[ps] = (v < p.nvox) && (c8 < C::NCH);
-        int t = static_cast<int>(vlive[ps] ? v : 0);               // nvox < 2^31 (checked on the host)
-        vw[ps] = t % W; t /= W;
-        vh[ps] = t % H; t /= H;
-        vd[ps] = t % D;
-        vbase[ps] = (t / D) * D * HW;                               // voxel index of (b, 0, 0, 0)
+        const int r = ps * kVoxPerPass + vsub;
+        const int hh = uh0 + (r >> 4), ww = uw0 + (r & 15);
+        vlive[ps] = (hh < H) && (ww < W) && lane_live;
+        vh[ps] = vlive[ps] ? hh : 0;
+        vw[ps] = vlive[ps] ? ww : 0;
       }
       for (int tap = 0; tap < kTaps; ++tap, ++g) {
         const int stage = g % kStages;
@@ -132,12 +153,13 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
           bulk_g2s(smem_u32(sa + C::A_STAGE_BYTES), p.w + static_cast<size_t>(tap) * (C::W_TAP_BYTES / 2), C::W_TAP_BYTES, &bar_full[stage]);
         }
         const int ti = tap / 9 - 1, tj = (tap / 3) % 3 - 1, tk = tap % 3 - 1;
+        const float fdz = static_cast<float>(ud + ti);
 #pragma unroll
         for (int ps = 0; ps < PASSES; ++ps) {
           const int r = ps * kVoxPerPass + vsub;             // row inside the work unit (0..255)
-          const int vox = vbase[ps] + (vd[ps] * H + vh[ps]) * W + vw[ps];
+          const int vox = vbase + (ud * H + vh[ps]) * W + vw[ps];
           const float* op = p.offset + static_cast<size_t>(vox) * 81 + tap * 3;
-          const float pd = static_cast<float>(vd[ps] + ti) + __ldg(op + 0);
+          const float pd = fdz + __ldg(op + 0);
           const float phh = static_cast<float>(vh[ps] + tj) + __ldg(op + 1);
           const float pw = static_cast<float>(vw[ps] + tk) + __ldg(op + 2);
           const bool inside = vlive[ps] && pd > -1.f && phh > -1.f && pw > -1.f && pd < static_cast<float>(D) &&
@@ -153,42 +175,57 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
           const int dc0 = min(max(d0, 0), D - 1), dc1 = min(max(d0 + 1, 0), D - 1);
           const int hc0 = min(max(h0, 0), H - 1), hc1 = min(max(h0 + 1, 0), H - 1);
           const int wc0 = min(max(w0, 0), W - 1), wc1 = min(max(w0 + 1, 0), W - 1);
-          const int r00 = vbase[ps] + dc0 * HW + hc0 * W, r01 = vbase[ps] + dc0 * HW + hc1 * W;
-          const int r10 = vbase[ps] + dc1 * HW + hc0 * W, r11 = vbase[ps] + dc1 * HW + hc1 * W;
-          uint4 u[8];
-          u[0] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r00 + wc0) * cs));
-          u[1] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r00 + wc1) * cs));
-          u[2] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r01 + wc0) * cs));
-          u[3] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r01 + wc1) * cs));
-          u[4] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r10 + wc0) * cs));
-          u[5] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r10 + wc1) * cs));
-          u[6] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r11 + wc0) * cs));
-          u[7] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<size_t>(r11 + wc1) * cs));
+          const uint32_t b00 = static_cast<uint32_t>(vbase + dc0 * HW + hc0 * W) * cs2 + lane_off;
+          const uint32_t b01 = static_cast<uint32_t>(vbase + dc0 * HW + hc1 * W) * cs2 + lane_off;
+          const uint32_t b10 = static_cast<uint32_t>(vbase + dc1 * HW + hc0 * W) * cs2 + lane_off;
+          const uint32_t b11 = static_cast<uint32_t>(vbase + dc1 * HW + hc1 * W) * cs2 + lane_off;
+          const uint32_t o0 = static_cast<uint32_t>(wc0) * cs2, o1 = static_cast<uint32_t>(wc1) * cs2;
+          uint4 ua[8], ub2[8];
+          ld_global_v8(xbytes + (b00 + o0), ua[0], ub2[0]);
+          ld_global_v8(xbytes + (b00 + o1), ua[1], ub2[1]);
+          ld_global_v8(xbytes + (b01 + o0), ua[2], ub2[2]);
+          ld_global_v8(xbytes + (b01 + o1), ua[3], ub2[3]);
+          ld_global_v8(xbytes + (b10 + o0), ua[4], ub2[4]);
+          ld_global_v8(xbytes + (b10 + o1), ua[5], ub2[5]);
+          ld_global_v8(xbytes + (b11 + o0), ua[6], ub2[6]);
+          ld_global_v8(xbytes + (b11 + o1), ua[7], ub2[7]);
           const float a00 = wd0 * wh0, a01 = wd0 * wh1, a10 = wd1 * wh0, a11 = wd1 * wh1;
           const float cw[8] = {a00 * ww0, a00 * ww1, a01 * ww0, a01 * ww1, a10 * ww0, a10 * ww1, a11 * ww0, a11 * ww1};
           // packed bf16 blend (HFMA2.BF16): the blended A tile is rounded to bf16 for the MMA anyway
-          __nv_bfloat162 acc[4];
+          __nv_bfloat162 acc[8];
           {
             const __nv_bfloat162 w2 = __float2bfloat162_rn(cw[0]);
-            acc[0] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[0].x));
-            acc[1] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[0].y));
-            acc[2] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[0].z));
-            acc[3] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[0].w));
+            acc[0] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[0].x));
+            acc[1] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[0].y));
+            acc[2] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[0].z));
+            acc[3] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[0].w));
+            acc[4] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[0].x));
+            acc[5] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[0].y));
+            acc[6] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[0].z));
+            acc[7] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[0].w));
           }
 #pragma unroll
           for (int c = 1; c < 8; ++c) {
             const __nv_bfloat162 w2 = __float2bfloat162_rn(cw[c]);
-            acc[0] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[c].x), acc[0]);
-            acc[1] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[c].y), acc[1]);
-            acc[2] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[c].z), acc[2]);
-            acc[3] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&u[c].w), acc[3]);
+            acc[0] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[c].x), acc[0]);
+            acc[1] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[c].y), acc[1]);
+            acc[2] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[c].z), acc[2]);
+            acc[3] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[c].w), acc[3]);
+            acc[4] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[c].x), acc[4]);
+            acc[5] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[c].y), acc[5]);
+            acc[6] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[c].z), acc[6]);
+            acc[7] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[c].w), acc[7]);
           }
-          if (c8 < C::NCH) {
-            uint4 o;
-            o.x = *reinterpret_cast<uint32_t*>(&acc[0]); o.y = *reinterpret_cast<uint32_t*>(&acc[1]);
-            o.z = *reinterpret_cast<uint32_t*>(&acc[2]); o.w = *reinterpret_cast<uint32_t*>(&acc[3]);
+          if (lane_live) {
+            uint4 oa, ob;
+            oa.x = *reinterpret_cast<uint32_t*>(&acc[0]); oa.y = *reinterpret_cast<uint32_t*>(&acc[1]);
+            oa.z = *reinterpret_cast<uint32_t*>(&acc[2]); oa.w = *reinterpret_cast<uint32_t*>(&acc[3]);
+            ob.x = *reinterpret_cast<uint32_t*>(&acc[4]); ob.y = *reinterpret_cast<uint32_t*>(&acc[5]);
+            ob.z = *reinterpret_cast<uint32_t*>(&acc[6]); ob.w = *reinterpret_cast<uint32_t*>(&acc[7]);
             const int blk = r >> 7, row = r & 127;
-            *reinterpret_cast<uint4*>(sa + blk * C::A_BLOCK_BYTES + c8 * C::A_CHUNK_BYTES + row * 16) = o;
+            uint8_t* dst = sa + blk * C::A_BLOCK_BYTES + (2 * cq) * C::A_CHUNK_BYTES + row * 16;
+            *reinterpret_cast<uint4*>(dst) = oa;
+            *reinterpret_cast<uint4*>(dst + C::A_CHUNK_BYTES) = ob;
           }
         }
         fence_proxy_async_smem();
@@ -204,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
     const uint32_t sbase = smem_u32(s_stage);
     const bool leader = elect_one();
     uint32_t g = 0, it = 0;
-    for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x, ++it) {
+    for (int unit = unit_lo; unit < unit_hi; ++unit, ++it) {
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       mbar_wait(&bar_tempty[as], aph ^ 1u);
       tc_fence_after_sync();
@@ -233,13 +270,17 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
   } else {
     // ======================================= epilogue =======================================================
     uint32_t it = 0;
-    for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x, ++it) {
+    for (int unit = unit_lo; unit < unit_hi; ++unit, ++it) {
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       mbar_wait(&bar_tfull[as], aph);
       tc_fence_after_sync();
+      int ud, uh0, uw0, ub;
+      unit_coords(unit, p, ud, uh0, uw0, ub);
 #pragma unroll 1
       for (int blk = 0; blk < kBlocks; ++blk) {
-        const long long v = static_cast<long long>(unit) * (kBlocks * 128) + blk * 128 + warp * 32 + lane;
+        const int r = blk * 128 + warp * 32 + lane;
+        const int hh = uh0 + (r >> 4), ww = uw0 + (r & 15);
+        const long long v = (hh < H && ww < W) ? ((static_cast<long long>(ub) * D + ud) * H + hh) * W + ww : p.nvox;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + (as * kBlocks + blk) * kNOut;
 #pragma unroll
         for (int c0 = 0; c0 < kNOut; c0 += 16) {
@@ -298,7 +339,7 @@ extern "C" int dpf_dcn3d_fwd(const void* x, const float* offset, const void* w, 
   DPF_REQUIRE(x && offset && w && y, "dpf_dcn3d_fwd: null pointer");
   DPF_REQUIRE(DPF_ALIGNED16(x) && DPF_ALIGNED16(w) && DPF_ALIGNED16(y), "dpf_dcn3d_fwd: pointers must be 16-byte aligned");
   DPF_REQUIRE(Cout == kNOut, "dpf_dcn3d_fwd: Cout=%d, only 64 is built", Cout);
-  DPF_REQUIRE(Cin_pad == 48 || Cin_pad == 64, "dpf_dcn3d_fwd: Cin_pad=%d must be 48 or 64", Cin_pad);
+  DPF_REQUIRE(Cin_pad == 32 || Cin_pad == 64, "dpf_dcn3d_fwd: Cin_pad=%d must be 32 or 64", Cin_pad);
   DPF_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "dpf_dcn3d_fwd: bad shape");
   DPF_REQUIRE(static_cast<long long>(B) * D * H * W < (1LL << 31) / 128, "dpf_dcn3d_fwd: tensor too large for 32-bit voxel indexing");
   DPF_REQUIRE(x_cstride >= Cin_pad && x_cstride % 8 == 0, "dpf_dcn3d_fwd: x_cstride=%d must be a multiple of 8 >= Cin_pad", x_cstride);
@@ -311,8 +352,10 @@ extern "C" int dpf_dcn3d_fwd(const void* x, const float* offset, const void* w, 
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.B = B; p.D = D; p.H = H; p.W = W; p.relu = relu; p.x_cstride = x_cstride;
   p.nvox = static_cast<long long>(B) * D * H * W;
-  p.nunits = static_cast<int>((p.nvox + kBlocks * 128 - 1) / (kBlocks * 128));
+  p.tiles_h = (H + 15) / 16;
+  p.tiles_w = (W + 15) / 16;
+  p.nunits = B * D * p.tiles_h * p.tiles_w;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (Cin_pad == 48) return launch_dcn<48>(p, st);
+  if (Cin_pad == 32) return launch_dcn<32>(p, st);
   return launch_dcn<64>(p, st);
 }
