@@ -18,8 +18,11 @@ from .synthetic import synthetic_batch
 
 class _StereoBase(LightningModule):
     predict_normal = False
+    train_supported = False
 
     def _common_init(self, option):
+        from .losses import LossModel
+        self.loss_model = LossModel(option)
         self.option = option
         self.mindisp = option.model.mindisp
         self.maxdisp = option.model.maxdisp
@@ -66,6 +69,12 @@ class _StereoBase(LightningModule):
 
     def _features(self, ref_img, tgt_img):
         b = ref_img.shape[0]
+        if self.training:
+            # the reference runs the encoder once per view (mainmodel.py:72-83): BatchNorm batch statistics are per call
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.encoder_autocast):
+                fr, ft = self.feature_extraction(ref_img.float()), self.feature_extraction(tgt_img.float())
+            to_cl = lambda t: t.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+            return to_cl(fr), to_cl(ft)
         x = torch.cat([ref_img, tgt_img], 0)
         if self.encoder_autocast:
             f = self._fused_encoder()(x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
@@ -85,9 +94,10 @@ class _StereoBase(LightningModule):
     def forward(self, batch):
         if not batch["left"].is_cuda:
             raise RuntimeError("the sm_100a hot path needs CUDA tensors; there is no CPU implementation")
-        if self.training:
-            raise NotImplementedError("the sm_100a training path (batch-statistics BatchNorm, aggregation backward) is not "
-                                      "built yet; call .eval().  There is deliberately no fallback.")
+        if self.training and not self.train_supported:
+            raise NotImplementedError(f"{type(self).__name__}: the sm_100a training path of the ASM volume and the ANM branch "
+                                      "(their backward kernels) is not built yet; call .eval().  There is deliberately no "
+                                      "fallback.  (PSMNET trains: cost volume, aggregation and regression have backward paths.)")
         ref_img, tgt_img = self._select_views(batch)
         self._mark("start")
         ref_fea, tgt_fea = self._features(ref_img, tgt_img)
@@ -107,6 +117,8 @@ class _StereoBase(LightningModule):
                    "prob_depth": torch.stack(cost_p, 1) if cost_p[0] is not None else None,
                    "pred_normal": normal,
                    "ref_feature": ref_fea.float().max(-1)[0]}
+        if self.training and "disp" in batch:
+            results.update(self.loss_model.forward(results, batch))
         return results
 
     def refresh(self):
@@ -170,6 +182,8 @@ class STEREODPNET(_StereoBase):
 
 
 class PSMNET(_StereoBase):
+    train_supported = True
+
     def __init__(self, option):
         super().__init__()
         self._common_init(option)

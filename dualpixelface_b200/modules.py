@@ -282,10 +282,12 @@ class CostVolumePSM(nn.Module):
             raise NotImplementedError(f"cost volume style is not defined : {self.style}")
 
     def forward(self, ref_feat, tar_feat):
-        if self.style == "psmnet":
-            return ops.costvol_fwd(ref_feat, tar_feat, self.shifts, "concat")
-        if self.style == "difference":
-            return ops.costvol_fwd(ref_feat, tar_feat, self.shifts, "diff")
+        if self.style in ("psmnet", "difference"):
+            mode = "concat" if self.style == "psmnet" else "diff"
+            if ref_feat.requires_grad or tar_feat.requires_grad:
+                from .train_ops import CostVolumeFn
+                return CostVolumeFn.apply(ref_feat, tar_feat, self.shifts, mode, 0)
+            return ops.costvol_fwd(ref_feat, tar_feat, self.shifts, mode)
         c = ref_feat.shape[-1]
         assert c % self.group_num == 0, "group_num must divide the feature channels (psmnet/modules.py:217)"
         raise NotImplementedError("gwcnet style (concat | gwc, 2C+G input channels) needs a Cin=2C+G first layer; "
@@ -374,8 +376,41 @@ class PSMNetHGAggregation(nn.Module):
         out = self._run(name + ".conv6", post, residual=cost0, relu=False)     # "+ cost0" of modules.py:315,318,321 fused
         return out, pre, post
 
+    # ---- training: batch-statistics BatchNorm, autograd Functions over the same kernels (train_ops.py) ----------
+    def _tl(self, seq, kind, x, residual=None, relu=True):
+        from .train_ops import ConvBNAct, LayerCfg
+        conv, bn = seq[0], seq[1]
+        return ConvBNAct.apply(x, conv.weight, bn.weight, bn.bias, residual, LayerCfg(kind, relu, bn))
+
+    def _hourglass_train(self, hg, x, presqu, postsqu, cost0):
+        o = self._tl(hg.conv1[0], KIND_S2, x)
+        pre = self._tl(hg.conv2, KIND_3x3x3, o, residual=postsqu, relu=True)
+        o = self._tl(hg.conv3[0], KIND_S2, pre)
+        o = self._tl(hg.conv4[0], KIND_3x3x3, o)
+        post = self._tl(hg.conv5, KIND_T2, o, residual=presqu if presqu is not None else pre, relu=True)
+        out = self._tl(hg.conv6, KIND_T2, post, residual=cost0, relu=False)
+        return out, pre, post
+
+    def _forward_train(self, cost):
+        from .train_ops import HeadConv
+        c0 = self._tl(self.dres0[0], KIND_3x3x3, cost)
+        c0 = self._tl(self.dres0[2], KIND_3x3x3, c0)
+        r = self._tl(self.dres1[0], KIND_3x3x3, c0)
+        cost0 = self._tl(self.dres1[2], KIND_3x3x3, r, residual=c0, relu=False)
+        out1, pre1, post1 = self._hourglass_train(self.dres2, cost0, None, None, cost0)
+        out2, _p2, post2 = self._hourglass_train(self.dres3, out1, pre1, post1, cost0)
+        out3, _p3, _q3 = self._hourglass_train(self.dres4, out2, pre1, post2, cost0)
+        costs, prev = [], None
+        for k, o in ((1, out1), (2, out2), (3, out3)):
+            cl = getattr(self, f"classif{k}")
+            prev = HeadConv.apply(self._tl(cl[0], KIND_3x3x3, o), cl[2].weight, prev)
+            costs.append(prev)
+        costs = [c.squeeze(-1) for c in costs]
+        return [costs[2], costs[1], costs[0]], [out3, out2, out1]
+
     def forward(self, cost: torch.Tensor, all_heads: Optional[bool] = None):
-        _require_eval(self)
+        if self.training:
+            return self._forward_train(cost)
         self._build()
         c0 = self._run("dres0.0", cost)
         c0 = self._run("dres0.2", c0)
@@ -412,6 +447,11 @@ class disp_regression(nn.Module):
         disps, probs = [], []
         for cost in x:
             assert cost.dim() == 4
+            if cost.requires_grad:
+                from .train_ops import RegressFn
+                disps.append(RegressFn.apply(cost, self.mindisp, self.step))
+                probs.append(None)
+                continue
             d, p = ops.regress_fwd(cost.contiguous(), self.mindisp, self.step, self.want_prob)
             disps.append(d)
             probs.append(p)

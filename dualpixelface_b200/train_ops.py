@@ -1,0 +1,173 @@
+"""Training path of the hot path: autograd Functions over the sm_100a kernels (forward AND backward).
+
+Forward of one reference layer  ``Conv3d/ConvTranspose3d -> BatchNorm3d (batch statistics) [-> + residual] [-> ReLU]``
+(convbn_3d, src/module/asm/basics.py:32-36; used by src/model/stereodpnet/modules.py:204-337):
+    z = conv(x)                      tcgen05 engine (dpf_conv3d_fwd), raw bf16 output
+    mean, var = stats(z)             dpf_channel_stats
+    y = act(z*a + b + res)           dpf_affine_act
+Backward:
+    S1, S2 = sum g, sum g*z          dpf_bn_bwd_reduce      (g = dy masked by the saved ReLU output)
+    dz, dres                         dpf_bn_bwd_apply
+    dx = conv^T(dz)                  the SAME tcgen05 engine with transformed weights: a stride-1 conv's data gradient is a
+                                     stride-1 conv with flipped/transposed taps, a stride-2 conv's is the transposed-conv kind,
+                                     a transposed conv's is the stride-2 kind
+    dW                               cuDNN weight-gradient via aten.convolution_backward on the channels-last views
+                                     (library call for now; a tcgen05 wgrad kernel is the next item)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+
+from . import _lib, ops
+from .layers import KIND_3x3x3, KIND_S2, KIND_T2, TCConv3d
+
+
+def _npix(t):
+    return t.numel() // t.shape[-1]
+
+
+def _affine_act(z, scale, bias, res, slope):
+    y = torch.empty_like(z)
+    _lib.check(ops.lib().dpf_affine_act(ops._p(z), ops._p(scale), ops._p(bias), ops._p(res), ops._p(y), _npix(z), z.shape[-1],
+                                        float(slope), ops._stream()), "dpf_affine_act")
+    return y
+
+
+def _bn_bwd(dy, y, z, a, mean, inv_std, relu, want_dres):
+    c, n = z.shape[-1], _npix(z)
+    sums = torch.empty(2 * c, device=z.device, dtype=torch.float32)
+    _lib.check(ops.lib().dpf_bn_bwd_reduce(ops._p(dy), ops._p(y), ops._p(z), ops._p(sums), n, c, int(relu), ops._stream()),
+               "dpf_bn_bwd_reduce")
+    s1, s2 = sums[:c], sums[c:]
+    centred = s2 - mean * s1
+    coef = torch.cat([a, s1 / n, inv_std * inv_std * centred / n, mean]).contiguous()
+    dz = torch.empty_like(z)
+    dres = torch.empty_like(z) if want_dres else None
+    _lib.check(ops.lib().dpf_bn_bwd_apply(ops._p(dy), ops._p(y), ops._p(z), ops._p(coef), ops._p(dz), ops._p(dres), n, c, int(relu),
+                                          ops._stream()), "dpf_bn_bwd_apply")
+    return dz, dres, inv_std * centred, s1          # dz, dres, dgamma, dbeta
+
+
+def _ncdhw(t):
+    """[B,D,H,W,C] contiguous -> logical NCDHW view with channels_last_3d strides (what cuDNN wants)."""
+    return t.permute(0, 4, 1, 2, 3)
+
+
+def _wgrad(x, dz, weight, kind):
+    """dW through cuDNN (aten.convolution_backward), inputs bf16 channels-last-3d, result cast back to the master dtype."""
+    transposed = kind == KIND_T2
+    stride = [1, 1, 1] if kind == KIND_3x3x3 else [2, 2, 2]
+    gw = torch.ops.aten.convolution_backward(_ncdhw(dz), _ncdhw(x), weight.to(torch.bfloat16), None, stride, [1, 1, 1], [1, 1, 1],
+                                             transposed, [1, 1, 1] if transposed else [0, 0, 0], 1, [False, True, False])[1]
+    return gw.to(weight.dtype)
+
+
+def _dgrad(dz, weight, kind):
+    if kind == KIND_3x3x3:
+        return TCConv3d(weight.transpose(0, 1).flip(2, 3, 4), KIND_3x3x3)(dz)
+    if kind == KIND_S2:                     # adjoint of a stride-2 conv = transposed conv with the same weight tensor
+        return TCConv3d(weight, KIND_T2, transposed=True)(dz)
+    return TCConv3d(weight, KIND_S2)(dz)    # adjoint of a transposed conv = stride-2 conv with the same weight tensor
+
+
+@dataclass
+class LayerCfg:
+    kind: int
+    relu: bool
+    bn: Optional[torch.nn.BatchNorm3d]      # running statistics are updated in place (momentum, unbiased variance)
+
+
+class ConvBNAct(Function):
+    """y = act(BN_train(conv(x)) + residual); all activations [B,D,H,W,C] bf16."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, residual, cfg: LayerCfg):
+        z = TCConv3d(weight, cfg.kind, transposed=cfg.kind == KIND_T2)(x)
+        c, n = z.shape[-1], _npix(z)
+        st = ops.channel_stats(z.view(1, n, c))[0]
+        mean = st[:, 0] / n
+        var = (st[:, 1] / n - mean * mean).clamp_min(0.0)
+        eps = cfg.bn.eps if cfg.bn is not None else 1e-5
+        inv_std = torch.rsqrt(var + eps)
+        a = (gamma.float() * inv_std).contiguous()
+        b = (beta.float() - mean * a).contiguous()
+        y = _affine_act(z, a, b, residual, 0.0 if cfg.relu else 1.0)
+        if cfg.bn is not None and cfg.bn.track_running_stats:
+            m = cfg.bn.momentum
+            cfg.bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+            cfg.bn.running_var.mul_(1 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
+            cfg.bn.num_batches_tracked += 1
+        ctx.save_for_backward(x, weight, z, y, a, mean, inv_std)
+        ctx.cfg, ctx.has_res = cfg, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, z, y, a, mean, inv_std = ctx.saved_tensors
+        cfg = ctx.cfg
+        dy = dy.to(torch.bfloat16).contiguous()
+        dz, dres, dgamma, dbeta = _bn_bwd(dy, y, z, a, mean, inv_std, cfg.relu, ctx.has_res)
+        dx = _dgrad(dz, weight, cfg.kind) if ctx.needs_input_grad[0] else None
+        dw = _wgrad(x, dz, weight, cfg.kind)
+        return dx, dw, dgamma, dbeta, dres, None
+
+
+class HeadConv(Function):
+    """cost = conv3x3x3(x, w[1,C,3,3,3]) + prev  (classif{k}.2 + the cumulative adds of modules.py:323-325); fp32 [B,D,H,W,1]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, prev):
+        y = TCConv3d(weight, KIND_3x3x3)(x, residual=prev, out_f32=True)
+        ctx.save_for_backward(x, weight)
+        ctx.has_prev = prev is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.float().contiguous()
+        c = x.shape[-1]
+        dzp = torch.zeros(*dy.shape[:-1], c, device=dy.device, dtype=torch.bfloat16)
+        dzp[..., 0] = dy[..., 0]
+        wt = torch.zeros(c, c, 3, 3, 3, device=weight.device, dtype=torch.float32)
+        wt[:, 0] = weight[0].flip(1, 2, 3)                     # W'[ci, 0, k] = W[0, ci, flip(k)]
+        dx = TCConv3d(wt, KIND_3x3x3)(dzp)
+        dw = _wgrad(x, dy.to(torch.bfloat16), weight, KIND_3x3x3)
+        return dx, dw, (dy if ctx.has_prev else None)
+
+
+class CostVolumeFn(Function):
+    """Integer-shift volume (dpf_costvol_fwd / dpf_costvol_bwd)."""
+
+    @staticmethod
+    def forward(ctx, ref, tgt, shifts, mode, groups):
+        ctx.save_for_backward(ref, tgt)
+        ctx.args = (list(shifts), mode, groups)
+        return ops.costvol_fwd(ref, tgt, shifts, mode, groups)
+
+    @staticmethod
+    def backward(ctx, dvol):
+        ref, tgt = ctx.saved_tensors
+        shifts, mode, groups = ctx.args
+        dref, dtgt = ops.costvol_bwd(ref, tgt, dvol.to(torch.bfloat16).contiguous(), shifts, mode, groups)
+        return dref, dtgt, None, None, None
+
+
+class RegressFn(Function):
+    """Fused upsample + soft-argmin (dpf_regress_fwd / dpf_regress_bwd); cost [B,D,H4,W4] fp32 -> disparity [B,H,W]."""
+
+    @staticmethod
+    def forward(ctx, cost, mindisp, step):
+        cost = cost.contiguous()
+        ctx.save_for_backward(cost)
+        ctx.args = (mindisp, step)
+        return ops.regress_fwd(cost, mindisp, step, False)[0]
+
+    @staticmethod
+    def backward(ctx, ddisp):
+        (cost,) = ctx.saved_tensors
+        return ops.regress_bwd(cost, ddisp.float().contiguous(), *ctx.args), None, None

@@ -59,10 +59,11 @@ def test_model_eval_parity(name, hw):
         assert n_err.mean().item() < 2e-2 and n_err.max().item() < 0.15
 
 
-def test_training_mode_fails_loudly():
-    model = build("psmnet").cuda().train()
+def test_unbuilt_training_path_fails_loudly():
+    """StereoDPNet's ASM volume / ANM backward kernels do not exist yet: train mode must raise, not fall back."""
+    model = build("stereodpnet").cuda().train()
     with pytest.raises(NotImplementedError):
-        model(to_cuda(synthetic_batch(2, 256, 256, training=True)))
+        model(to_cuda(synthetic_batch(2, 64, 96, training=True)))
 
 
 def test_cpu_input_fails_loudly():
