@@ -253,7 +253,9 @@ class CostVolumeSDP(nn.Module):
 
     def forward(self, ref_feat: torch.Tensor, tar_feat: torch.Tensor) -> torch.Tensor:
         """ref/tar [B,H4,W4,C] bf16 (channels-last)."""
-        _require_eval(self)
+        if self.training:
+            from .train_asm import asm_volume_train
+            return asm_volume_train(self, ref_feat, tar_feat)
         b, h, w, c = ref_feat.shape
         vol = torch.empty(b, self.level, h, w, 2 * c, device=ref_feat.device, dtype=torch.bfloat16)
         levels = [(0, self.level, self.costrange[0])] if self.cached_first_level else \

@@ -23,7 +23,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib, ops
-from .layers import KIND_3x3x3, KIND_S2, KIND_T2, TCConv3d
+from .layers import KIND_1x1x1, KIND_1x3x3, KIND_3x3x3, KIND_S2, KIND_T2, TCConv3d
 
 
 def _npix(t):
@@ -60,13 +60,16 @@ def _ncdhw(t):
 def _wgrad(x, dz, weight, kind):
     """dW through cuDNN (aten.convolution_backward), inputs bf16 channels-last-3d, result cast back to the master dtype."""
     transposed = kind == KIND_T2
-    stride = [1, 1, 1] if kind == KIND_3x3x3 else [2, 2, 2]
-    gw = torch.ops.aten.convolution_backward(_ncdhw(dz), _ncdhw(x), weight.to(torch.bfloat16), None, stride, [1, 1, 1], [1, 1, 1],
+    stride = [2, 2, 2] if kind in (KIND_S2, KIND_T2) else [1, 1, 1]
+    pad = {KIND_1x3x3: [0, 1, 1], KIND_1x1x1: [0, 0, 0]}.get(kind, [1, 1, 1])
+    gw = torch.ops.aten.convolution_backward(_ncdhw(dz), _ncdhw(x), weight.to(torch.bfloat16), None, stride, pad, [1, 1, 1],
                                              transposed, [1, 1, 1] if transposed else [0, 0, 0], 1, [False, True, False])[1]
     return gw.to(weight.dtype)
 
 
 def _dgrad(dz, weight, kind):
+    if kind in (KIND_3x3x3, KIND_1x3x3, KIND_1x1x1):      # stride 1: same kind, taps flipped, channels transposed
+        return TCConv3d(weight.transpose(0, 1).flip(2, 3, 4), kind)(dz)
     if kind == KIND_3x3x3:
         return TCConv3d(weight.transpose(0, 1).flip(2, 3, 4), KIND_3x3x3)(dz)
     if kind == KIND_S2:                     # adjoint of a stride-2 conv = transposed conv with the same weight tensor
@@ -101,6 +104,7 @@ class ConvBNAct(Function):
             cfg.bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
             cfg.bn.running_var.mul_(1 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
             cfg.bn.num_batches_tracked += 1
+            cfg.bn.__dict__["_dpf_last_stats"] = (mean, var * (n / max(n - 1, 1)))
         ctx.save_for_backward(x, weight, z, y, a, mean, inv_std)
         ctx.cfg, ctx.has_res = cfg, residual is not None
         return y

@@ -171,6 +171,18 @@ int dpf_bn_bwd_reduce(const void* dy, const void* y, const void* z, float* sums,
 int dpf_bn_bwd_apply(const void* dy, const void* y, const void* z, const float* coef, void* dz, void* dres, long long npix,
                      int C, int relu, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * (9) Backward of the ASM volume pieces (autograd of src/module/asm/asm.py:87-127,160-171 in the reference).
+ *     dpf_asm_blend_bwd : dy = sum over the D_rep slices of dvol[b,d0..,h,w,ch_off+c]; outputs the direct-path gradient
+ *                         wrt the samples (dsamples) and the gradient wrt the normalised logits (dlhat), both [B,S,H4,W4,C] bf16.
+ *     dpf_asm_sample_bwd: dfeat [B,H4,W4,C] fp32 (zeroed by the call) += transpose of the table gather of dpf_asm_sample_fwd.
+ * ------------------------------------------------------------------------------------------------- */
+int dpf_asm_blend_bwd(const void* samples, const void* logits, const float* in_a, const float* in_d, const void* dvol,
+                      void* dsamples, void* dlhat, int B, int H4, int W4, int C, int S, int D_vol, int d0, int D_rep, int ch_off,
+                      int Cvol, void* stream);
+int dpf_asm_sample_bwd(const void* dsamples, float* dfeat, int B, int H4, int W4, int C, int S, const int* ri, const float* rw,
+                       const int* ci, const float* cw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,9 +11,11 @@ from oracle import dpf_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def build(name):
+def build(name, **model_overrides):
     from dualpixelface_b200.runner import load_config, model_selector
     opt = load_config("eval_faceDP" if name == "stereodpnet" else "eval_faceDP_psmnet", "pytest", root=ROOT, make_dirs=False)
+    for k, v in model_overrides.items():
+        setattr(opt.model, k, v)
     return model_selector(opt, root=ROOT)
 
 
@@ -57,13 +59,6 @@ def test_model_eval_parity(name, hw):
         n_err = (got["pred_normal"].float().cpu() - want["pred_normal"]).abs()
         print(f"   normal max err {n_err.max():.4f} mean {n_err.mean():.5f}")
         assert n_err.mean().item() < 2e-2 and n_err.max().item() < 0.15
-
-
-def test_unbuilt_training_path_fails_loudly():
-    """StereoDPNet's ASM volume / ANM backward kernels do not exist yet: train mode must raise, not fall back."""
-    model = build("stereodpnet").cuda().train()
-    with pytest.raises(NotImplementedError):
-        model(to_cuda(synthetic_batch(2, 64, 96, training=True)))
 
 
 def test_cpu_input_fails_loudly():
