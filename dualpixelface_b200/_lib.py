@@ -53,6 +53,7 @@ SIGNATURES = {
     "dpf_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]),
     "dpf_asm_blend_bwd": (c_int, [c_void_p] * 7 + [c_int] * 10 + [c_void_p]),
     "dpf_asm_sample_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dpf_conv3d_wgrad": (c_int, [c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p]),
     "dpf_dcn3d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

@@ -15,7 +15,7 @@
 
 namespace {
 
-constexpr int kRows = 8;       // output rows per CTA
+constexpr int kRows = 4;       // output rows per CTA (45 KB of staging -> 5 CTAs per SM overlap their load and store phases)
 constexpr int kWS = 64;        // pixels per strip
 constexpr int kThreads = 256;
 constexpr int kMaxD = 16;

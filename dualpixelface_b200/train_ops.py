@@ -58,7 +58,11 @@ def _ncdhw(t):
 
 
 def _wgrad(x, dz, weight, kind):
-    """dW through cuDNN (aten.convolution_backward), inputs bf16 channels-last-3d, result cast back to the master dtype."""
+    """dW.  Stride-1 kinds: the tcgen05 wgrad kernel (dpf_conv3d_wgrad).  Stride-2 / transposed kinds (11 % of the FLOPs):
+    still cuDNN through aten.convolution_backward on the bf16 channels-last-3d views (their tcgen05 wgrad is next)."""
+    if kind in (KIND_3x3x3, KIND_1x3x3, KIND_1x1x1):
+        from .ops_wgrad import conv3d_wgrad
+        return conv3d_wgrad(x, dz, kind).to(weight.dtype)
     transposed = kind == KIND_T2
     stride = [2, 2, 2] if kind in (KIND_S2, KIND_T2) else [1, 1, 1]
     pad = {KIND_1x3x3: [0, 1, 1], KIND_1x1x1: [0, 0, 0]}.get(kind, [1, 1, 1])

@@ -183,6 +183,17 @@ int dpf_asm_blend_bwd(const void* samples, const void* logits, const float* in_a
 int dpf_asm_sample_bwd(const void* dsamples, float* dfeat, int B, int H4, int W4, int C, int S, const int* ri, const float* rw,
                        const int* ci, const float* cw, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * (10) Weight gradient of the stride-1 convolution kinds (0, 3, 4) on tcgen05 (voxel positions are the GEMM K dimension,
+ *      both operands MN-major straight from the forward kernel's shared-memory staging).  Replaces the dW half of autograd
+ *      through nn.Conv3d (src/model/stereodpnet/modules.py:204-337).
+ *        dw[tap][ci][co] += sum_{b,d,h,w} x[b, (d,h,w)+tap-pad, x_coff+ci] * dz[b,d,h,w, z_coff+co]
+ *      x [B,D,H,W,x_cstride], dz [B,D,H,W,z_cstride] bf16 (dz channels padded to a multiple of 8); dw fp32
+ *      [ntaps][Cin][Cout], accumulated with atomics (zero it first).  Cin in {32,64}, Cout <= 32 per launch.
+ * ------------------------------------------------------------------------------------------------- */
+int dpf_conv3d_wgrad(int kind, const void* x, const void* dz, float* dw, int B, int D, int H, int W, int Cin, int x_cstride,
+                     int x_coff, int Cout, int z_cstride, int z_coff, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
