@@ -55,6 +55,8 @@ SIGNATURES = {
     "dpf_asm_sample_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dpf_conv3d_wgrad": (c_int, [c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p]),
     "dpf_dcn3d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dpf_dcn3d_bwd_data": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_void_p]),
+    "dpf_dcn3d_bwd_weight": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
 }
 
 _lib = None
