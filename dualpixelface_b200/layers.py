@@ -3,7 +3,7 @@
 One reference layer (nn.Conv3d / nn.ConvTranspose3d [+ BatchNorm3d] [+ ReLU] [+ add]) becomes one or a few launches of
 ``dpf_conv3d_fwd``.  The per-launch limits of the kernel (include/dpf_sm100.h) are met by splitting:
   * output channels into chunks written at ``y_coff`` into the same output tensor;
-  * (stride-2 only) input channels into 32-wide windows read at ``x_coff``, chained through an fp32 partial sum
+  * (stride-2, and stride-1 layers wider than 64 channels) input channels into 32/64-wide windows read at ``x_coff``, chained through an fp32 partial sum
     (``res_pre``) so that the affine / ReLU is applied once, by the last launch.
 """
 from __future__ import annotations
@@ -31,9 +31,8 @@ def plan_launches(kind: int, cin: int, cout: int) -> List[Launch]:
     if cin % 32 != 0 or cin > 64 * 4:
         raise ValueError(f"input channels must be a multiple of 32 (pad on the host), got {cin}")
     if kind in (KIND_3x3x3, KIND_1x3x3, KIND_1x1x1):
-        if cin not in (32, 64):
-            raise ValueError(f"stride-1 kinds take Cin in (32, 64), got {cin}")
-        kwin, cchunk = cin, (64 if cin == 32 else 32)
+        kwin = cin if cin in (32, 64) else (64 if cin % 64 == 0 else 32)    # wider layers: input-channel windows (K-split)
+        cchunk = 64 if kwin == 32 else 32
     elif kind == KIND_S2:
         kwin, cchunk = 32, 32
     elif kind == KIND_T2:

@@ -94,10 +94,6 @@ class _StereoBase(LightningModule):
     def forward(self, batch):
         if not batch["left"].is_cuda:
             raise RuntimeError("the sm_100a hot path needs CUDA tensors; there is no CPU implementation")
-        if self.training and self.predict_normal:
-            raise NotImplementedError("the backward kernels of the ANM normal branch (3-D deformable conv dgrad / offset-grad / "
-                                      "wgrad) are not built yet: train with model.predict_normal=false, or call .eval().  "
-                                      "There is deliberately no fallback.")
         ref_img, tgt_img = self._select_views(batch)
         self._mark("start")
         ref_fea, tgt_fea = self._features(ref_img, tgt_img)

@@ -522,7 +522,10 @@ class ANM(nn.Module):
 
     def forward(self, costs: Sequence[torch.Tensor], disp_maps: Sequence[torch.Tensor], batch: dict):
         """costs: [out3] as [B,D,H4,W4,C] bf16; disp_maps: [disparity [B,H,W] fp32] -> ([normal [B,3,H,W]], offsets, offsets)."""
-        _require_eval(self)
+        if self.training:                      # forward + backward through the autograd Functions of train_anm.py
+            from .train_anm import anm_train
+            outs = [anm_train(self, out3, disp, batch) for out3, disp in zip(costs, disp_maps)]
+            return [o[0] for o in outs], [o[1] for o in outs], [o[2] for o in outs]
         p = self._build()
         normals, off1s, off2s = [], [], []
         for out3, disp in zip(costs, disp_maps):

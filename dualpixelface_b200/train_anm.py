@@ -1,0 +1,140 @@
+"""Training path of the ANM normal branch (src/model/stereodpnet/normal_module.py:140-194): autograd Functions over the
+sm_100a kernels, forward AND backward.
+
+    fv      = gather(out3 at the k sampled levels) ++ normalised coordinates     dpf_anm_gather / dpf_anm_gather_bwd
+    off_i   = conv3x3x3(x; W_off) + b_off                                        tcgen05 conv engine (fwd, dgrad, wgrad)
+    z_i     = D3D(x, off_i; W)                                                   dpf_dcn3d_fwd / dpf_dcn3d_bwd_data / _bwd_weight
+    f_i     = ReLU(BN_train(z_i + bias))                                         dpf_channel_stats / dpf_affine_act / dpf_bn_bwd_*
+    n_convs : six dilated 2-D convs + LeakyReLU(0.1) on the (b*k) slices         cuDNN through torch autograd (adjacent op)
+    normal  = mean_k sigmoid(bilinear x4) * 2 - 1                                dpf_anm_tail / dpf_anm_tail_bwd
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+
+from . import _lib, ops
+from .layers import KIND_3x3x3, TCConv3d
+from .ops_dcn_bwd import DCNFn
+from .ops_tail import anm_tail
+from .ops_wgrad import conv3d_wgrad
+from .train_ops import _affine_act, _bn_bwd, _npix
+
+
+class GatherFn(Function):
+    """out3 [B,D,H4,W4,C] bf16 -> fv [B,K,H4,W4,64] bf16 (C cost channels, 3 coordinates, zero pad)."""
+
+    @staticmethod
+    def forward(ctx, out3, idx, coord, minmax):
+        ctx.save_for_backward(idx)
+        ctx.shape = out3.shape
+        return ops.anm_gather(out3, idx, coord, minmax, 64)
+
+    @staticmethod
+    def backward(ctx, dfv):
+        (idx,) = ctx.saved_tensors
+        b, d, h4, w4, c = ctx.shape
+        dfv = dfv.contiguous()
+        a = dfv if dfv.dtype == torch.float32 else None
+        bb = dfv if dfv.dtype == torch.bfloat16 else None
+        assert a is not None or bb is not None
+        dout3 = torch.empty(ctx.shape, device=dfv.device, dtype=torch.bfloat16)
+        _lib.check(ops.lib().dpf_anm_gather_bwd(ops._p(a), ops._p(bb), ops._p(idx), ops._p(dout3), b, d, idx.shape[1], h4, w4, c,
+                                                dfv.shape[-1], ops._stream()), "dpf_anm_gather_bwd")
+        return dout3, None, None, None
+
+
+class OffsetConvFn(Function):
+    """offset = conv3x3x3(x; W[81,Cin,3,3,3]) + bias -> fp32 [B,K,H4,W4,81]; x is the 64-channel (zero padded) volume."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return TCConv3d(weight, KIND_3x3x3, cin_pad=64)(x, shift=bias.detach().float().contiguous(), out_f32=True)
+
+    @staticmethod
+    def backward(ctx, doff):
+        x, weight = ctx.saved_tensors
+        cout, cin = weight.shape[:2]
+        dzp = torch.zeros(*doff.shape[:-1], 96, device=doff.device, dtype=torch.bfloat16)       # 81 -> 96 channel windows
+        dzp[..., :cout] = doff
+        wt = torch.zeros(64, cout, 3, 3, 3, device=weight.device, dtype=torch.float32)
+        wt[:cin] = weight.detach().float().transpose(0, 1).flip(2, 3, 4)
+        dx = TCConv3d(wt, KIND_3x3x3, cin_pad=96)(dzp)                                          # [.,64] bf16, pad channels zero
+        dw = conv3d_wgrad(x, dzp, KIND_3x3x3)[:cout, :cin].to(weight.dtype)
+        db = doff.reshape(-1, cout).sum(0)
+        return dx, dw, db
+
+
+class BNActFn(Function):
+    """y = ReLU(BatchNorm3d_train(z + conv_bias)) on channels-last bf16.  With batch statistics the conv bias cancels in y (its
+    gradient is exactly zero); it only enters the running mean."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, conv_bias, bn):
+        c, n = z.shape[-1], _npix(z)
+        st = ops.channel_stats(z.view(1, n, c))[0]
+        mean = st[:, 0] / n
+        var = (st[:, 1] / n - mean * mean).clamp_min(0.0)
+        inv_std = torch.rsqrt(var + bn.eps)
+        a = (gamma.float() * inv_std).contiguous()
+        b = (beta.float() - mean * a).contiguous()
+        y = _affine_act(z, a, b, None, 0.0)
+        if bn.track_running_stats:
+            m = bn.momentum
+            unb = var * (n / max(n - 1, 1))
+            bn.running_mean.mul_(1 - m).add_(mean + conv_bias.detach().float(), alpha=m)
+            bn.running_var.mul_(1 - m).add_(unb, alpha=m)
+            bn.num_batches_tracked += 1
+            bn.__dict__["_dpf_last_stats"] = (mean + conv_bias.detach().float(), unb)
+        ctx.save_for_backward(z, y, a, mean, inv_std)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, y, a, mean, inv_std = ctx.saved_tensors
+        dz, _, dgamma, dbeta = _bn_bwd(dy.to(torch.bfloat16).contiguous(), y, z, a, mean, inv_std, True, False)
+        return dz, dgamma, dbeta, torch.zeros_like(dbeta), None
+
+
+class TailFn(Function):
+    """x [B*K,H4,W4,3] bf16 -> normal [B,3,H,W] fp32."""
+
+    @staticmethod
+    def forward(ctx, x, b, k):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        ctx.bk = (b, k)
+        return anm_tail(x, b, k)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        b, k = ctx.bk
+        dx = torch.zeros(x.shape, device=x.device, dtype=torch.float32)
+        _lib.check(ops.lib().dpf_anm_tail_bwd(ops._p(x), ops._p(dout.float().contiguous()), ops._p(dx), b, k, x.shape[1], x.shape[2],
+                                              ops._stream()), "dpf_anm_tail_bwd")
+        return dx.to(torch.bfloat16), None, None
+
+
+def anm_train(anm, out3: torch.Tensor, disp: torch.Tensor, batch: dict):
+    """One (cost, disparity) pair through the normal branch in training mode -> (normal [B,3,H,W], offset1, offset2)."""
+    b = out3.shape[0]
+    kq = batch["K"].float().clone()
+    kq[:, :2, :] = kq[:, :2, :] / 4.0
+    kinv = torch.inverse(kq).contiguous()
+    idx, coord, minmax = ops.anm_select(disp.detach().contiguous(), kinv, batch["abvalue"].float().contiguous(), anm.levels, anm.k)
+    fv = GatherFn.apply(out3, idx, coord, minmax)
+    x, offs = fv, []
+    for dc, act in ((anm.deform_conv1, anm.act1), (anm.deform_conv2, anm.act2)):
+        off = OffsetConvFn.apply(x, dc.conv_offset.weight, dc.conv_offset.bias)
+        z = DCNFn.apply(x, off, dc.weight)
+        x = BNActFn.apply(z, act[0].weight, act[0].bias, dc.bias, act[0])
+        offs.append(off)
+    f = x.view(b * anm.k, x.shape[2], x.shape[3], x.shape[4]).permute(0, 3, 1, 2)                # NCHW view, channels-last memory
+    for m in anm.n_convs:
+        conv = m[0]
+        f = F.leaky_relu(F.conv2d(f, conv.weight.to(torch.bfloat16), None, 1, conv.dilation, conv.dilation), 0.1)
+    normal = TailFn.apply(f.permute(0, 2, 3, 1), b, anm.k)
+    return normal, offs[0], offs[1]

@@ -153,6 +153,15 @@ int dpf_dcn3d_bwd_data(const void* x, const float* offset, const void* dy, const
 int dpf_dcn3d_bwd_weight(const void* x, const float* offset, const void* dy, float* dw, int B, int D, int H, int W,
                          int x_cstride, void* stream);
 
+/* (6c) Backward of the memory-bound ANM ops (normal_module.py:140-194).
+ *      tail_bwd:   x [B*K,H4,W4,3] bf16 (the forward input), dout [B,3,4*H4,4*W4] fp32 -> dx [B*K,H4,W4,3] fp32, ACCUMULATED
+ *                  (zero it first): adjoint of mean_k(sigmoid(bilinear x4, align_corners=True)) * 2 - 1 (normal_module.py:186-192).
+ *      gather_bwd: dfv_f32 and/or dfv_bf16 [B,K,H4,W4,Cpad] (summed; either may be NULL), idx [B,K,H4,W4] ->
+ *                  dout3 [B,D,H4,W4,C] bf16, fully written (levels not selected get zero); adjoint of dpf_anm_gather. */
+int dpf_anm_tail_bwd(const void* x, const float* dout, float* dx, int B, int K, int H4, int W4, void* stream);
+int dpf_anm_gather_bwd(const float* dfv_f32, const void* dfv_bf16, const int* idx, void* dout3, int B, int D, int K,
+                       int H4, int W4, int C, int Cpad, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * (7) Fused per-channel bias + residual + activation on channels-last bf16 (one memory pass).  Replaces the
  *     aten::add_ (conv bias) / aten::add (skip) / aten::prelu|relu|leaky_relu chains around the cuDNN 2-D convolutions of

@@ -66,6 +66,8 @@ def test_plan_launches():
     assert [(l.x_coff, l.y_coff, l.first_k, l.last_k) for l in s2] == [(0, 0, True, False), (32, 0, False, True),
                                                                       (0, 32, True, False), (32, 32, False, True)]
     assert len(P(layers.KIND_T2, 64, 64)) == 2
+    k96 = P(layers.KIND_3x3x3, 96, 64)                       # offset-conv data gradient: 81 -> 96 padded channels
+    assert [(l.x_coff, l.cin, l.first_k, l.last_k) for l in k96] == [(0, 32, True, False), (32, 32, False, False), (64, 32, False, True)]
     with pytest.raises(ValueError):
         P(layers.KIND_3x3x3, 48, 32)
 
