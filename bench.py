@@ -79,13 +79,81 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-def build_model(device):
+def build_model(device, config="eval_faceDP", name="stereodpnet"):
     from dualpixelface_b200.runner import load_config, model_selector
     from dualpixelface_b200.synthetic import synth_state
-    opt = load_config("eval_faceDP", "bench", root=ROOT, make_dirs=False)
+    opt = load_config(config, "bench", root=ROOT, make_dirs=False)
     model = model_selector(opt, root=ROOT)
-    model.load_state_dict(synth_state(state_shapes("stereodpnet"), seed=1), strict=False)
+    model.load_state_dict(synth_state(state_shapes(name), seed=1), strict=False)
     return model.to(device).eval()
+
+
+def run_train(args):
+    """Extra (not the driver's contract line): one TRAINING step = forward + backward + optimizer step, BASELINE configs 3/4
+    (`--mode train --model stereodpnet|psmnet --batch B --height H --width W`); weak scaling with the bucketed gradient
+    all-reduce of parallel.make_grad_sync when launched under torchrun."""
+    from dualpixelface_b200 import ops
+    from dualpixelface_b200.runner import optimizer_selector
+    from dualpixelface_b200.synthetic import synthetic_batch
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    ops.lib()
+    cfg = "train_faceDP" if args.model == "stereodpnet" else "train_faceDP_psmnet"
+    model = build_model(dev, cfg, args.model).train()
+    opt = optimizer_selector(model.parameters(), model.option)
+    sync = None
+    if world > 1:
+        from dualpixelface_b200.parallel import make_grad_sync
+        sync = make_grad_sync(model)
+    b, h, w = args.batch, args.height, args.width
+    batch = {k: v.to(dev) for k, v in synthetic_batch(b, h, w, training=True, seed=rank).items()}
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        res = model(batch)
+        res["final_loss"].backward()
+        if sync is not None:
+            sync()
+        opt.step()
+        return res
+
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    n0 = ops.launch_count()
+    torch.cuda.reset_peak_memory_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = t.item()
+    if rank == 0:
+        vox = 8 * (h // 4) * (w // 4) * b
+        print(json.dumps({
+            "metric": f"{args.model} training DP-pairs/sec (fwd+bwd+optimizer)", "value": world * b * args.steps / (ms * 1e-3),
+            "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.model}_train_{h}x{w}_b{b}", "batch_per_gpu": b, "height": h, "width": w,
+                       "parallelism": f"dp{world}", "predict_normal": bool(getattr(model, "predict_normal", False))},
+            "gpu_launches": int(ops.launch_count() - n0), "final_loss": float(res["final_loss"].detach()),
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+            "aggregation_tflop_per_step_fwd_bwd": 3 * AGG_FLOP_PER_VOXEL * vox / 1e12}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 def cpu_reference_pairs_per_s(steps, warmup, sample_hw=(448, 672)):
@@ -245,8 +313,20 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train = extra fwd+bwd+optimizer line")
+    ap.add_argument("--model", default="stereodpnet", choices=["stereodpnet", "psmnet"])
+    ap.add_argument("--batch", type=int, default=None, help="pairs per GPU (default: 4 inference = BASELINE configs[1], 8 training)")
+    ap.add_argument("--height", type=int, default=H)
+    ap.add_argument("--width", type=int, default=W)
     a = ap.parse_args()
+    if a.mode == "train":
+        a.batch = a.batch or 8
+    else:                                  # other inference shapes (e.g. BASELINE config 5: --batch 1 --height 2240 --width 3360)
+        H, W, B = a.height, a.width, a.batch or B
+        WORKLOAD = f"stereodpnet_infer_{H}x{W}_b{B}"
     if a.impl == "reference":
         run_reference(a)
+    elif a.mode == "train":
+        run_train(a)
     else:
         run_ours(a)
