@@ -39,6 +39,7 @@ struct BwdParams {
   float* dw;                    // weight kernel: [27][c][o] fp32 (zeroed by the caller)
   int B, D, H, W, x_cstride;
   int nunits, tiles_h, tiles_w, tap0, tap1;
+  int dx_channels;              // data kernel: 32 -> only channels [0,32) of dx are accumulated, else all 64
 };
 
 __device__ __forceinline__ void unit_coords(int unit, const BwdParams& p, int& d, int& h0, int& w0, int& b) {
@@ -65,16 +66,22 @@ __device__ __forceinline__ void load_tile_256x64(uint8_t* dst, const __nv_bfloat
 // ============================================================================================================
 // data + offset gradient
 // ============================================================================================================
-constexpr int kDThreads = (4 + 1 + 2) * 32;      // 4 epilogue warps, MMA warp, 2 loader warps
+constexpr int kDEpi = 16;                         // epilogue warps: TMEM lane quarter = warp & 3, 128-row block = (warp >> 2) & 1,
+                                                  // 16-row half of the quarter = warp >> 3
+constexpr int kDMma = kDEpi;                      // MMA warp index
+constexpr int kDThreads = (kDEpi + 1 + 2) * 32;   // + MMA warp + 2 loader warps
 constexpr int kDWStages = 3;
-constexpr int kDSmem = 2 * kTile + kDWStages * kWTap + (2 * 2 + 2 * kDWStages + 4) * 8 + 16 + 128;
+constexpr int kGPitch = kC + 4;                   // floats per staged dcol row (conflict-free 128-bit row writes)
+constexpr int kGTile = 16 * kGPitch * 4;          // one warp's [16 voxels][64 channels] fp32 staging tile
+constexpr int kDSmem = 2 * kTile + kDWStages * kWTap + kDEpi * kGTile + (2 * 2 + 2 * kDWStages + 4) * 8 + 16 + 128;
 
 __global__ void __launch_bounds__(kDThreads, 1) dcn3d_bwd_data_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
   uint8_t* s_dy = smem;                                   // [2][kTile]
   uint8_t* s_w = smem + 2 * kTile;                        // [kDWStages][kWTap]
-  uint64_t* bar_zfull = reinterpret_cast<uint64_t*>(s_w + kDWStages * kWTap);
+  float* s_g = reinterpret_cast<float*>(s_w + kDWStages * kWTap);   // [kDEpi][16][kGPitch]
+  uint64_t* bar_zfull = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_g) + kDEpi * kGTile);
   uint64_t* bar_zempty = bar_zfull + 2;
   uint64_t* bar_wfull = bar_zempty + 2;
   uint64_t* bar_wempty = bar_wfull + kDWStages;
@@ -83,11 +90,11 @@ __global__ void __launch_bounds__(kDThreads, 1) dcn3d_bwd_data_kernel(const __gr
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_zfull[i], 2); mbar_init(&bar_zempty[i], 1); mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_zfull[i], 2); mbar_init(&bar_zempty[i], 1); mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], kDEpi); }
     for (int i = 0; i < kDWStages; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 1); }
     mbar_fence_init();
   }
-  if (warp == 4) { tmem_alloc(s_tmem, 256); tmem_relinquish(); }
+  if (warp == kDMma) { tmem_alloc(s_tmem, 256); tmem_relinquish(); }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -96,9 +103,9 @@ __global__ void __launch_bounds__(kDThreads, 1) dcn3d_bwd_data_kernel(const __gr
   const int per_cta = (p.nunits + gridDim.x - 1) / gridDim.x;
   const int unit_lo = min(static_cast<int>(blockIdx.x) * per_cta, p.nunits), unit_hi = min(unit_lo + per_cta, p.nunits);
 
-  if (warp > 4) {
+  if (warp > kDMma) {
     // ---------------- loaders: dy tile per unit (cp.async), W^T tap tiles (TMA bulk) ----------------------
-    const int ltid = threadIdx.x - 5 * 32;
+    const int ltid = threadIdx.x - (kDMma + 1) * 32;
     uint32_t gw = 0, it = 0;
     for (int unit = unit_lo; unit < unit_hi; ++unit, ++it) {
       int ud, uh0, uw0, ub;
@@ -119,7 +126,7 @@ __global__ void __launch_bounds__(kDThreads, 1) dcn3d_bwd_data_kernel(const __gr
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kDMma) {
     // ---------------- MMA: dcol[128 x 64] = dy[128 x 64(o)] * W_tap^T[64(o) x 64(c)] ------------------------
     constexpr uint32_t idesc = umma_idesc_bf16_f32(128, kC);
     const uint64_t adesc_hi = umma_desc_nosw(0, kChunk, 128);
@@ -155,9 +162,15 @@ __global__ void __launch_bounds__(kDThreads, 1) dcn3d_bwd_data_kernel(const __gr
       }
     }
   } else {
-    // ---------------- epilogue: one thread per voxel -> scatter dx, write doffset --------------------------
-    uint32_t ga = 0;
+    // ---------------- epilogue: TMEM -> per-warp smem tile -> 8 lanes per voxel scatter dx / reduce doffset --
+    // Lane j of a voxel's 8-lane group owns channels [4j, 4j+4) and [32+4j, 32+4j+4): each red.global.add.v4.f32 of a group
+    // covers one full 128-byte line of dx, each 64-bit x load one 64-byte half line.
+    const int quarter = warp & 3, blk = (warp >> 2) & 1, half = warp >> 3;
+    float* g_tile = s_g + warp * (16 * kGPitch);
+    const int grp = lane >> 3, j = lane & 7;
     const uint32_t cs = static_cast<uint32_t>(p.x_cstride);
+    const bool hi_live = p.dx_channels > 32;
+    uint32_t ga = 0;
     for (int unit = unit_lo; unit < unit_hi; ++unit) {
       int ud, uh0, uw0, ub;
       unit_coords(unit, p, ud, uh0, uw0, ub);
@@ -166,71 +179,96 @@ __global__ void __launch_bounds__(kDThreads, 1) dcn3d_bwd_data_kernel(const __gr
         const uint32_t as = ga & 1u;
         mbar_wait(&bar_tfull[as], (ga >> 1) & 1u);
         tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * 2 + blk) * kC;
+#pragma unroll
+        for (int c0 = 0; c0 < kC; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          if ((lane >> 4) == half) {                           // this warp scatters rows [16*half, 16*half+16) of the quarter
+            float4* dst = reinterpret_cast<float4*>(g_tile + (lane & 15) * kGPitch + c0);
+            dst[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+            dst[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+            dst[2] = make_float4(__uint_as_float(v[8]), __uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+            dst[3] = make_float4(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]), __uint_as_float(v[15]));
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[as]);          // the accumulator is free again while this warp scatters
         const int ti = tap / 9 - 1, tj = (tap / 3) % 3 - 1, tk = tap % 3 - 1;
 #pragma unroll 1
-        for (int blk = 0; blk < 2; ++blk) {
-          const int r = blk * 128 + warp * 32 + lane;
+        for (int rnd = 0; rnd < 4; ++rnd) {
+          const int row = rnd * 4 + grp;                       // row of this warp's 16-voxel slice
+          const int r = blk * 128 + quarter * 32 + half * 16 + row;
           const int hh = uh0 + (r >> 4), ww = uw0 + (r & 15);
           const bool live = hh < H && ww < W;
-          float g[kC];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + (as * 2 + blk) * kC;
-#pragma unroll
-          for (int c0 = 0; c0 < kC; c0 += 16) {
-            uint32_t v[16];
-            __syncwarp();
-            tmem_ld16(taddr + c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) g[c0 + j] = __uint_as_float(v[j]);
-          }
-          if (!live) continue;
-          const int vox = vbase + (ud * H + hh) * W + ww;
+          const int vox = vbase + (ud * H + (live ? hh : 0)) * W + (live ? ww : 0);
           const float* op = p.offset + static_cast<size_t>(vox) * 81 + tap * 3;
           const float pd = static_cast<float>(ud + ti) + __ldg(op + 0);
           const float ph = static_cast<float>(hh + tj) + __ldg(op + 1);
           const float pw = static_cast<float>(ww + tk) + __ldg(op + 2);
-          float gd = 0.f, gh = 0.f, gw2 = 0.f;
-          if (pd > -1.f && ph > -1.f && pw > -1.f && pd < static_cast<float>(D) && ph < static_cast<float>(H) && pw < static_cast<float>(W)) {
-            const float fd = floorf(pd), fh = floorf(ph), fw = floorf(pw);
-            const int d0 = static_cast<int>(fd), h0 = static_cast<int>(fh), w0 = static_cast<int>(fw);
-            const float ld = pd - fd, lh = ph - fh, lw = pw - fw;
-#pragma unroll 1
-            for (int corner = 0; corner < 8; ++corner) {
-              const int cd = corner >> 2, ch = (corner >> 1) & 1, cw = corner & 1;
-              const int di = d0 + cd, hi = h0 + ch, wi = w0 + cw;
-              if (di < 0 || di > D - 1 || hi < 0 || hi > H - 1 || wi < 0 || wi > W - 1) continue;
-              const float wd = cd ? ld : 1.f - ld, wh = ch ? lh : 1.f - lh, wv = cw ? lw : 1.f - lw;
-              const float wc = wd * wh * wv;
-              const size_t idx = static_cast<size_t>(vbase + di * HW + hi * W + wi) * cs;
-              const __nv_bfloat16* xp = p.x + idx;
-              float* dxp = p.dx + idx;
-              float s = 0.f;
+          const bool inside = live && pd > -1.f && ph > -1.f && pw > -1.f && pd < static_cast<float>(D) &&
+                              ph < static_cast<float>(H) && pw < static_cast<float>(W);
+          const float4 ga4 = *reinterpret_cast<const float4*>(g_tile + row * kGPitch + 4 * j);
+          const float4 gb4 = *reinterpret_cast<const float4*>(g_tile + row * kGPitch + 32 + 4 * j);
+          const float fd = floorf(pd), fh = floorf(ph), fw = floorf(pw);
+          const int d0 = static_cast<int>(fd), h0 = static_cast<int>(fh), w0 = static_cast<int>(fw);
+          const float ld = pd - fd, lh = ph - fh, lw = pw - fw;
+          float gd = 0.f, gh = 0.f, gw2 = 0.f;                 // this lane's partial sums (its 8 channels); reduced once below
 #pragma unroll
-              for (int j = 0; j < kNCH; ++j) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(xp + j * 8));
-                const float xv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+          for (int cd = 0; cd < 2; ++cd) {
+            // the 8 loads of one depth pair of corners are issued before any use (branch-free clamped addresses)
+            uint2 xa[4], xb[4];
+            uint32_t cidx[4];
+            const int dc = min(max(d0 + cd, 0), D - 1);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) s = fmaf(g[j * 8 + k], xv[k], s);
-                atomicAdd(reinterpret_cast<float4*>(dxp + j * 8), make_float4(wc * g[j * 8], wc * g[j * 8 + 1], wc * g[j * 8 + 2], wc * g[j * 8 + 3]));
-                atomicAdd(reinterpret_cast<float4*>(dxp + j * 8 + 4), make_float4(wc * g[j * 8 + 4], wc * g[j * 8 + 5], wc * g[j * 8 + 6], wc * g[j * 8 + 7]));
+            for (int q = 0; q < 4; ++q) {
+              const int hi = min(max(h0 + (q >> 1), 0), H - 1), wi = min(max(w0 + (q & 1), 0), W - 1);
+              cidx[q] = static_cast<uint32_t>(vbase + dc * HW + hi * W + wi) * cs;
+              xa[q] = __ldg(reinterpret_cast<const uint2*>(p.x + cidx[q] + 4 * j));
+              xb[q] = __ldg(reinterpret_cast<const uint2*>(p.x + cidx[q] + 32 + 4 * j));
+            }
+            const float wd = cd ? ld : 1.f - ld;
+            const bool dok = inside && d0 + cd >= 0 && d0 + cd <= D - 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int ch = q >> 1, cw = q & 1;
+              const int hi = h0 + ch, wi = w0 + cw;
+              const bool ok = dok && hi >= 0 && hi <= H - 1 && wi >= 0 && wi <= W - 1;
+              const float wh = ch ? lh : 1.f - lh, wv = cw ? lw : 1.f - lw;
+              float s = ga4.x * bf16_lo(xa[q].x) + ga4.y * bf16_hi(xa[q].x) + ga4.z * bf16_lo(xa[q].y) + ga4.w * bf16_hi(xa[q].y) +
+                        gb4.x * bf16_lo(xb[q].x) + gb4.y * bf16_hi(xb[q].x) + gb4.z * bf16_lo(xb[q].y) + gb4.w * bf16_hi(xb[q].y);
+              s = ok ? s : 0.f;
+              if (ok) {
+                const float wc = wd * wh * wv;
+                float* dxp = p.dx + cidx[q];
+                atomicAdd(reinterpret_cast<float4*>(dxp + 4 * j), make_float4(wc * ga4.x, wc * ga4.y, wc * ga4.z, wc * ga4.w));
+                if (hi_live) atomicAdd(reinterpret_cast<float4*>(dxp + 32 + 4 * j), make_float4(wc * gb4.x, wc * gb4.y, wc * gb4.z, wc * gb4.w));
               }
               gd += (cd ? 1.f : -1.f) * wh * wv * s;
               gh += (ch ? 1.f : -1.f) * wd * wv * s;
               gw2 += (cw ? 1.f : -1.f) * wd * wh * s;
             }
           }
-          float* dop = p.doff + static_cast<size_t>(vox) * 81 + tap * 3;
-          dop[0] = gd; dop[1] = gh; dop[2] = gw2;
+#pragma unroll
+          for (int m = 1; m < 8; m <<= 1) {
+            gd += __shfl_xor_sync(0xffffffffu, gd, m);
+            gh += __shfl_xor_sync(0xffffffffu, gh, m);
+            gw2 += __shfl_xor_sync(0xffffffffu, gw2, m);
+          }
+          if (live && j < 3) {
+            float* dop = p.doff + static_cast<size_t>(vox) * 81 + tap * 3;
+            dop[j] = j == 0 ? gd : (j == 1 ? gh : gw2);
+          }
         }
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_tempty[as]);
+        __syncwarp();                                          // the tile is rewritten by the next tap
       }
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 256); }
+  if (warp == kDMma) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 256); }
 }
 
 // ============================================================================================================
@@ -454,16 +492,18 @@ int fill(BwdParams& p, int B, int D, int H, int W, int x_cstride) {
 }  // namespace
 
 extern "C" int dpf_dcn3d_bwd_data(const void* x, const float* offset, const void* dy, const void* w_t, float* dx, float* doffset,
-                                  int B, int D, int H, int W, int x_cstride, void* stream) {
+                                  int B, int D, int H, int W, int x_cstride, int dx_channels, void* stream) {
   DPF_REQUIRE(x && offset && dy && w_t && dx && doffset, "dpf_dcn3d_bwd_data: null pointer");
   DPF_REQUIRE(x_cstride >= kC && x_cstride % 8 == 0, "dpf_dcn3d_bwd_data: x_cstride=%d must be a multiple of 8 >= 64", x_cstride);
+  DPF_REQUIRE(dx_channels == 32 || dx_channels == 64, "dpf_dcn3d_bwd_data: dx_channels=%d must be 32 or 64", dx_channels);
+  DPF_REQUIRE(DPF_ALIGNED16(x) && DPF_ALIGNED16(dx) && DPF_ALIGNED16(dy) && DPF_ALIGNED16(w_t), "dpf_dcn3d_bwd_data: pointers must be 16-byte aligned");
   DPF_REQUIRE(static_cast<long long>(B) * D * H * W < (1LL << 31) / 128, "dpf_dcn3d_bwd_data: tensor too large for 32-bit voxel indexing");
   BwdParams p{};
   p.x = reinterpret_cast<const __nv_bfloat16*>(x);
   p.offset = offset;
   p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
   p.w = reinterpret_cast<const __nv_bfloat16*>(w_t);
-  p.dx = dx; p.doff = doffset;
+  p.dx = dx; p.doff = doffset; p.dx_channels = dx_channels;
   fill(p, B, D, H, W, x_cstride);
   static bool attr = false;
   if (!attr) {

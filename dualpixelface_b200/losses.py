@@ -6,6 +6,14 @@ import torch
 import torch.nn.functional as F
 
 
+def _masked_mean(val, mask):
+    """mean of val over mask > 0 without boolean-mask gathers (their backward is an index_put scatter)."""
+    while mask.dim() < val.dim():
+        mask = mask.unsqueeze(-1)
+    m = (mask > 0).to(val.dtype)
+    return (val * m).sum() / (m.sum() * (val.numel() // m.numel())).clamp_min(1.0)
+
+
 def smooth_l1(pred, batch, weights):
     """src/loss/depth/smoothL1.py:15-49, 'given' conversion with a disparity target: weighted sum over the heads."""
     n = pred.shape[1]
@@ -13,21 +21,19 @@ def smooth_l1(pred, batch, weights):
     assert len(ws) == n
     gt = batch["disp"]
     if "mask" in batch:
-        m = batch["mask"] > 0
-        return sum(ws[i] * F.smooth_l1_loss(pred[:, i][m], gt[m]) for i in range(n))
+        return sum(ws[i] * _masked_mean(F.smooth_l1_loss(pred[:, i], gt, reduction="none"), batch["mask"]) for i in range(n))
     return sum(ws[i] * F.smooth_l1_loss(pred[:, i], gt) for i in range(n))
 
 
 def cosine(pred, batch):
     """src/loss/normal/cosine.py:35-55 (masked branch, one prediction); note the element-wise similarity of :18-26."""
-    m = batch["mask"] > 0
-    p = pred.permute(0, 3, 4, 1, 2)[m]
-    g = batch["normal"].permute(0, 2, 3, 1)[m]
+    p = pred.permute(0, 3, 4, 1, 2)                                   # [B,H,W,1,3]
+    g = batch["normal"].permute(0, 2, 3, 1)                           # [B,H,W,3]
     p = p / torch.norm(p, p=2, dim=-1, keepdim=True).clamp_min(1e-6)
     g = g / torch.norm(g, p=2, dim=-1, keepdim=True).clamp_min(1e-6)
-    a = p[:, 0]
+    a = p[..., 0, :]
     den = (torch.norm(a, p=2, dim=-1, keepdim=True) * torch.norm(g, p=2, dim=-1, keepdim=True)).clamp_min(1e-6)
-    return torch.mean(1.0 - ((a * g) / den).clamp(-1.0, 1.0))
+    return _masked_mean(1.0 - ((a * g) / den).clamp(-1.0, 1.0), batch["mask"])
 
 
 class LossModel:

@@ -71,8 +71,14 @@ class _StereoBase(LightningModule):
         b = ref_img.shape[0]
         if self.training:
             # the reference runs the encoder once per view (mainmodel.py:72-83): BatchNorm batch statistics are per call
+            # channels-last end to end: cuDNN then needs no NCHW<->NHWC transposes and BatchNorm takes the NHWC kernels
+            cl = torch.channels_last
+            if not self.__dict__.get("_enc_channels_last", False):
+                self.feature_extraction.to(memory_format=cl)
+                self.__dict__["_enc_channels_last"] = True
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.encoder_autocast):
-                fr, ft = self.feature_extraction(ref_img.float()), self.feature_extraction(tgt_img.float())
+                fr = self.feature_extraction(ref_img.float().contiguous(memory_format=cl))
+                ft = self.feature_extraction(tgt_img.float().contiguous(memory_format=cl))
             to_cl = lambda t: t.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
             return to_cl(fr), to_cl(ft)
         x = torch.cat([ref_img, tgt_img], 0)

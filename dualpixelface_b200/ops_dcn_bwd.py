@@ -10,9 +10,10 @@ from torch.autograd import Function
 from . import _lib, ops
 
 
-def dcn3d_bwd_data(x: torch.Tensor, offset: torch.Tensor, dy: torch.Tensor, weight: torch.Tensor):
+def dcn3d_bwd_data(x: torch.Tensor, offset: torch.Tensor, dy: torch.Tensor, weight: torch.Tensor, dx_channels: int = 64):
     """x [B,D,H,W,Cs] bf16 (Cs >= 64, channels >= Cin zero), offset [B,D,H,W,81] fp32, dy [B,D,H,W,64] bf16,
-    weight [64,Cin,3,3,3] -> (dx [B,D,H,W,Cs] fp32, doffset [B,D,H,W,81] fp32)."""
+    weight [64,Cin,3,3,3] -> (dx [B,D,H,W,Cs] fp32, doffset [B,D,H,W,81] fp32).  dx_channels = 32 leaves dx[..., 32:] zero
+    (for callers that need no gradient there, e.g. the constant coordinate channels of the ANM volume)."""
     ops._req(x, torch.bfloat16, "x"); ops._req(offset, torch.float32, "offset"); ops._req(dy, torch.bfloat16, "dy")
     b, d, h, w, cs = x.shape
     assert dy.shape == (b, d, h, w, 64) and weight.shape[0] == 64 and weight.shape[1] <= 64
@@ -21,7 +22,7 @@ def dcn3d_bwd_data(x: torch.Tensor, offset: torch.Tensor, dy: torch.Tensor, weig
     dx = torch.zeros(b, d, h, w, cs, device=x.device, dtype=torch.float32)
     doff = torch.empty(b, d, h, w, 81, device=x.device, dtype=torch.float32)
     _lib.check(ops.lib().dpf_dcn3d_bwd_data(ops._p(x), ops._p(offset), ops._p(dy), ops._p(w_t), ops._p(dx), ops._p(doff), b, d, h, w,
-                                            cs, ops._stream()), "dpf_dcn3d_bwd_data")
+                                            cs, dx_channels, ops._stream()), "dpf_dcn3d_bwd_data")
     return dx, doff
 
 
@@ -39,15 +40,16 @@ class DCNFn(Function):
     """z = D3D(x, offset; W) (raw bf16, bias-free: the bias is folded into the following BatchNorm shift)."""
 
     @staticmethod
-    def forward(ctx, x, offset, weight):
+    def forward(ctx, x, offset, weight, dx_channels=64):
         wp = ops.pack_conv_weight(weight.detach(), cin_pad=64)
         ctx.save_for_backward(x, offset, weight)
+        ctx.dx_channels = dx_channels
         return ops.dcn3d(x, offset, wp, 64)
 
     @staticmethod
     def backward(ctx, dz):
         x, offset, weight = ctx.saved_tensors
         dz = dz.to(torch.bfloat16).contiguous()
-        dx, doff = dcn3d_bwd_data(x, offset, dz, weight)
+        dx, doff = dcn3d_bwd_data(x, offset, dz, weight, ctx.dx_channels)
         dw = dcn3d_bwd_weight(x, offset, dz, weight.shape[1]).to(weight.dtype)
-        return dx.to(torch.bfloat16), doff, dw
+        return dx.to(torch.bfloat16), doff, dw, None

@@ -127,9 +127,10 @@ def anm_train(anm, out3: torch.Tensor, disp: torch.Tensor, batch: dict):
     idx, coord, minmax = ops.anm_select(disp.detach().contiguous(), kinv, batch["abvalue"].float().contiguous(), anm.levels, anm.k)
     fv = GatherFn.apply(out3, idx, coord, minmax)
     x, offs = fv, []
-    for dc, act in ((anm.deform_conv1, anm.act1), (anm.deform_conv2, anm.act2)):
+    for i, (dc, act) in enumerate(((anm.deform_conv1, anm.act1), (anm.deform_conv2, anm.act2))):
         off = OffsetConvFn.apply(x, dc.conv_offset.weight, dc.conv_offset.bias)
-        z = DCNFn.apply(x, off, dc.weight)
+        # layer 1 reads the gathered volume: only its 32 cost channels need a gradient (the coordinates are constants)
+        z = DCNFn.apply(x, off, dc.weight, 32 if (i == 0 and out3.shape[-1] == 32) else 64)
         x = BNActFn.apply(z, act[0].weight, act[0].bias, dc.bias, act[0])
         offs.append(off)
     f = x.view(b * anm.k, x.shape[2], x.shape[3], x.shape[4]).permute(0, 3, 1, 2)                # NCHW view, channels-last memory

@@ -146,10 +146,11 @@ int dpf_dcn3d_fwd(const void* x, const float* offset, const void* w, const float
  *      col2im_coord kernels src/cuda/deform_im2col_cuda.cuh:267-405; called from functions/deform_conv_func.py:42-60).
  *      x [B,D,H,W,x_cstride] bf16 (first 64 channels used, zero padded), offset [.,81] fp32, dy [B,D,H,W,64] bf16.
  *      bwd_data:   w_t = W^T packed like kind 0 with the roles of the channels swapped ([27][64/8 o][64 c][8]);
- *                  dx [B,D,H,W,x_cstride] fp32 is ACCUMULATED into (zero it first), doffset [.,81] fp32 is written.
+ *                  dx [B,D,H,W,x_cstride] fp32 is ACCUMULATED into (zero it first; dx_channels = 32 restricts the scatter to
+ *                  channels [0,32) when the caller needs no gradient for the rest), doffset [.,81] fp32 is written.
  *      bwd_weight: dw [27][64 c][64 o] fp32 is ACCUMULATED into (zero it first). */
 int dpf_dcn3d_bwd_data(const void* x, const float* offset, const void* dy, const void* w_t, float* dx, float* doffset,
-                       int B, int D, int H, int W, int x_cstride, void* stream);
+                       int B, int D, int H, int W, int x_cstride, int dx_channels, void* stream);
 int dpf_dcn3d_bwd_weight(const void* x, const float* offset, const void* dy, float* dw, int B, int D, int H, int W,
                          int x_cstride, void* stream);
 

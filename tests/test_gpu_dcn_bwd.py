@@ -47,6 +47,11 @@ def test_dcn3d_backward(cin, shape):
     assert rel_l2(dx[..., :cin].permute(0, 4, 1, 2, 3), want_dx) < 1e-2
     assert rel_l2(doff.permute(0, 4, 1, 2, 3), want_doff) < 1e-2
     assert rel_l2(dw, want_dw) < 1e-2                   # the sampled tile is rounded to bf16 before the MMA
+    dx32, doff32 = dcn3d_bwd_data(xp.cuda(), offp, dyp, wt.cuda(), dx_channels=32)
+    torch.cuda.synchronize()
+    c32 = min(cin, 32)
+    assert rel_l2(dx32[..., :c32].permute(0, 4, 1, 2, 3), want_dx[:, :c32]) < 1e-2 and float(dx32[..., 32:].abs().max()) == 0.0
+    assert rel_l2(doff32.permute(0, 4, 1, 2, 3), want_doff) < 1e-2
 
 
 def test_dcn_autograd_function():

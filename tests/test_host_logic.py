@@ -67,7 +67,10 @@ def test_plan_launches():
                                                                       (0, 32, True, False), (32, 32, False, True)]
     assert len(P(layers.KIND_T2, 64, 64)) == 2
     k96 = P(layers.KIND_3x3x3, 96, 64)                       # offset-conv data gradient: 81 -> 96 padded channels
-    assert [(l.x_coff, l.cin, l.first_k, l.last_k) for l in k96] == [(0, 32, True, False), (32, 32, False, False), (64, 32, False, True)]
+    assert [(l.x_coff, l.cin, l.y_coff, l.first_k, l.last_k) for l in k96] == [
+        (0, 32, 0, True, False), (32, 32, 0, False, False), (64, 32, 0, False, True),
+        (0, 32, 32, True, False), (32, 32, 32, False, False), (64, 32, 32, False, True)]
+    assert [(l.y_coff, l.cout) for l in P(layers.KIND_1x3x3, 32, 64)] == [(0, 64)]
     with pytest.raises(ValueError):
         P(layers.KIND_3x3x3, 48, 32)
 
@@ -127,3 +130,16 @@ def test_synthetic_is_deterministic_and_aliased():
     sh = {"cost_volume.attention_layer.normalize.weight": (32,), "cost_volume.attention_layer.mask_convs.3.1.weight": (32,)}
     st = synth_state(sh)
     assert torch.equal(*st.values())                                          # one InstanceNorm registered under two names
+
+
+def test_losses_match_oracle_on_partial_mask():
+    """Dense masked-mean form of the losses (no boolean-mask gathers) == the reference's `x[mask]` form (oracle restatement)."""
+    from dualpixelface_b200 import losses
+    from oracle import dpf_oracle as O
+    g = torch.Generator().manual_seed(0)
+    pred, disp = torch.randn(2, 3, 16, 24, generator=g), torch.randn(2, 16, 24, generator=g)
+    mask = (torch.rand(2, 16, 24, generator=g) > 0.3).float()
+    pn, nrm = torch.randn(2, 1, 3, 16, 24, generator=g), torch.randn(2, 3, 16, 24, generator=g)
+    b = {"disp": disp, "mask": mask, "normal": nrm}
+    assert abs(float(losses.smooth_l1(pred, b, (1.0, 0.7, 0.5))) - float(O.smooth_l1_multi(pred, disp, mask, (1.0, 0.7, 0.5)))) < 1e-5
+    assert abs(float(losses.cosine(pn, b)) - float(O.cosine_normal_loss(pn, nrm, mask))) < 1e-5
