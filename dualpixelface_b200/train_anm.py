@@ -57,12 +57,18 @@ class OffsetConvFn(Function):
     def backward(ctx, doff):
         x, weight = ctx.saved_tensors
         cout, cin = weight.shape[:2]
-        dzp = torch.zeros(*doff.shape[:-1], 96, device=doff.device, dtype=torch.bfloat16)       # 81 -> 96 channel windows
-        dzp[..., :cout] = doff
-        wt = torch.zeros(64, cout, 3, 3, 3, device=weight.device, dtype=torch.float32)
-        wt[:cin] = weight.detach().float().transpose(0, 1).flip(2, 3, 4)
-        dx = TCConv3d(wt, KIND_3x3x3, cin_pad=96)(dzp)                                          # [.,64] bf16, pad channels zero
-        dw = conv3d_wgrad(x, dzp, KIND_3x3x3)[:cout, :cin].to(weight.dtype)
+        # 81 gradient channels = a 64-wide and a (zero padded) 32-wide input window: two launches per output chunk chained
+        # through the bf16 residual input of the engine (no fp32 partial-sum pass)
+        dz_a = doff[..., :64].to(torch.bfloat16).contiguous()
+        dz_b = torch.zeros(*doff.shape[:-1], 32, device=doff.device, dtype=torch.bfloat16)
+        dz_b[..., :cout - 64] = doff[..., 64:]
+        wt = weight.detach().float().transpose(0, 1).flip(2, 3, 4)                               # [cin, 81, 3,3,3]
+        wa = torch.zeros(64, 64, 3, 3, 3, device=weight.device, dtype=torch.float32)
+        wb = torch.zeros(64, 32, 3, 3, 3, device=weight.device, dtype=torch.float32)
+        wa[:cin] = wt[:, :64]
+        wb[:cin, :cout - 64] = wt[:, 64:]
+        dx = TCConv3d(wb, KIND_3x3x3)(dz_b, residual=TCConv3d(wa, KIND_3x3x3)(dz_a))            # [.,64] bf16, pad channels zero
+        dw = torch.cat([conv3d_wgrad(x, dz_a, KIND_3x3x3), conv3d_wgrad(x, dz_b, KIND_3x3x3)[:cout - 64]], 0)[:, :cin].to(weight.dtype)
         db = doff.reshape(-1, cout).sum(0)
         return dx, dw, db
 
