@@ -163,9 +163,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
 
   if (warp > kMmaWarp) {
     // =================================== producers: global -> shared ring ===================================
-    const int ptid = threadIdx.x - (kMmaWarp + 1) * 32;          // 0..127
+    const int pwarp = warp - (kMmaWarp + 1);                     // 0..kProdWarps-1
     constexpr int PIECES_PER_ROW = C::CWIN * C::NCH;
-    constexpr int PIECES = C::RWIN * PIECES_PER_ROW;
     uint32_t g = 0;
     int prev_slot = -1;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -181,19 +180,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         mbar_wait(&bar_empty[slot], ph ^ 1u);
         const uint32_t sbase = smem_u32(s_slots + slot * C::SLOT_BYTES);
         const __nv_bfloat16* xplane = p.x + (static_cast<size_t>(b) * D + pl) * H * static_cast<size_t>(W) * p.x_cstride + p.x_coff;
-#pragma unroll 4
-        for (int q = ptid; q < PIECES; q += kProdWarps * 32) {
-          const int row = q / PIECES_PER_ROW;
-          const int rem = q - row * PIECES_PER_ROW;
-          const int col = rem / C::NCH;
-          const int c8 = rem - col * C::NCH;
-          const int h = h0 + row, w = w0 + col;
-          const bool ok = (h >= 0) && (h < H) && (w >= 0) && (w < W);
-          const __nv_bfloat16* src = ok ? (xplane + (static_cast<size_t>(h) * W + w) * p.x_cstride + c8 * 8) : p.x;
-          int pos;
-          if (GEO == GEO_S2) pos = ((row & 1) * 2 + (col & 1)) * C::SUB_POS + (row >> 1) * C::WPS + (col >> 1);
-          else pos = row * C::WPS + col;
-          if (!(p.debug & 1)) cp_async16_zfill(sbase + c8 * C::CH_STRIDE + pos * 16, src, ok);
+        // row-based copy: one warp per window row (row decode once per row), lanes over the (column, channel-chunk) pieces
+        if (!(p.debug & 1)) {
+          for (int row = pwarp; row < C::RWIN; row += kProdWarps) {
+            const int h = h0 + row;
+            const bool hok = (h >= 0) && (h < H);
+            const __nv_bfloat16* xrow = xplane + static_cast<size_t>(hok ? h : 0) * W * p.x_cstride;
+            const int rowpos = (GEO == GEO_S2) ? (row & 1) * 2 * C::SUB_POS + (row >> 1) * C::WPS : row * C::WPS;
+#pragma unroll
+            for (int q = lane; q < PIECES_PER_ROW; q += 32) {
+              const int col = q / C::NCH, c8 = q % C::NCH;      // NCH is 4 or 8: shifts
+              const int w = w0 + col;
+              const bool ok = hok && (w >= 0) && (w < W);
+              const __nv_bfloat16* src = ok ? (xrow + static_cast<size_t>(w) * p.x_cstride + c8 * 8) : p.x;
+              const int pos = rowpos + ((GEO == GEO_S2) ? (col & 1) * C::SUB_POS + (col >> 1) : col);
+              cp_async16_zfill(sbase + c8 * C::CH_STRIDE + pos * 16, src, ok);
+            }
+          }
         }
         cp_async_commit();
         if (prev_slot >= 0) {                                    // complete the previous plane (one group of lag)
@@ -319,15 +322,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
               if (p.y_f32) {
                 float* yo = reinterpret_cast<float*>(p.y) + vox * p.y_cstride + p.y_coff + c0;
                 const float* ro = p.residual ? reinterpret_cast<const float*>(p.residual) + vox * p.y_cstride + p.y_coff + c0 : nullptr;
+                if (n == 16 && ((p.y_cstride | p.y_coff) & 3) == 0) {   // 16-byte aligned full chunk: 128-bit loads / stores
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {                    // fully unrolled + predicated: keeps f[] in registers
-                  if (j < n) {
-                    float val = f[j];
-                    if (ro && p.res_pre) val += ro[j];
-                    val = val * s_scale[c0 + j] + s_shift[c0 + j];
-                    if (ro && !p.res_pre) val += ro[j];
-                    if (p.relu) val = fmaxf(val, 0.f);
-                    yo[j] = val;
+                  for (int j4 = 0; j4 < 16; j4 += 4) {
+                    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ro) r = *reinterpret_cast<const float4*>(ro + j4);
+                    float o[4] = {f[j4], f[j4 + 1], f[j4 + 2], f[j4 + 3]};
+                    const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      if (ro && p.res_pre) o[k] += rr[k];
+                      o[k] = o[k] * s_scale[c0 + j4 + k] + s_shift[c0 + j4 + k];
+                      if (ro && !p.res_pre) o[k] += rr[k];
+                      if (p.relu) o[k] = fmaxf(o[k], 0.f);
+                    }
+                    *reinterpret_cast<float4*>(yo + j4) = make_float4(o[0], o[1], o[2], o[3]);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {                  // fully unrolled + predicated: keeps f[] in registers
+                    if (j < n) {
+                      float val = f[j];
+                      if (ro && p.res_pre) val += ro[j];
+                      val = val * s_scale[c0 + j] + s_shift[c0 + j];
+                      if (ro && !p.res_pre) val += ro[j];
+                      if (p.relu) val = fmaxf(val, 0.f);
+                      yo[j] = val;
+                    }
                   }
                 }
               } else {
@@ -478,9 +499,8 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
 
   if (warp > kFMmaWarp) {
     // =================================== producers (identical to the generic kernel) ======================
-    const int ptid = threadIdx.x - (kFMmaWarp + 1) * 32;
+    const int pwarp = warp - (kFMmaWarp + 1);
     constexpr int PIECES_PER_ROW = C::WP * C::NCH;
-    constexpr int PIECES = 18 * PIECES_PER_ROW;
     uint32_t g = 0;
     int prev_slot = -1;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -493,16 +513,20 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
         mbar_wait(&bar_empty[slot], ((g / NS) & 1u) ^ 1u);
         const uint32_t sbase = smem_u32(s_slots + slot * C::SLOT_BYTES);
         const __nv_bfloat16* xplane = p.x + (static_cast<size_t>(b) * D + pl) * H * static_cast<size_t>(W) * p.x_cstride + p.x_coff;
-#pragma unroll 4
-        for (int q = ptid; q < PIECES; q += kProdWarps * 32) {
-          const int row = q / PIECES_PER_ROW;
-          const int rem = q - row * PIECES_PER_ROW;
-          const int col = rem / C::NCH;
-          const int c8 = rem - col * C::NCH;
-          const int h = h0 + row, w = w0 + col;
-          const bool ok = (h >= 0) && (h < H) && (w >= 0) && (w < W);
-          const __nv_bfloat16* src = ok ? (xplane + (static_cast<size_t>(h) * W + w) * p.x_cstride + c8 * 8) : p.x;
-          if (!(p.debug & 1)) cp_async16_zfill(sbase + c8 * C::CH_STRIDE + (row * C::WP + col) * 16, src, ok);
+        if (!(p.debug & 1)) {                                    // row-based copy, see the generic kernel
+          for (int row = pwarp; row < 18; row += kProdWarps) {
+            const int h = h0 + row;
+            const bool hok = (h >= 0) && (h < H);
+            const __nv_bfloat16* xrow = xplane + static_cast<size_t>(hok ? h : 0) * W * p.x_cstride;
+#pragma unroll
+            for (int q = lane; q < PIECES_PER_ROW; q += 32) {
+              const int col = q / C::NCH, c8 = q % C::NCH;
+              const int w = w0 + col;
+              const bool ok = hok && (w >= 0) && (w < W);
+              const __nv_bfloat16* src = ok ? (xrow + static_cast<size_t>(w) * p.x_cstride + c8 * 8) : p.x;
+              cp_async16_zfill(sbase + c8 * C::CH_STRIDE + (row * C::WP + col) * 16, src, ok);
+            }
+          }
         }
         cp_async_commit();
         if (prev_slot >= 0) {
@@ -639,15 +663,33 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
           if (p.y_f32) {
             float* yo = reinterpret_cast<float*>(p.y) + vox * p.y_cstride + p.y_coff + c0;
             const float* ro = p.residual ? reinterpret_cast<const float*>(p.residual) + vox * p.y_cstride + p.y_coff + c0 : nullptr;
+            if (n == 16 && ((p.y_cstride | p.y_coff) & 3) == 0) {     // 16-byte aligned full chunk: 128-bit loads / stores
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {                        // fully unrolled + predicated: keeps f[] in registers
-              if (j < n) {
-                float val = f[j];
-                if (ro && p.res_pre) val += ro[j];
-                val = val * s_scale[c0 + j] + s_shift[c0 + j];
-                if (ro && !p.res_pre) val += ro[j];
-                if (p.relu) val = fmaxf(val, 0.f);
-                yo[j] = val;
+              for (int j4 = 0; j4 < 16; j4 += 4) {
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ro) r = *reinterpret_cast<const float4*>(ro + j4);
+                float o[4] = {f[j4], f[j4 + 1], f[j4 + 2], f[j4 + 3]};
+                const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (ro && p.res_pre) o[k] += rr[k];
+                  o[k] = o[k] * s_scale[c0 + j4 + k] + s_shift[c0 + j4 + k];
+                  if (ro && !p.res_pre) o[k] += rr[k];
+                  if (p.relu) o[k] = fmaxf(o[k], 0.f);
+                }
+                *reinterpret_cast<float4*>(yo + j4) = make_float4(o[0], o[1], o[2], o[3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {                      // fully unrolled + predicated: keeps f[] in registers
+                if (j < n) {
+                  float val = f[j];
+                  if (ro && p.res_pre) val += ro[j];
+                  val = val * s_scale[c0 + j] + s_shift[c0 + j];
+                  if (ro && !p.res_pre) val += ro[j];
+                  if (p.relu) val = fmaxf(val, 0.f);
+                  yo[j] = val;
+                }
               }
             }
           } else {

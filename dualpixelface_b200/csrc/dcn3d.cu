@@ -4,7 +4,7 @@
 // Replaces DCN.deform_conv_forward (src/module/dcn3d/src/deform_conv.h:10-29 -> src/cuda/deform_conv_cuda.cu:18-126)
 // and its im2col kernel (src/cuda/deform_im2col_cuda.cuh:192-265, sampling rule :26-72, in-bounds test :248).
 //   y[v, o] = relu?( scale[o] * sum_{tap,c} W[o,c,tap] * trilinear(x[:, c], p_v + tap - 1 + offset[v, 3*tap + (0,1,2)]) + shift[o] )
-// x [B,D,H,W,x_cstride] bf16 (the first CINP channels are gathered; zero-padded beyond the real Cin), offset [B,D,H,W,81] fp32 ((d,h,w) per tap), y [B,D,H,W,64] bf16.
+// x [B,D,H,W,x_cstride] bf16 (the first CINP channels are gathered; zero-padded beyond the real Cin), offset [B,D,H,W,off_cstride >= 81] fp32 ((d,h,w) per tap), y [B,D,H,W,64] bf16.
 //
 // Work unit: a 16 x 16 spatial tile of one depth plane = 256 voxels (2 GEMM blocks of 128 rows); every CTA owns a
 // contiguous range of units so that the planes a tap gathers from stay hot in L1 / L2 across taps and units.  For every tap, 16 producer warps compute the
@@ -37,7 +37,7 @@ struct DcnParams {
   const float* scale;
   const float* shift;
   __nv_bfloat16* y;
-  int B, D, H, W, relu, x_cstride;
+  int B, D, H, W, relu, x_cstride, off_cstride;
   long long nvox;
   int nunits, tiles_h, tiles_w;
 };
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
         for (int ps = 0; ps < PASSES; ++ps) {
           const int r = ps * kVoxPerPass + vsub;             // row inside the work unit (0..255)
           const int vox = vbase + (ud * H + vh[ps]) * W + vw[ps];
-          const float* op = p.offset + static_cast<size_t>(vox) * 81 + tap * 3;
+          const float* op = p.offset + static_cast<size_t>(vox) * p.off_cstride + tap * 3;
           const float pd = fdz + __ldg(op + 0);
           const float phh = static_cast<float>(vh[ps] + tj) + __ldg(op + 1);
           const float pw = static_cast<float>(vw[ps] + tk) + __ldg(op + 2);
@@ -335,7 +335,8 @@ int launch_dcn(const DcnParams& p, cudaStream_t st) {
 }  // namespace
 
 extern "C" int dpf_dcn3d_fwd(const void* x, const float* offset, const void* w, const float* scale, const float* shift,
-                             void* y, int B, int D, int H, int W, int Cin_pad, int x_cstride, int Cout, int relu, void* stream) {
+                             void* y, int B, int D, int H, int W, int Cin_pad, int x_cstride, int off_cstride, int Cout, int relu,
+                             void* stream) {
   DPF_REQUIRE(x && offset && w && y, "dpf_dcn3d_fwd: null pointer");
   DPF_REQUIRE(DPF_ALIGNED16(x) && DPF_ALIGNED16(w) && DPF_ALIGNED16(y), "dpf_dcn3d_fwd: pointers must be 16-byte aligned");
   DPF_REQUIRE(Cout == kNOut, "dpf_dcn3d_fwd: Cout=%d, only 64 is built", Cout);
@@ -343,9 +344,11 @@ extern "C" int dpf_dcn3d_fwd(const void* x, const float* offset, const void* w, 
   DPF_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "dpf_dcn3d_fwd: bad shape");
   DPF_REQUIRE(static_cast<long long>(B) * D * H * W < (1LL << 31) / 128, "dpf_dcn3d_fwd: tensor too large for 32-bit voxel indexing");
   DPF_REQUIRE(x_cstride >= Cin_pad && x_cstride % 8 == 0, "dpf_dcn3d_fwd: x_cstride=%d must be a multiple of 8 >= Cin_pad", x_cstride);
+  DPF_REQUIRE(off_cstride >= 81, "dpf_dcn3d_fwd: off_cstride=%d must be >= 81", off_cstride);
   DcnParams p{};
   p.x = reinterpret_cast<const __nv_bfloat16*>(x);
   p.offset = offset;
+  p.off_cstride = off_cstride;
   p.w = reinterpret_cast<const __nv_bfloat16*>(w);
   p.scale = scale;
   p.shift = shift;

@@ -35,9 +35,9 @@ struct BwdParams {
   const __nv_bfloat16* dy;
   const __nv_bfloat16* w;       // data kernel: W^T packed [tap][o/8][c][8]
   float* dx;                    // [nvox][x_cstride] fp32 (zeroed by the caller)
-  float* doff;                  // [nvox][81] fp32
+  float* doff;                  // [nvox][off_cstride] fp32 (channels >= 81 are not written)
   float* dw;                    // weight kernel: [27][c][o] fp32 (zeroed by the caller)
-  int B, D, H, W, x_cstride;
+  int B, D, H, W, x_cstride, off_cstride;
   int nunits, tiles_h, tiles_w, tap0, tap1;
   int dx_channels;              // data kernel: 32 -> only channels [0,32) of dx are accumulated, else all 64
 };
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kDThreads, 1) dcn3d_bwd_data_kernel(const __gr
           const int hh = uh0 + (r >> 4), ww = uw0 + (r & 15);
           const bool live = hh < H && ww < W;
           const int vox = vbase + (ud * H + (live ? hh : 0)) * W + (live ? ww : 0);
-          const float* op = p.offset + static_cast<size_t>(vox) * 81 + tap * 3;
+          const float* op = p.offset + static_cast<size_t>(vox) * p.off_cstride + tap * 3;
           const float pd = static_cast<float>(ud + ti) + __ldg(op + 0);
           const float ph = static_cast<float>(hh + tj) + __ldg(op + 1);
           const float pw = static_cast<float>(ww + tk) + __ldg(op + 2);
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kDThreads, 1) dcn3d_bwd_data_kernel(const __gr
             gw2 += __shfl_xor_sync(0xffffffffu, gw2, m);
           }
           if (live && j < 3) {
-            float* dop = p.doff + static_cast<size_t>(vox) * 81 + tap * 3;
+            float* dop = p.doff + static_cast<size_t>(vox) * p.off_cstride + tap * 3;
             dop[j] = j == 0 ? gd : (j == 1 ? gh : gw2);
           }
         }
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(kWThreads, 1) dcn3d_bwd_weight_kernel(const __
         for (int ps = 0; ps < PASSES; ++ps) {
           const int r = ps * kVoxPerPass + vsub;
           const int vox = vbase + (ud * H + vh[ps]) * W + vw[ps];
-          const float* op = p.offset + static_cast<size_t>(vox) * 81 + tap * 3;
+          const float* op = p.offset + static_cast<size_t>(vox) * p.off_cstride + tap * 3;
           const float pd = fdz + __ldg(op + 0);
           const float phh = static_cast<float>(vh[ps] + tj) + __ldg(op + 1);
           const float pw = static_cast<float>(vw[ps] + tk) + __ldg(op + 2);
@@ -481,8 +481,8 @@ __global__ void __launch_bounds__(kWThreads, 1) dcn3d_bwd_weight_kernel(const __
   if (warp == 4) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
 }
 
-int fill(BwdParams& p, int B, int D, int H, int W, int x_cstride) {
-  p.B = B; p.D = D; p.H = H; p.W = W; p.x_cstride = x_cstride;
+int fill(BwdParams& p, int B, int D, int H, int W, int x_cstride, int off_cstride) {
+  p.B = B; p.D = D; p.H = H; p.W = W; p.x_cstride = x_cstride; p.off_cstride = off_cstride;
   p.tiles_h = (H + 15) / 16;
   p.tiles_w = (W + 15) / 16;
   p.nunits = B * D * p.tiles_h * p.tiles_w;
@@ -492,7 +492,7 @@ int fill(BwdParams& p, int B, int D, int H, int W, int x_cstride) {
 }  // namespace
 
 extern "C" int dpf_dcn3d_bwd_data(const void* x, const float* offset, const void* dy, const void* w_t, float* dx, float* doffset,
-                                  int B, int D, int H, int W, int x_cstride, int dx_channels, void* stream) {
+                                  int B, int D, int H, int W, int x_cstride, int off_cstride, int dx_channels, void* stream) {
   DPF_REQUIRE(x && offset && dy && w_t && dx && doffset, "dpf_dcn3d_bwd_data: null pointer");
   DPF_REQUIRE(x_cstride >= kC && x_cstride % 8 == 0, "dpf_dcn3d_bwd_data: x_cstride=%d must be a multiple of 8 >= 64", x_cstride);
   DPF_REQUIRE(dx_channels == 32 || dx_channels == 64, "dpf_dcn3d_bwd_data: dx_channels=%d must be 32 or 64", dx_channels);
@@ -504,7 +504,8 @@ extern "C" int dpf_dcn3d_bwd_data(const void* x, const float* offset, const void
   p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
   p.w = reinterpret_cast<const __nv_bfloat16*>(w_t);
   p.dx = dx; p.doff = doffset; p.dx_channels = dx_channels;
-  fill(p, B, D, H, W, x_cstride);
+  DPF_REQUIRE(off_cstride >= 81, "dpf_dcn3d_bwd: off_cstride=%d must be >= 81", off_cstride);
+  fill(p, B, D, H, W, x_cstride, off_cstride);
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(dcn3d_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem);
@@ -516,7 +517,7 @@ extern "C" int dpf_dcn3d_bwd_data(const void* x, const float* offset, const void
 }
 
 extern "C" int dpf_dcn3d_bwd_weight(const void* x, const float* offset, const void* dy, float* dw, int B, int D, int H, int W,
-                                    int x_cstride, void* stream) {
+                                    int x_cstride, int off_cstride, void* stream) {
   DPF_REQUIRE(x && offset && dy && dw, "dpf_dcn3d_bwd_weight: null pointer");
   DPF_REQUIRE(x_cstride >= kC && x_cstride % 8 == 0, "dpf_dcn3d_bwd_weight: x_cstride=%d must be a multiple of 8 >= 64", x_cstride);
   DPF_REQUIRE(static_cast<long long>(B) * D * H * W < (1LL << 31) / 128, "dpf_dcn3d_bwd_weight: tensor too large for 32-bit voxel indexing");
@@ -525,7 +526,8 @@ extern "C" int dpf_dcn3d_bwd_weight(const void* x, const float* offset, const vo
   p.offset = offset;
   p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
   p.dw = dw;
-  fill(p, B, D, H, W, x_cstride);
+  DPF_REQUIRE(off_cstride >= 81, "dpf_dcn3d_bwd: off_cstride=%d must be >= 81", off_cstride);
+  fill(p, B, D, H, W, x_cstride, off_cstride);
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(dcn3d_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem);

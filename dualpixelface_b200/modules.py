@@ -519,8 +519,9 @@ class ANM(nn.Module):
                 bn = act[0]
                 cin = dc.weight.shape[1]
                 cpad = 64      # gathering 64 (zero-padded) channels measured faster than the 48-channel variant
-                p[f"off{i}"] = TCConv3d(dc.conv_offset.weight, KIND_3x3x3, cin_pad=64)
-                p[f"offb{i}"] = dc.conv_offset.bias.detach().float().contiguous()
+                # 81 -> 96 zero-padded offset channels: a 384-byte voxel pitch keeps the fp32 epilogue on 128-bit stores
+                p[f"off{i}"] = TCConv3d(F.pad(dc.conv_offset.weight.detach(), (0, 0, 0, 0, 0, 0, 0, 0, 0, 15)), KIND_3x3x3, cin_pad=64)
+                p[f"offb{i}"] = F.pad(dc.conv_offset.bias.detach().float(), (0, 15)).contiguous()
                 p[f"w{i}"] = ops.pack_conv_weight(dc.weight.detach(), cin_pad=cpad)
                 p[f"cpad{i}"] = cpad
                 p[f"aff{i}"] = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, conv_bias=dc.bias)
@@ -556,6 +557,6 @@ class ANM(nn.Module):
             # fused x4 bilinear upsample + sigmoid + mean over the k sampled planes + rescale to [-1, 1]
             from .ops_tail import anm_tail
             normals.append(anm_tail(x.permute(0, 2, 3, 1).contiguous(), b, self.k))
-            off1s.append(off1)
-            off2s.append(off2)
+            off1s.append(off1[..., :81])
+            off2s.append(off2[..., :81])
         return normals, off1s, off2s

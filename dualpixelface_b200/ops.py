@@ -107,6 +107,27 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None, transposed:
     return buf.reshape(taps, cin_pad // 8, 8, npad).permute(0, 1, 3, 2).contiguous().to(torch.bfloat16)
 
 
+# Opt-in per-launch timing (bench.py sets KERNEL_TIMING = {} around its stage passes): CUDA events on the launching stream
+# around single launches, keyed by kernel + shape class; value = list of (start, end, algorithmic work, unit).
+KERNEL_TIMING = None
+
+
+def _timing_begin():
+    if KERNEL_TIMING is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _timing_end(e0, key, work, unit):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    KERNEL_TIMING.setdefault(key, []).append((e0, e1, float(work), unit))
+
+
 def conv3d(x: torch.Tensor, w_packed: torch.Tensor, kind: int, cout: int, scale: Optional[torch.Tensor] = None,
            shift: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, relu: bool = False,
            out: Optional[torch.Tensor] = None, out_f32: bool = False, y_coff: int = 0, cin: Optional[int] = None,
@@ -140,7 +161,10 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, kind: int, cout: int, scale:
                  shift=shift.data_ptr() if shift is not None else None,
                  residual=residual.data_ptr() if residual is not None else None, relu=int(relu), stats=None,
                  x_cstride=cx, x_coff=x_coff, res_pre=int(res_pre))
+    tm = _timing_begin()
     check(lib().dpf_conv3d_fwd(C.byref(a), _stream()), "dpf_conv3d_fwd")
+    vox = b * (d * h * w if kind == KIND_T2 else do * ho * wo)       # transposed: every input voxel meets all 27 taps
+    _timing_end(tm, f"conv3d kind{kind} {cin}->{cout}", 2.0 * w_packed.shape[0] * cin * cout * vox, "flop")
     return out
 
 
@@ -152,7 +176,9 @@ def regress_fwd(cost: torch.Tensor, mindisp: float, step: float, want_prob: bool
     b, d, h4, w4 = cost.shape
     disp = torch.empty(b, 4 * h4, 4 * w4, device=cost.device, dtype=torch.float32)
     prob = torch.empty(b, 4 * d, 4 * h4, 4 * w4, device=cost.device, dtype=torch.float32) if want_prob else None
+    tm = _timing_begin()
     check(lib().dpf_regress_fwd(_p(cost), _p(disp), _p(prob), b, d, h4, w4, float(mindisp), float(step), _stream()), "dpf_regress_fwd")
+    _timing_end(tm, "regress_fwd", cost.numel() * 4.0 + disp.numel() * 4.0 + (prob.numel() * 4.0 if prob is not None else 0.0), "byte")
     return disp, prob
 
 
@@ -196,8 +222,11 @@ def asm_blend(samples: torch.Tensor, logits: torch.Tensor, in_a: torch.Tensor, i
     b, s, h, w, c = samples.shape
     assert logits.shape == samples.shape and in_a.shape == (b, c) and in_d.shape == (b, c)
     assert vol.shape[0] == b and vol.shape[2:4] == (h, w)
+    tm = _timing_begin()
     check(lib().dpf_asm_blend_fwd(_p(samples), _p(logits), _p(in_a), _p(in_d), _p(vol), b, h, w, c, s, vol.shape[1], d0, d_rep,
                                   ch_off, vol.shape[-1], _stream()), "dpf_asm_blend_fwd")
+    # algorithmic bytes: samples + logits read once, d_rep volume slices of c channels written
+    _timing_end(tm, "asm_blend", 2.0 * (samples.numel() + logits.numel()) + 2.0 * b * h * w * c * d_rep, "byte")
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -220,13 +249,15 @@ def anm_select(disp: torch.Tensor, kinv: torch.Tensor, abvalue: torch.Tensor, le
 
 def dcn3d(x: torch.Tensor, offset: torch.Tensor, w_packed: torch.Tensor, cin_pad: int, scale: Optional[torch.Tensor] = None,
           shift: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
-    """3-D deformable conv 3x3x3 (stride 1, pad 1): x [B,D,H,W,Cs] bf16, offset [B,D,H,W,81] fp32 -> [B,D,H,W,64] bf16."""
+    """3-D deformable conv 3x3x3 (stride 1, pad 1): x [B,D,H,W,Cs] bf16, offset [B,D,H,W,>=81] fp32 -> [B,D,H,W,64] bf16."""
     _req(x, torch.bfloat16, "x"); _req(offset, torch.float32, "offset"); _req(w_packed, torch.bfloat16, "w_packed")
     b, d, h, w, cs = x.shape
-    assert offset.shape == (b, d, h, w, 81)
+    assert offset.shape[:4] == (b, d, h, w) and offset.shape[-1] >= 81 and offset.is_contiguous()
     y = torch.empty(b, d, h, w, 64, device=x.device, dtype=torch.bfloat16)
-    check(lib().dpf_dcn3d_fwd(_p(x), _p(offset), _p(w_packed), _p(scale), _p(shift), _p(y), b, d, h, w, cin_pad, cs, 64,
-                              int(relu), _stream()), "dpf_dcn3d_fwd")
+    tm = _timing_begin()
+    check(lib().dpf_dcn3d_fwd(_p(x), _p(offset), _p(w_packed), _p(scale), _p(shift), _p(y), b, d, h, w, cin_pad, cs,
+                              offset.shape[-1], 64, int(relu), _stream()), "dpf_dcn3d_fwd")
+    _timing_end(tm, "dcn3d 64->64", 2.0 * 27 * 64 * 64 * b * d * h * w, "flop")
     return y
 
 

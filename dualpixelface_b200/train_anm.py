@@ -46,22 +46,24 @@ class GatherFn(Function):
 
 
 class OffsetConvFn(Function):
-    """offset = conv3x3x3(x; W[81,Cin,3,3,3]) + bias -> fp32 [B,K,H4,W4,81]; x is the 64-channel (zero padded) volume."""
+    """offset = conv3x3x3(x; W[81,Cin,3,3,3]) + bias -> fp32 [B,K,H4,W4,96] (81 real channels, zero padded so that the voxel
+    pitch is 384 B and the fp32 epilogue uses 128-bit stores); x is the 64-channel (zero padded) volume."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
-        return TCConv3d(weight, KIND_3x3x3, cin_pad=64)(x, shift=bias.detach().float().contiguous(), out_f32=True)
+        wpad = F.pad(weight.detach(), (0, 0, 0, 0, 0, 0, 0, 0, 0, 96 - weight.shape[0]))
+        bpad = F.pad(bias.detach().float(), (0, 96 - weight.shape[0])).contiguous()
+        return TCConv3d(wpad, KIND_3x3x3, cin_pad=64)(x, shift=bpad, out_f32=True)
 
     @staticmethod
     def backward(ctx, doff):
         x, weight = ctx.saved_tensors
         cout, cin = weight.shape[:2]
-        # 81 gradient channels = a 64-wide and a (zero padded) 32-wide input window: two launches per output chunk chained
+        # 96 gradient channels (81 real) = a 64-wide and a 32-wide input window: two launches per output chunk chained
         # through the bf16 residual input of the engine (no fp32 partial-sum pass)
         dz_a = doff[..., :64].to(torch.bfloat16).contiguous()
-        dz_b = torch.zeros(*doff.shape[:-1], 32, device=doff.device, dtype=torch.bfloat16)
-        dz_b[..., :cout - 64] = doff[..., 64:]
+        dz_b = doff[..., 64:].to(torch.bfloat16).contiguous()
         wt = weight.detach().float().transpose(0, 1).flip(2, 3, 4)                               # [cin, 81, 3,3,3]
         wa = torch.zeros(64, 64, 3, 3, 3, device=weight.device, dtype=torch.float32)
         wb = torch.zeros(64, 32, 3, 3, 3, device=weight.device, dtype=torch.float32)
@@ -69,7 +71,7 @@ class OffsetConvFn(Function):
         wb[:cin, :cout - 64] = wt[:, 64:]
         dx = TCConv3d(wb, KIND_3x3x3)(dz_b, residual=TCConv3d(wa, KIND_3x3x3)(dz_a))            # [.,64] bf16, pad channels zero
         dw = torch.cat([conv3d_wgrad(x, dz_a, KIND_3x3x3), conv3d_wgrad(x, dz_b, KIND_3x3x3)[:cout - 64]], 0)[:, :cin].to(weight.dtype)
-        db = doff.reshape(-1, cout).sum(0)
+        db = doff[..., :cout].reshape(-1, cout).sum(0)
         return dx, dw, db
 
 
@@ -138,7 +140,7 @@ def anm_train(anm, out3: torch.Tensor, disp: torch.Tensor, batch: dict):
         # layer 1 reads the gathered volume: only its 32 cost channels need a gradient (the coordinates are constants)
         z = DCNFn.apply(x, off, dc.weight, 32 if (i == 0 and out3.shape[-1] == 32) else 64)
         x = BNActFn.apply(z, act[0].weight, act[0].bias, dc.bias, act[0])
-        offs.append(off)
+        offs.append(off[..., :81])
     f = x.view(b * anm.k, x.shape[2], x.shape[3], x.shape[4]).permute(0, 3, 1, 2)                # NCHW view, channels-last memory
     for m in anm.n_convs:
         conv = m[0]

@@ -136,23 +136,25 @@ int dpf_anm_gather(const void* out3, const int* idx, const float* coord, const f
  * (6) 3-D deformable convolution (D3D), 3x3x3 stride 1 pad 1, groups 1.  Replaces DCN.deform_conv_forward
  *     (src/module/dcn3d/src/deform_conv.h:10-29 -> src/cuda/deform_conv_cuda.cu:18-126 and the im2col kernel
  *     src/cuda/deform_im2col_cuda.cuh:192-265) without the [27*Cin, B*D*H*W] column buffer.
- *     x [B,D,H,W,x_cstride] bf16 (first Cin_pad in {48,64} channels used), offset [B,D,H,W,81] fp32 ((d,h,w) per tap), w packed like kind 0 with Cin_pad,
+ *     x [B,D,H,W,x_cstride] bf16 (first Cin_pad in {48,64} channels used), offset [B,D,H,W,off_cstride>=81] fp32
+ *     ((d,h,w) per tap; a stride of 96 lets the offset conv use 128-bit fp32 stores), w packed like kind 0 with Cin_pad,
  *     y = relu?( dconv * scale + shift ) -> [B,D,H,W,Cout] bf16.
  * ------------------------------------------------------------------------------------------------- */
 int dpf_dcn3d_fwd(const void* x, const float* offset, const void* w, const float* scale, const float* shift, void* y,
-                  int B, int D, int H, int W, int Cin_pad, int x_cstride, int Cout, int relu, void* stream);
+                  int B, int D, int H, int W, int Cin_pad, int x_cstride, int off_cstride, int Cout, int relu, void* stream);
 
 /* (6b) D3D backward.  Replaces DCN.deform_conv_backward (src/module/dcn3d/src/cuda/deform_conv_cuda.cu:128-285; col2im and
  *      col2im_coord kernels src/cuda/deform_im2col_cuda.cuh:267-405; called from functions/deform_conv_func.py:42-60).
- *      x [B,D,H,W,x_cstride] bf16 (first 64 channels used, zero padded), offset [.,81] fp32, dy [B,D,H,W,64] bf16.
+ *      x [B,D,H,W,x_cstride] bf16 (first 64 channels used, zero padded), offset and doffset [.,off_cstride] fp32 (81 used),
+ *      dy [B,D,H,W,64] bf16.
  *      bwd_data:   w_t = W^T packed like kind 0 with the roles of the channels swapped ([27][64/8 o][64 c][8]);
  *                  dx [B,D,H,W,x_cstride] fp32 is ACCUMULATED into (zero it first; dx_channels = 32 restricts the scatter to
  *                  channels [0,32) when the caller needs no gradient for the rest), doffset [.,81] fp32 is written.
  *      bwd_weight: dw [27][64 c][64 o] fp32 is ACCUMULATED into (zero it first). */
 int dpf_dcn3d_bwd_data(const void* x, const float* offset, const void* dy, const void* w_t, float* dx, float* doffset,
-                       int B, int D, int H, int W, int x_cstride, int dx_channels, void* stream);
+                       int B, int D, int H, int W, int x_cstride, int off_cstride, int dx_channels, void* stream);
 int dpf_dcn3d_bwd_weight(const void* x, const float* offset, const void* dy, float* dw, int B, int D, int H, int W,
-                         int x_cstride, void* stream);
+                         int x_cstride, int off_cstride, void* stream);
 
 /* (6c) Backward of the memory-bound ANM ops (normal_module.py:140-194).
  *      tail_bwd:   x [B*K,H4,W4,3] bf16 (the forward input), dout [B,3,4*H4,4*W4] fp32 -> dx [B*K,H4,W4,3] fp32, ACCUMULATED
