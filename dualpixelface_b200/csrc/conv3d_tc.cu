@@ -355,33 +355,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                 __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + vox * p.y_cstride + p.y_coff + c0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] = f[j] * s_scale[c0 + j] + s_shift[c0 + j];
+                const bool wide = (n == 16) && (((p.y_cstride | p.y_coff) & 15) == 0);   // 32-byte aligned full chunk
                 if (p.residual) {
                   const __nv_bfloat16* ro = reinterpret_cast<const __nv_bfloat16*>(p.residual) + vox * p.y_cstride + p.y_coff + c0;
-#pragma unroll
-                  for (int j8 = 0; j8 < 16; j8 += 8) {
-                    if (j8 < n) {
-                      const uint4 r = *reinterpret_cast<const uint4*>(ro + j8);
-                      f[j8 + 0] += bf16_lo(r.x); f[j8 + 1] += bf16_hi(r.x);
-                      f[j8 + 2] += bf16_lo(r.y); f[j8 + 3] += bf16_hi(r.y);
-                      f[j8 + 4] += bf16_lo(r.z); f[j8 + 5] += bf16_hi(r.z);
-                      f[j8 + 6] += bf16_lo(r.w); f[j8 + 7] += bf16_hi(r.w);
-                    }
+                  uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+                  if (wide) ld_global_v8(ro, r0, r1);
+                  else {
+                    r0 = *reinterpret_cast<const uint4*>(ro);
+                    if (n > 8) r1 = *reinterpret_cast<const uint4*>(ro + 8);
                   }
+                  f[0] += bf16_lo(r0.x); f[1] += bf16_hi(r0.x); f[2] += bf16_lo(r0.y); f[3] += bf16_hi(r0.y);
+                  f[4] += bf16_lo(r0.z); f[5] += bf16_hi(r0.z); f[6] += bf16_lo(r0.w); f[7] += bf16_hi(r0.w);
+                  f[8] += bf16_lo(r1.x); f[9] += bf16_hi(r1.x); f[10] += bf16_lo(r1.y); f[11] += bf16_hi(r1.y);
+                  f[12] += bf16_lo(r1.z); f[13] += bf16_hi(r1.z); f[14] += bf16_lo(r1.w); f[15] += bf16_hi(r1.w);
                 }
                 if (p.relu) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
                 }
-#pragma unroll
-                for (int j8 = 0; j8 < 16; j8 += 8) {             // n is a multiple of 8 (checked on the host)
-                  if (j8 < n) {
-                    uint4 o;
-                    o.x = pack_bf16x2(f[j8 + 0], f[j8 + 1]);
-                    o.y = pack_bf16x2(f[j8 + 2], f[j8 + 3]);
-                    o.z = pack_bf16x2(f[j8 + 4], f[j8 + 5]);
-                    o.w = pack_bf16x2(f[j8 + 6], f[j8 + 7]);
-                    *reinterpret_cast<uint4*>(yo + j8) = o;
-                  }
+                uint4 o0, o1;                                      // n is a multiple of 8 (checked on the host)
+                o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]); o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
+                o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]); o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                if (wide) st_global_v8(yo, o0, o1);
+                else {
+                  *reinterpret_cast<uint4*>(yo) = o0;
+                  if (n > 8) *reinterpret_cast<uint4*>(yo + 8) = o1;
                 }
               }
             }
