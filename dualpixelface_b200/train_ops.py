@@ -11,8 +11,8 @@ Backward:
     dx = conv^T(dz)                  the SAME tcgen05 engine with transformed weights: a stride-1 conv's data gradient is a
                                      stride-1 conv with flipped/transposed taps, a stride-2 conv's is the transposed-conv kind,
                                      a transposed conv's is the stride-2 kind
-    dW                               cuDNN weight-gradient via aten.convolution_backward on the channels-last views
-                                     (library call for now; a tcgen05 wgrad kernel is the next item)
+    dW                               dpf_conv3d_wgrad: tcgen05, voxel positions as the GEMM K dimension, MN-major operands
+                                     straight from the forward staging layout (all five kinds)
 """
 from __future__ import annotations
 
@@ -52,23 +52,10 @@ def _bn_bwd(dy, y, z, a, mean, inv_std, relu, want_dres):
     return dz, dres, inv_std * centred, s1          # dz, dres, dgamma, dbeta
 
 
-def _ncdhw(t):
-    """[B,D,H,W,C] contiguous -> logical NCDHW view with channels_last_3d strides (what cuDNN wants)."""
-    return t.permute(0, 4, 1, 2, 3)
-
-
 def _wgrad(x, dz, weight, kind):
-    """dW.  Stride-1 kinds: the tcgen05 wgrad kernel (dpf_conv3d_wgrad).  Stride-2 / transposed kinds (11 % of the FLOPs):
-    still cuDNN through aten.convolution_backward on the bf16 channels-last-3d views (their tcgen05 wgrad is next)."""
-    if kind in (KIND_3x3x3, KIND_1x3x3, KIND_1x1x1):
-        from .ops_wgrad import conv3d_wgrad
-        return conv3d_wgrad(x, dz, kind).to(weight.dtype)
-    transposed = kind == KIND_T2
-    stride = [2, 2, 2] if kind in (KIND_S2, KIND_T2) else [1, 1, 1]
-    pad = {KIND_1x3x3: [0, 1, 1], KIND_1x1x1: [0, 0, 0]}.get(kind, [1, 1, 1])
-    gw = torch.ops.aten.convolution_backward(_ncdhw(dz), _ncdhw(x), weight.to(torch.bfloat16), None, stride, pad, [1, 1, 1],
-                                             transposed, [1, 1, 1] if transposed else [0, 0, 0], 1, [False, True, False])[1]
-    return gw.to(weight.dtype)
+    """dW on the tcgen05 wgrad kernel (dpf_conv3d_wgrad) for every kind; the transposed kind swaps the roles of x and dz."""
+    from .ops_wgrad import conv3d_wgrad
+    return conv3d_wgrad(x, dz, kind).to(weight.dtype)
 
 
 def _dgrad(dz, weight, kind):
