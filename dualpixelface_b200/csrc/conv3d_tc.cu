@@ -413,9 +413,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
 // mixes "first contribution" and "accumulate" columns, accumulators are zeroed by the epilogue (tcgen05.st) when it
 // drains them, and every MMA accumulates.  When the three stages wrap around the ring the MMA is split in two.
 // ============================================================================================================
-constexpr int kFEpiWarps = 8;                                       // fused kernel: 8 epilogue warps, MMA warp 8, 4 producers
+constexpr int kFEpiWarps = 8;                                       // fused kernel: 8 epilogue warps, MMA warps 8-9, 4 producers
 constexpr int kFMmaWarp = kFEpiWarps;
-constexpr int kFThreads = (kFEpiWarps + 1 + kProdWarps) * 32;       // 416
+// The single MMA-issuing thread was the critical path (ncu source view: ~10 uniform-datapath instructions of descriptor
+// arithmetic per tcgen05.mma, the warp 64 % busy issuing while every other warp waits on it).  Four warps issue disjoint
+// quarters of each plane's MMAs: the (128-row block, K-step) pairs are dealt round-robin -- different blocks own different
+// accumulators, K-steps of one block share one (every MMA accumulates into a pre-zeroed stage, so the order is free).
+constexpr int kFMmaWarps = 4;
+constexpr int kFThreads = (kFEpiWarps + kFMmaWarps + kProdWarps) * 32;   // 512
 
 template <int CIN, int NPAD, int WT, int NS, int R>
 struct FCfg {
@@ -477,10 +482,10 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) {
       mbar_init(&bar_full[i], kProdWarps);
-      mbar_init(&bar_empty[i], 1);
+      mbar_init(&bar_empty[i], kFMmaWarps);
     }
     for (int i = 0; i < R; ++i) {
-      mbar_init(&bar_tfull[i], 1);
+      mbar_init(&bar_tfull[i], kFMmaWarps);
       mbar_init(&bar_tempty[i], kFEpiWarps);
     }
     mbar_fence_init();
@@ -495,9 +500,9 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
   const uint32_t tmem_base = *s_tmem;
   const int D = p.D, H = p.H, W = p.W;
 
-  if (warp > kFMmaWarp) {
+  if (warp >= kFMmaWarp + kFMmaWarps) {
     // =================================== producers (identical to the generic kernel) ======================
-    const int pwarp = warp - (kFMmaWarp + 1);
+    const int pwarp = warp - (kFMmaWarp + kFMmaWarps);
     constexpr int PIECES_PER_ROW = C::WP * C::NCH;
     uint32_t g = 0;
     int prev_slot = -1;
@@ -542,8 +547,9 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[prev_slot]);
     }
-  } else if (warp == kFMmaWarp) {
-    // =================================== MMA issuer =======================================================
+  } else if (warp >= kFMmaWarp) {
+    // =================================== MMA issuers (kFMmaWarps warps, disjoint shares of every plane) ===
+    const int mw = warp - kFMmaWarp;
     const uint32_t wbase = smem_u32(s_w) >> 4;
     const uint32_t sbase0 = smem_u32(s_slots);
     const uint64_t adesc_hi = umma_desc_nosw(0, C::CH_STRIDE, C::WP * 16);
@@ -581,6 +587,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
                 const uint64_t bd2 = bdesc_hi | static_cast<uint64_t>((b0 + ks * 2 * C::W_ROWS + run1 * NPAD) & 0x3FFF);
 #pragma unroll
                 for (int blk = 0; blk < C::NBLK; ++blk) {
+                  if ((blk * C::KSTEPS + ks) % kFMmaWarps != mw) continue;           // this warp's share of the plane
                   if (blk < nblk) {
                     const uint64_t adesc = adesc_hi | static_cast<uint64_t>((a0 + ks * 2 * (C::CH_STRIDE >> 4) + blk * 8) & 0x3FFF);
                     const uint32_t col = tmem_base + blk * (R * NPAD);
