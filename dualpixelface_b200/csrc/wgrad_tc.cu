@@ -28,8 +28,9 @@ using namespace dpf;
 
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
+constexpr int kMmaWarps = 4;             // the rows of a tile are dealt round-robin to 4 issuing warps (see conv3d_tc.cu)
 constexpr int kProdWarps = 4;
-constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;
+constexpr int kThreads = (kEpiWarps + kMmaWarps + kProdWarps) * 32;
 constexpr int kMaxTaps = 27;
 constexpr int kWT = 16;                 // tile width (one K=16 segment per row)
 
@@ -94,9 +95,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSX; ++i) { mbar_init(&bar_xfull[i], kProdWarps); mbar_init(&bar_xempty[i], 1); }
-    for (int i = 0; i < NSZ; ++i) { mbar_init(&bar_zfull[i], kProdWarps); mbar_init(&bar_zempty[i], 1); }
-    mbar_init(bar_done, 1);
+    for (int i = 0; i < NSX; ++i) { mbar_init(&bar_xfull[i], kProdWarps); mbar_init(&bar_xempty[i], kMmaWarps); }
+    for (int i = 0; i < NSZ; ++i) { mbar_init(&bar_zfull[i], kProdWarps); mbar_init(&bar_zempty[i], kMmaWarps); }
+    mbar_init(bar_done, kMmaWarps);
     mbar_fence_init();
   }
   if (warp == kMmaWarp) {
@@ -119,9 +120,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after_sync();
 
-  if (warp > kMmaWarp) {
+  if (warp >= kMmaWarp + kMmaWarps) {
     // =================================== producers: x halo windows and dz tiles ===========================
-    const int ptid = threadIdx.x - (kMmaWarp + 1) * 32;
+    const int ptid = threadIdx.x - (kMmaWarp + kMmaWarps) * 32;
     constexpr int XPR = C::XCOLS * C::NCH, XPIECES = C::XROWS * XPR;
     constexpr int ZPR = kWT * C::ZCHUNKS, ZPIECES = C::TR * ZPR;
     uint32_t gx_base = 0, gz = 0;
@@ -206,8 +207,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         mbar_arrive(&bar_zfull[prev_z]);
       }
     }
-  } else if (warp == kMmaWarp) {
-    // =================================== MMA issuer =======================================================
+  } else if (warp >= kMmaWarp) {
+    // =================================== MMA issuers ======================================================
+    const int mw = warp - kMmaWarp;
     const uint32_t idesc = idesc_mn(64, NPAD);
     const uint64_t adesc_hi = umma_desc_nosw(0, 128, C::XCH);          // LBO = next 8 positions, SBO = next channel chunk
     const uint64_t bdesc_hi = umma_desc_nosw(0, 128, C::ZCH);
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
           const uint32_t acc = tmem_base + (static_cast<uint32_t>((t & 1) * 16) << 16) + (t >> 1) * NPAD;
           if (leader) {
 #pragma unroll 4
-            for (int row = 0; row < C::TR; ++row) {
+            for (int row = mw; row < C::TR; row += kMmaWarps) {
               const uint64_t adesc = adesc_hi | static_cast<uint64_t>((a0 + row * C::WP) & 0x3FFF);
               const uint64_t bdesc = bdesc_hi | static_cast<uint64_t>((z0 + row * kWT) & 0x3FFF);
               umma_bf16(acc, adesc, bdesc, idesc, true);
