@@ -130,9 +130,23 @@ class _StereoBase(LightningModule):
             if m is not self and hasattr(m, "refresh"):
                 m.refresh()
 
+    @staticmethod
+    def convert_checkpoint_keys(state_dict):
+        """Key layout of the released checkpoints (README.md:95-101 of the reference) -> this torch / torchvision:
+        * `normal_estimator.grid` is registered lazily by the reference (normal_module.py:91-99) and rebuilt here;
+        * torchvision <= 0.14 FeaturePyramidNetwork stored plain convs (`fpn.inner_blocks.N.weight`), current torchvision wraps
+          them in Conv2dNormActivation (`fpn.inner_blocks.N.0.weight`)."""
+        import re
+        out = {}
+        for k, v in state_dict.items():
+            if k.endswith("normal_estimator.grid"):
+                continue
+            k = re.sub(r"(\.fpn\.(?:inner|layer)_blocks\.\d+)\.(weight|bias)$", r"\1.0.\2", k)
+            out[k] = v
+        return out
+
     def load_state_dict(self, state_dict, strict=True, **kw):
-        sd = dict(state_dict)
-        sd.pop("normal_estimator.grid", None)       # lazily registered by the reference (normal_module.py:91-99)
+        sd = self.convert_checkpoint_keys(state_dict)
         out = super().load_state_dict(sd, strict=strict, **kw)
         self.refresh()
         return out

@@ -143,3 +143,13 @@ def test_losses_match_oracle_on_partial_mask():
     b = {"disp": disp, "mask": mask, "normal": nrm}
     assert abs(float(losses.smooth_l1(pred, b, (1.0, 0.7, 0.5))) - float(O.smooth_l1_multi(pred, disp, mask, (1.0, 0.7, 0.5)))) < 1e-5
     assert abs(float(losses.cosine(pn, b)) - float(O.cosine_normal_loss(pn, nrm, mask))) < 1e-5
+
+
+def test_checkpoint_key_conversion():
+    """Released checkpoints: lazily-registered ANM grid dropped, torchvision-0.6 FPN key names mapped to the current ones."""
+    from dualpixelface_b200.models import _StereoBase
+    old = {"feature_extraction.fpn.inner_blocks.1.weight": 1, "feature_extraction.fpn.layer_blocks.2.bias": 2,
+           "feature_extraction.fpn.inner_blocks.0.0.weight": 3, "normal_estimator.grid": 4, "aggregation.dres0.0.0.weight": 5}
+    new = _StereoBase.convert_checkpoint_keys(old)
+    assert new == {"feature_extraction.fpn.inner_blocks.1.0.weight": 1, "feature_extraction.fpn.layer_blocks.2.0.bias": 2,
+                   "feature_extraction.fpn.inner_blocks.0.0.weight": 3, "aggregation.dres0.0.0.weight": 5}
