@@ -336,7 +336,7 @@ def run_ours(args):
         # achieved = algorithmic FLOPs per launch / average launch duration, CUDA events around the single launches
         "roofline": {"kernel": "conv3d_kdfused_kernel<32,32> (3x3x3 stride-1 conv, 32->32 channels)", "bound": "tensor",
                      "achieved": dom["achieved"], "peak": peaks["tf"], "unit": "TFLOP/s", "frac": dom["achieved"] / peaks["tf"],
-                     "traffic": 437.1e6, "traffic_source": "ncu --set full, dram__bytes_read+write per launch "
+                     "traffic": 439.2e6, "traffic_source": "ncu --set full, dram__bytes_read+write per launch "
                      "(profiles/r01_conv_kdfused_32x32.txt; algorithmic 481.7 MB)", "peak_source": peaks["src"],
                      "flops_per_launch": dom["work_per_launch"], "avg_launch_ms": dom["avg_launch_ms"],
                      "launches_per_step": dom["launches_per_step"]},

@@ -42,5 +42,5 @@ def full(rep, tag):
 if __name__ == "__main__":
     # bench.py --steps 2 --warmup 1 runs 3 warm-up + 2 timed + 2 stage + 2 per-kernel + 2+2 e2e passes = 13 model passes
     launch_list("gpurun_out/r01_launches_bench.csv", 13, "r01_bench")
-    for t in ("r01_conv_kdfused_32x32", "r01_conv_kdfused_64x32", "r01_dcn3d", "r01_dcn3d_bwd_data"):
+    for t in ("r01_conv_kdfused_32x32", "r01_conv_kdfused_64x32", "r01_dcn3d", "r01_dcn3d_bwd_data", "r01_wgrad_32x32"):
         full(f"gpurun_out/{t}.ncu-rep", t)
