@@ -27,7 +27,10 @@ constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;   // 672
 constexpr int kVoxPerPass = kProdWarps * 32 / 4;              // 4 threads (32 bytes = two channel chunks each) per voxel
 constexpr int kNOut = 64;
 constexpr int kBlocks = 2;                                    // GEMM blocks (128 voxels each) per work unit
-constexpr int kStages = 3;
+#ifndef DPF_DCN_STAGES
+#define DPF_DCN_STAGES 3
+#endif
+constexpr int kStages = DPF_DCN_STAGES;
 constexpr int kTaps = 27;
 
 struct DcnParams {

@@ -30,6 +30,13 @@ def _conv(x, f):
     return F.conv2d(x, f["w"], None, f["stride"], f["pad"], f["dil"], f["groups"])
 
 
+def _conv_bias_relu(x, f):
+    """conv + bias + ReLU as ONE cuDNN fused op (no separate tail pass); used where the activation is a plain ReLU."""
+    if "b16" not in f:
+        f["b16"] = f["b"].to(torch.bfloat16)
+    return torch.cudnn_convolution_relu(x, f["w"], f["b16"], f["stride"], f["pad"], f["dil"], f["groups"])
+
+
 def _slope(m) -> float:
     if isinstance(m, nn.PReLU):
         assert m.weight.numel() == 1
@@ -81,7 +88,7 @@ class FusedSDPEncoder:
         from collections import OrderedDict
         x = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         for f in self.first:
-            x = ops.bias_act(_conv(x, f), f["b"], 0.0)
+            x = _conv_bias_relu(x, f)
         o1 = self.block1(x)
         o2 = o1
         for b in self.inter1:
@@ -95,5 +102,5 @@ class FusedSDPEncoder:
         up = lambda t, s: F.interpolate(t, scale_factor=s, mode="bilinear", align_corners=True)
         y = torch.cat([f["layer1"], up(f["layer2"], 2), up(f["layer3"], 4)], 1).contiguous(memory_format=torch.channels_last)
         for fl in self.last:
-            y = ops.bias_act(_conv(y, fl), fl["b"], 0.0)
+            y = _conv_bias_relu(y, fl)
         return y
