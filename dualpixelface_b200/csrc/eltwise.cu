@@ -110,3 +110,74 @@ extern "C" int dpf_anm_tail(const void* x, float* out, int B, int K, int H4, int
   anm_tail_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, K, H4, W4);
   return dpf::after_launch("dpf_anm_tail");
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Feature-pyramid tail of the StereoDPNet encoder (src/model/stereodpnet/modules.py:128-133 of the reference):
+//   cat([f1, bilinear_x2(f2), bilinear_x4(f3)], channel)  with align_corners=True, channels-last bf16.
+// One pass writes the [N,h,w,3C] tensor directly (PyTorch: two upsample kernels, a cat and a layout copy).
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ void bilerp8(const __nv_bfloat16* __restrict__ src, int n, int hs, int ws, int C, int y, int x, int h,
+                                        int w, int c0, float (&f)[8]) {
+  const float sy = (h > 1) ? static_cast<float>(hs - 1) / static_cast<float>(h - 1) * static_cast<float>(y) : 0.f;
+  const float sx = (w > 1) ? static_cast<float>(ws - 1) / static_cast<float>(w - 1) * static_cast<float>(x) : 0.f;
+  const int y0 = min(static_cast<int>(sy), hs - 1), x0 = min(static_cast<int>(sx), ws - 1);
+  const int y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
+  const float ly = sy - static_cast<float>(y0), lx = sx - static_cast<float>(x0);
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const __nv_bfloat16* base = src + static_cast<size_t>(n) * hs * ws * C + c0;
+  const uint4 a = dpf::ld_nc_v4(base + (static_cast<size_t>(y0) * ws + x0) * C);
+  const uint4 b = dpf::ld_nc_v4(base + (static_cast<size_t>(y0) * ws + x1) * C);
+  const uint4 c = dpf::ld_nc_v4(base + (static_cast<size_t>(y1) * ws + x0) * C);
+  const uint4 d = dpf::ld_nc_v4(base + (static_cast<size_t>(y1) * ws + x1) * C);
+  const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w}, uc[4] = {c.x, c.y, c.z, c.w}, ud[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f[2 * k] = w00 * dpf::bf16_lo(ua[k]) + w01 * dpf::bf16_lo(ub[k]) + w10 * dpf::bf16_lo(uc[k]) + w11 * dpf::bf16_lo(ud[k]);
+    f[2 * k + 1] = w00 * dpf::bf16_hi(ua[k]) + w01 * dpf::bf16_hi(ub[k]) + w10 * dpf::bf16_hi(uc[k]) + w11 * dpf::bf16_hi(ud[k]);
+  }
+}
+
+__global__ void __launch_bounds__(256) pyramid_cat_kernel(const __nv_bfloat16* __restrict__ f1, const __nv_bfloat16* __restrict__ f2,
+                                                          const __nv_bfloat16* __restrict__ f3, __nv_bfloat16* __restrict__ out,
+                                                          int N, int h, int w, int h2, int w2, int h3, int w3, int C) {
+  const int c8n = C >> 3;
+  const long long total = static_cast<long long>(N) * h * w * 3 * c8n;
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < total;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int piece = static_cast<int>(q % (3 * c8n));
+    long long t = q / (3 * c8n);
+    const int x = static_cast<int>(t % w);
+    t /= w;
+    const int y = static_cast<int>(t % h);
+    const int n = static_cast<int>(t / h);
+    const int lvl = piece / c8n, c0 = (piece % c8n) * 8;
+    uint4 o;
+    if (lvl == 0) {
+      o = dpf::ld_nc_v4(f1 + ((static_cast<size_t>(n) * h + y) * w + x) * C + c0);
+    } else {
+      float f[8];
+      if (lvl == 1) bilerp8(f2, n, h2, w2, C, y, x, h, w, c0, f);
+      else bilerp8(f3, n, h3, w3, C, y, x, h, w, c0, f);
+      o.x = dpf::pack_bf16x2(f[0], f[1]); o.y = dpf::pack_bf16x2(f[2], f[3]);
+      o.z = dpf::pack_bf16x2(f[4], f[5]); o.w = dpf::pack_bf16x2(f[6], f[7]);
+    }
+    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * h + y) * w + x) * (3 * C) + lvl * C + c0) = o;
+  }
+}
+
+}  // namespace
+
+extern "C" int dpf_pyramid_cat(const void* f1, const void* f2, const void* f3, void* out, int N, int h, int w, int h2, int w2,
+                               int h3, int w3, int C, void* stream) {
+  DPF_REQUIRE(f1 && f2 && f3 && out, "dpf_pyramid_cat: null pointer");
+  DPF_REQUIRE(DPF_ALIGNED16(f1) && DPF_ALIGNED16(f2) && DPF_ALIGNED16(f3) && DPF_ALIGNED16(out), "dpf_pyramid_cat: pointers must be 16-byte aligned");
+  DPF_REQUIRE(N > 0 && h > 0 && w > 0 && h2 > 0 && w2 > 0 && h3 > 0 && w3 > 0 && C >= 8 && C % 8 == 0, "dpf_pyramid_cat: bad shape");
+  const long long total = static_cast<long long>(N) * h * w * 3 * (C / 8);
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(dpf::sm_count()) * 16));
+  pyramid_cat_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(f1), reinterpret_cast<const __nv_bfloat16*>(f2), reinterpret_cast<const __nv_bfloat16*>(f3),
+      reinterpret_cast<__nv_bfloat16*>(out), N, h, w, h2, w2, h3, w3, C);
+  return dpf::after_launch("dpf_pyramid_cat");
+}

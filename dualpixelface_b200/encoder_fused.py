@@ -37,6 +37,20 @@ def _conv_bias_relu(x, f):
     return torch.cudnn_convolution_relu(x, f["w"], f["b16"], f["stride"], f["pad"], f["dil"], f["groups"])
 
 
+def pyramid_cat(f1, f2, f3):
+    """cat([f1, bilinear x2 (f2), bilinear x4 (f3)], 1) with align_corners=True (modules.py:128-133 of the reference); inputs
+    and output are NCHW views of channels-last bf16 memory."""
+    from . import _lib
+    n, c, h, w = f1.shape
+    a, b, d = (t.permute(0, 2, 3, 1).contiguous() for t in (f1, f2, f3))
+    for t in (a, b, d):
+        ops._req(t, torch.bfloat16, "pyramid level")
+    out = torch.empty(n, h, w, 3 * c, device=f1.device, dtype=torch.bfloat16)
+    _lib.check(ops.lib().dpf_pyramid_cat(ops._p(a), ops._p(b), ops._p(d), ops._p(out), n, h, w, b.shape[1], b.shape[2], d.shape[1],
+                                         d.shape[2], c, ops._stream()), "dpf_pyramid_cat")
+    return out.permute(0, 3, 1, 2)
+
+
 def _slope(m) -> float:
     if isinstance(m, nn.PReLU):
         assert m.weight.numel() == 1
@@ -99,8 +113,7 @@ class FusedSDPEncoder:
             o3 = b(o3)
         o3 = self.block3(o3)
         f = self.fpn(OrderedDict(layer1=o1, layer2=o2, layer3=o3))
-        up = lambda t, s: F.interpolate(t, scale_factor=s, mode="bilinear", align_corners=True)
-        y = torch.cat([f["layer1"], up(f["layer2"], 2), up(f["layer3"], 4)], 1).contiguous(memory_format=torch.channels_last)
+        y = pyramid_cat(f["layer1"], f["layer2"], f["layer3"])       # upsample x2 / x4 + concat in one pass
         for fl in self.last:
             y = _conv_bias_relu(y, fl)
         return y

@@ -81,11 +81,14 @@ class _StereoBase(LightningModule):
                 ft = self.feature_extraction(tgt_img.float().contiguous(memory_format=cl))
             to_cl = lambda t: t.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
             return to_cl(fr), to_cl(ft)
-        x = torch.cat([ref_img, tgt_img], 0)
         if self.encoder_autocast:
-            f = self._fused_encoder()(x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+            # both views go straight into one bf16 channels-last batch (one conversion pass each, no fp32 cat)
+            x = torch.empty(2 * b, *ref_img.shape[1:], device=ref_img.device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            x[:b].copy_(ref_img)
+            x[b:].copy_(tgt_img)
+            f = self._fused_encoder()(x)
         else:
-            f = self.feature_extraction(x.float())
+            f = self.feature_extraction(torch.cat([ref_img, tgt_img], 0).float())
         f = f.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()      # [2B,H4,W4,C] channels-last bf16
         return f[:b], f[b:]
 
@@ -118,7 +121,7 @@ class _StereoBase(LightningModule):
         results = {"pred_depth": torch.stack(cost_f, 1),
                    "prob_depth": torch.stack(cost_p, 1) if cost_p[0] is not None else None,
                    "pred_normal": normal,
-                   "ref_feature": ref_fea.float().max(-1)[0]}
+                   "ref_feature": ref_fea.amax(-1).float()}
         if self.training and "disp" in batch:
             results.update(self.loss_model.forward(results, batch))
         return results

@@ -176,6 +176,11 @@ int dpf_anm_gather_bwd(const float* dfv_f32, const void* dfv_bf16, const int* id
 int dpf_bias_act(const void* x, const float* bias, const void* res, void* y, long long npix, int C, int y_cstride,
                  int y_coff, float slope, void* stream);
 
+/* Feature-pyramid tail of the StereoDPNet encoder (src/model/stereodpnet/modules.py:128-133): one pass writes
+ * out[N,h,w,3C] = cat(f1[N,h,w,C], bilinear(f2[N,h2,w2,C]), bilinear(f3[N,h3,w3,C])), align_corners=True, bf16 channels-last. */
+int dpf_pyramid_cat(const void* f1, const void* f2, const void* f3, void* out, int N, int h, int w, int h2, int w2, int h3,
+                    int w3, int C, void* stream);
+
 /* ANM tail: bilinear x4 upsample (align_corners) -> sigmoid -> mean over K -> *2-1 in one pass.  Replaces final_layer and
  * the mean / rescale of ANM.forward (src/model/stereodpnet/normal_module.py:69-72,185-190).
  * x [B*K,H4,W4,3] bf16 (channels-last) -> out [B,3,4*H4,4*W4] fp32. */

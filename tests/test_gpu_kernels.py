@@ -270,3 +270,17 @@ def test_dcn3d(ops, cin):
                     torch.ones(64).cuda(), bias.cuda(), relu=True)
     torch.cuda.synchronize()
     assert rel_err(from_ndhwc(got), want) < 2e-2        # the gathered A tile is rounded to bf16 before the MMA
+
+
+def test_pyramid_cat_matches_interpolate():
+    """dpf_pyramid_cat == cat([f1, bilinear x2, bilinear x4]) with align_corners=True (bf16 rounding of the fp32 blend)."""
+    from dualpixelface_b200.encoder_fused import pyramid_cat
+    g = torch.Generator().manual_seed(61)
+    f1, f2, f3 = (torch.randn(2, 32, 20 // s, 28 // s, generator=g).to(torch.bfloat16) for s in (1, 2, 4))
+    up = lambda t, s: F.interpolate(t.float(), scale_factor=s, mode="bilinear", align_corners=True)
+    want = torch.cat([f1.float(), up(f2, 2), up(f3, 4)], 1)
+    cl = lambda t: t.cuda().contiguous(memory_format=torch.channels_last)
+    got = pyramid_cat(cl(f1), cl(f2), cl(f3)).float().cpu()
+    assert got.shape == want.shape
+    assert torch.equal(got[:, :32], f1.float())
+    assert (got - want).abs().max().item() < 2e-2
