@@ -181,3 +181,64 @@ extern "C" int dpf_pyramid_cat(const void* f1, const void* f2, const void* f3, v
       reinterpret_cast<__nv_bfloat16*>(out), N, h, w, h2, w2, h3, w3, C);
   return dpf::after_launch("dpf_pyramid_cat");
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// FPN top-down merge (torchvision.ops.FeaturePyramidNetwork.forward as used by src/model/stereodpnet/modules.py:83,124):
+//   y[n, p, c] = x[n, p, c] + bias[c] + top[n, nearest(p), c]      (lateral 1x1 conv output + bias + nearest-upsampled coarser level)
+// one pass instead of aten::add_ (bias), upsample_nearest2d and aten::add.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) fpn_merge_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ bias,
+                                                        const __nv_bfloat16* __restrict__ top, __nv_bfloat16* __restrict__ y, int N,
+                                                        int h, int w, int ht, int wt, int C) {
+  const int c8n = C >> 3;
+  const long long total = static_cast<long long>(N) * h * w * c8n;
+  const float sy = static_cast<float>(ht) / static_cast<float>(h), sx = static_cast<float>(wt) / static_cast<float>(w);
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < total;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(q % c8n) * 8;
+    long long t = q / c8n;
+    const int px = static_cast<int>(t % w);
+    t /= w;
+    const int py = static_cast<int>(t % h);
+    const int n = static_cast<int>(t / h);
+    const int ty = min(static_cast<int>(floorf(static_cast<float>(py) * sy)), ht - 1);
+    const int tx = min(static_cast<int>(floorf(static_cast<float>(px) * sx)), wt - 1);
+    const size_t o = ((static_cast<size_t>(n) * h + py) * w + px) * C + c0;
+    const uint4 u = dpf::ld_nc_v4(x + o);
+    const uint4 r = dpf::ld_nc_v4(top + ((static_cast<size_t>(n) * ht + ty) * wt + tx) * C + c0);
+    float f[8] = {dpf::bf16_lo(u.x), dpf::bf16_hi(u.x), dpf::bf16_lo(u.y), dpf::bf16_hi(u.y),
+                  dpf::bf16_lo(u.z), dpf::bf16_hi(u.z), dpf::bf16_lo(u.w), dpf::bf16_hi(u.w)};
+    if (bias != nullptr) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+      f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+    }
+    // the lateral (x + bias) is rounded to bf16 first, like the conv output of the PyTorch module it replaces
+    uint4 l;
+    l.x = dpf::pack_bf16x2(f[0], f[1]); l.y = dpf::pack_bf16x2(f[2], f[3]); l.z = dpf::pack_bf16x2(f[4], f[5]); l.w = dpf::pack_bf16x2(f[6], f[7]);
+    uint4 out;
+    out.x = dpf::pack_bf16x2(dpf::bf16_lo(l.x) + dpf::bf16_lo(r.x), dpf::bf16_hi(l.x) + dpf::bf16_hi(r.x));
+    out.y = dpf::pack_bf16x2(dpf::bf16_lo(l.y) + dpf::bf16_lo(r.y), dpf::bf16_hi(l.y) + dpf::bf16_hi(r.y));
+    out.z = dpf::pack_bf16x2(dpf::bf16_lo(l.z) + dpf::bf16_lo(r.z), dpf::bf16_hi(l.z) + dpf::bf16_hi(r.z));
+    out.w = dpf::pack_bf16x2(dpf::bf16_lo(l.w) + dpf::bf16_lo(r.w), dpf::bf16_hi(l.w) + dpf::bf16_hi(r.w));
+    *reinterpret_cast<uint4*>(y + o) = out;
+  }
+}
+
+}  // namespace
+
+extern "C" int dpf_fpn_merge(const void* x, const float* bias, const void* top, void* y, int N, int h, int w, int ht, int wt, int C,
+                             void* stream) {
+  DPF_REQUIRE(x && top && y, "dpf_fpn_merge: null pointer");
+  DPF_REQUIRE(DPF_ALIGNED16(x) && DPF_ALIGNED16(top) && DPF_ALIGNED16(y) && (bias == nullptr || DPF_ALIGNED16(bias)),
+              "dpf_fpn_merge: pointers must be 16-byte aligned");
+  DPF_REQUIRE(N > 0 && h > 0 && w > 0 && ht > 0 && wt > 0 && C >= 8 && C % 8 == 0, "dpf_fpn_merge: bad shape");
+  const long long total = static_cast<long long>(N) * h * w * (C / 8);
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(dpf::sm_count()) * 16));
+  fpn_merge_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), bias, reinterpret_cast<const __nv_bfloat16*>(top), reinterpret_cast<__nv_bfloat16*>(y),
+      N, h, w, ht, wt, C);
+  return dpf::after_launch("dpf_fpn_merge");
+}

@@ -84,6 +84,35 @@ class _Block:
         return ops.bias_act(_conv(x, self.skip), self.skip["b"], 1.0, res=v)                         # + weighted skip
 
 
+def fpn_merge(lateral, bias, top):
+    """lateral + bias + nearest-upsampled top (one pass, dpf_fpn_merge); NCHW views of channels-last bf16 memory."""
+    from . import _lib
+    n, c, h, w = lateral.shape
+    a, t = lateral.permute(0, 2, 3, 1).contiguous(), top.permute(0, 2, 3, 1).contiguous()
+    ops._req(a, torch.bfloat16, "lateral"); ops._req(t, torch.bfloat16, "top")
+    out = torch.empty_like(a)
+    _lib.check(ops.lib().dpf_fpn_merge(ops._p(a), ops._p(bias), ops._p(t), ops._p(out), n, h, w, t.shape[1], t.shape[2], c,
+                                       ops._stream()), "dpf_fpn_merge")
+    return out.permute(0, 3, 1, 2)
+
+
+class _FPN:
+    """torchvision.ops.FeaturePyramidNetwork.forward (no extra blocks) over folded bf16 convs: lateral 1x1 convs, top-down
+    nearest-upsample + add fused with the lateral bias (dpf_fpn_merge), 3x3 output convs."""
+
+    def __init__(self, fpn):
+        self.inner = [_fold(b[0], None) for b in fpn.inner_blocks]
+        self.layer = [_fold(b[0], None) for b in fpn.layer_blocks]
+
+    def __call__(self, feats):
+        last = ops.bias_act(_conv(feats[-1], self.inner[-1]), self.inner[-1]["b"], 1.0)
+        outs = [ops.bias_act(_conv(last, self.layer[-1]), self.layer[-1]["b"], 1.0)]
+        for i in range(len(feats) - 2, -1, -1):
+            last = fpn_merge(_conv(feats[i], self.inner[i]), self.inner[i]["b"], last)
+            outs.insert(0, ops.bias_act(_conv(last, self.layer[i]), self.layer[i]["b"], 1.0))
+        return outs
+
+
 class FusedSDPEncoder:
     def __init__(self, enc):
         fc = enc.firstconv
@@ -93,13 +122,11 @@ class FusedSDPEncoder:
         self.block2 = _Block(enc.block2)
         self.inter2 = [_Block(b) for b in enc.interblock2]
         self.block3 = _Block(enc.block3)
-        import copy
-        self.fpn = copy.deepcopy(enc.fpn).eval().to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        self.fpn = _FPN(enc.fpn)
         self.last = [_fold(enc.lastconv[i][0], enc.lastconv[i][1]) for i in (0, 2)]
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         """x [N,3,H,W] -> features [N,C,H/4,W/4] bf16, channels-last memory format."""
-        from collections import OrderedDict
         x = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         for f in self.first:
             x = _conv_bias_relu(x, f)
@@ -112,8 +139,8 @@ class FusedSDPEncoder:
         for b in self.inter2:
             o3 = b(o3)
         o3 = self.block3(o3)
-        f = self.fpn(OrderedDict(layer1=o1, layer2=o2, layer3=o3))
-        y = pyramid_cat(f["layer1"], f["layer2"], f["layer3"])       # upsample x2 / x4 + concat in one pass
+        f1, f2, f3 = self.fpn([o1, o2, o3])
+        y = pyramid_cat(f1, f2, f3)                                  # upsample x2 / x4 + concat in one pass
         for fl in self.last:
             y = _conv_bias_relu(y, fl)
         return y

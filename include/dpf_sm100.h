@@ -180,6 +180,10 @@ int dpf_bias_act(const void* x, const float* bias, const void* res, void* y, lon
  * out[N,h,w,3C] = cat(f1[N,h,w,C], bilinear(f2[N,h2,w2,C]), bilinear(f3[N,h3,w3,C])), align_corners=True, bf16 channels-last. */
 int dpf_pyramid_cat(const void* f1, const void* f2, const void* f3, void* out, int N, int h, int w, int h2, int w2, int h3,
                     int w3, int C, void* stream);
+/* FPN top-down merge (torchvision FeaturePyramidNetwork.forward, used at src/model/stereodpnet/modules.py:83,124):
+ * y[N,h,w,C] = x + bias + nearest_upsample(top[N,ht,wt,C]); bf16 channels-last, one pass. */
+int dpf_fpn_merge(const void* x, const float* bias, const void* top, void* y, int N, int h, int w, int ht, int wt, int C,
+                  void* stream);
 
 /* ANM tail: bilinear x4 upsample (align_corners) -> sigmoid -> mean over K -> *2-1 in one pass.  Replaces final_layer and
  * the mean / rescale of ANM.forward (src/model/stereodpnet/normal_module.py:69-72,185-190).

@@ -284,3 +284,16 @@ def test_pyramid_cat_matches_interpolate():
     assert got.shape == want.shape
     assert torch.equal(got[:, :32], f1.float())
     assert (got - want).abs().max().item() < 2e-2
+
+
+def test_fpn_merge_matches_torch():
+    """dpf_fpn_merge == (lateral + bias) + F.interpolate(top, size, 'nearest'), bf16."""
+    from dualpixelface_b200.encoder_fused import fpn_merge
+    g = torch.Generator().manual_seed(62)
+    lat = torch.randn(2, 32, 18, 26, generator=g).to(torch.bfloat16)
+    top = torch.randn(2, 32, 9, 13, generator=g).to(torch.bfloat16)
+    bias = torch.randn(32, generator=g)
+    want = ((lat.float() + bias.view(1, -1, 1, 1)).to(torch.bfloat16).float() + F.interpolate(top.float(), size=(18, 26), mode="nearest")).to(torch.bfloat16)
+    cl = lambda t: t.cuda().contiguous(memory_format=torch.channels_last)
+    got = fpn_merge(cl(lat), bias.cuda(), cl(top)).cpu()
+    assert torch.equal(got, want)
