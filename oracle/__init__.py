@@ -13,8 +13,10 @@ reference's own code imported from ``/root/reference`` through the shim layer
 in ``tests/golden/ref_shim.py``; the fixtures and the generating script are
 committed under ``tests/golden/``.  The one piece that cannot be executed in
 the build container is the reference's compiled 3-D deformable convolution
-(CUDA only, no CPU path): for it the oracle restates
-``src/module/dcn3d/src/cuda/deform_im2col_cuda.cuh`` and that restatement is
-"parity unpinned" against the compiled op (it is pinned against an
-independent dense-conv identity and autograd instead).
+(CUDA only, no CPU path): the oracle restates
+``src/module/dcn3d/src/cuda/deform_im2col_cuda.cuh``; that restatement is pinned
+on the GPU box against the reference's own CUDA kernels, compiled from the
+unmodified sources into the git-ignored ``oracle/_ref/DCN.so`` by
+``oracle/build_ref_dcn.py`` (``tests/test_gpu_dcn_reference.py``: forward and all
+four gradients within 1e-4).
 """

@@ -8,7 +8,14 @@ so the same seeded synthetic weights can be fed to the reference (golden
 generation), to this oracle and to the CUDA product.
 
 Nothing here touches CUDA; everything runs on whatever device its inputs are on
-(CPU in the tests and in the bench's cpu_baseline leg).
+(CPU in the tests and in the bench's cpu_baseline leg; tests/test_gpu_fullsize.py also
+executes it on GPU tensors as the full-size checker).
+
+Parity pins: bit-exact against the unmodified reference code run through
+tests/golden/ref_shim.py (tests/test_oracle_golden.py, committed fixtures under
+tests/golden/); the 3-D deformable convolution, which the reference only implements
+in CUDA, against the reference's own kernels built into oracle/_ref/DCN.so by
+oracle/build_ref_dcn.py (tests/test_gpu_dcn_reference.py).
 """
 from __future__ import annotations
 

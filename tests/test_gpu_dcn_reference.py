@@ -1,0 +1,83 @@
+"""Pins the 3-D deformable convolution against the REFERENCE'S OWN CUDA kernels (oracle/_ref/DCN.so, built from the unmodified
+sources under /root/reference/src/module/dcn3d/src by oracle/build_ref_dcn.py):
+
+  * the oracle's restatement (oracle.dpf_oracle.deform_conv3d + autograd) == DCN.deform_conv_forward / deform_conv_backward
+    in fp32 -- this is what removes the 'parity unpinned' caveat of the D3D restatement;
+  * the sm_100a kernels (dpf_dcn3d_fwd / _bwd_data / _bwd_weight) == the reference kernels within the bf16 tolerance.
+"""
+import importlib.machinery
+import importlib.util
+
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import dpf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REF_SO = ROOT / "oracle" / "_ref" / "DCN.so"
+ARGS = (3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1)     # kernel, stride, pad, dilation, group, deformable_group, im2col_step
+
+
+@pytest.fixture(scope="module")
+def dcn():
+    if not REF_SO.is_file():
+        pytest.skip("oracle/_ref/DCN.so not built (python oracle/build_ref_dcn.py needs /root/reference)")
+    loader = importlib.machinery.ExtensionFileLoader("DCN", str(REF_SO))
+    mod = importlib.util.module_from_spec(importlib.util.spec_from_loader("DCN", loader))
+    loader.exec_module(mod)
+    return mod
+
+
+def rel_l2(got, want):
+    got, want = got.float().cpu(), want.float().cpu()
+    return float((got - want).norm() / want.norm().clamp_min(1e-12))
+
+
+def case(cin, shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    b, d, h, w = shape
+    x = torch.randn(b, cin, d, h, w, generator=g).to(torch.bfloat16).float()
+    off = (torch.rand(b, 81, d, h, w, generator=g) - 0.5) * 3.0
+    wt = (torch.randn(64, cin, 3, 3, 3, generator=g) * (2.0 / (cin * 27)) ** 0.5).to(torch.bfloat16).float()
+    bias = torch.randn(64, generator=g) * 0.1
+    dy = torch.randn(b, 64, d, h, w, generator=g).to(torch.bfloat16).float()
+    return x, off, wt, bias, dy
+
+
+@pytest.mark.parametrize("cin,shape", [(35, (2, 4, 10, 13)), (64, (1, 3, 17, 20))])
+def test_oracle_restatement_matches_reference_kernels(dcn, cin, shape):
+    x, off, wt, bias, dy = case(cin, shape, 31)
+    xc, oc, wc, bc, dc = (t.cuda().contiguous() for t in (x, off, wt, bias, dy))
+    ref_y = dcn.deform_conv_forward(xc, wc, bc, oc, *ARGS)
+    ref_dx, ref_doff, ref_dw, ref_db = dcn.deform_conv_backward(xc, wc, bc, oc, dc, *ARGS)
+    xo, oo, wo, bo = (t.clone().requires_grad_(True) for t in (x, off, wt, bias))
+    y = O.deform_conv3d(xo, oo, wo, bo)
+    y.backward(dy)
+    assert (ref_y.cpu() - y.detach()).abs().max().item() < 1e-4
+    assert rel_l2(ref_dx, xo.grad) < 1e-4 and rel_l2(ref_doff, oo.grad) < 1e-4
+    assert rel_l2(ref_dw, wo.grad) < 1e-4 and rel_l2(ref_db, bo.grad) < 1e-4
+
+
+@pytest.mark.parametrize("cin,shape", [(35, (2, 4, 10, 13)), (64, (1, 3, 17, 20))])
+def test_sm100_kernels_match_reference_kernels(dcn, cin, shape):
+    from dualpixelface_b200 import ops
+    from dualpixelface_b200.ops_dcn_bwd import dcn3d_bwd_data, dcn3d_bwd_weight
+    x, off, wt, bias, dy = case(cin, shape, 32)
+    xc, oc, wc, bc, dc = (t.cuda().contiguous() for t in (x, off, wt, bias, dy))
+    ref_y = dcn.deform_conv_forward(xc, wc, bc, oc, *ARGS)
+    ref_dx, ref_doff, ref_dw, _ = dcn.deform_conv_backward(xc, wc, bc, oc, dc, *ARGS)
+    b, d, h, w = shape
+    xp = torch.zeros(b, d, h, w, 64, dtype=torch.bfloat16, device="cuda")
+    xp[..., :cin] = xc.permute(0, 2, 3, 4, 1)
+    offp = oc.permute(0, 2, 3, 4, 1).contiguous()
+    dyp = dc.permute(0, 2, 3, 4, 1).to(torch.bfloat16).contiguous()
+    got_y = ops.dcn3d(xp, offp, ops.pack_conv_weight(wc, cin_pad=64), 64, torch.ones(64, device="cuda"), bc)
+    dx, doff = dcn3d_bwd_data(xp, offp, dyp, wc)
+    dw = dcn3d_bwd_weight(xp, offp, dyp, cin)
+    torch.cuda.synchronize()
+    assert rel_l2(got_y.permute(0, 4, 1, 2, 3), ref_y) < 2e-2           # sampled tile rounded to bf16 before the MMA
+    assert rel_l2(dx[..., :cin].permute(0, 4, 1, 2, 3), ref_dx) < 1e-2
+    assert rel_l2(doff.permute(0, 4, 1, 2, 3), ref_doff) < 1e-2
+    assert rel_l2(dw, ref_dw) < 1e-2
