@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
     const int m = warp * 32 + lane;
     const int hrow = m >> 3, wcol = m & 7;
     constexpr int OS = (GEO == GEO_T2) ? 2 : 1;                  // output stride of the GEMM-row grid
+    constexpr bool kPrefetch = (GEO == GEO_T2) && (C::NBLK == 1) && (NPAD == 32);
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int tw = tile % p.tiles_w;
       const int th = (tile / p.tiles_w) % p.tiles_h;
@@ -296,9 +297,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       const int mh = th * 16 + hrow;
       for (int item = 0; item < p.items; ++item, ++it) {
         const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+        // Transposed kind: a lane's 8 residual chunks (4 parity classes x 2 channel chunks) do not depend on the MMAs, so they
+        // are requested BEFORE waiting for the accumulators; fetching them one by one inside the loop below (8 dependent
+        // ~600-cycle round trips per work item on only four epilogue warps) was longer than the item's MMA phase.
+        uint4 rr[kPrefetch ? 8 : 1][2];
+        const bool use_pref = kPrefetch && p.residual != nullptr && !p.y_f32 && p.cout == NPAD && (((p.y_cstride | p.y_coff) & 15) == 0);
+        if (kPrefetch && use_pref) {
+#pragma unroll
+          for (int cls = 0; cls < C::NCLS; ++cls) {
+            const int oh = mh * OS + (cls >> 1), mw = tw * WT + wcol, ow = mw * OS + (cls & 1);
+            const bool ok = (mh < p.Mh) && (mw < p.Mw) && (oh < p.Ho) && (ow < p.Wo);
+            const size_t vox = ((static_cast<size_t>(b) * p.Do + item) * p.Ho + oh) * static_cast<size_t>(p.Wo) + ow;
+            const __nv_bfloat16* ro = reinterpret_cast<const __nv_bfloat16*>(p.residual) + vox * p.y_cstride + p.y_coff;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              rr[(cls * 2 + q) % (kPrefetch ? 8 : 1)][0] = make_uint4(0u, 0u, 0u, 0u);
+              rr[(cls * 2 + q) % (kPrefetch ? 8 : 1)][1] = make_uint4(0u, 0u, 0u, 0u);
+              if (ok) ld_global_v8(ro + q * 16, rr[(cls * 2 + q) % (kPrefetch ? 8 : 1)][0], rr[(cls * 2 + q) % (kPrefetch ? 8 : 1)][1]);
+            }
+          }
+        }
         mbar_wait(&bar_tfull[as], aph);
         tc_fence_after_sync();
-#pragma unroll 1
+#pragma unroll(kPrefetch ? 4 : 1)
         for (int cls = 0; cls < C::NCLS; ++cls) {
           const int oh = mh * OS + (cls >> 1);
 #pragma unroll 1
@@ -359,7 +380,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                 if (p.residual) {
                   const __nv_bfloat16* ro = reinterpret_cast<const __nv_bfloat16*>(p.residual) + vox * p.y_cstride + p.y_coff + c0;
                   uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
-                  if (wide) ld_global_v8(ro, r0, r1);
+                  if (kPrefetch && use_pref) {
+                    r0 = rr[(cls * 2 + (c0 >> 4)) % (kPrefetch ? 8 : 1)][0];
+                    r1 = rr[(cls * 2 + (c0 >> 4)) % (kPrefetch ? 8 : 1)][1];
+                  } else if (wide) ld_global_v8(ro, r0, r1);
                   else {
                     r0 = *reinterpret_cast<const uint4*>(ro);
                     if (n > 8) r1 = *reinterpret_cast<const uint4*>(ro + 8);
