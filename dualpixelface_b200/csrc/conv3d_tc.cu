@@ -40,7 +40,12 @@ using namespace dpf;
 constexpr int kEpiWarps = 4;
 constexpr int kProdWarps = 4;
 constexpr int kMmaWarp = kEpiWarps;                                   // warp 4
-constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;          // 288
+// The taps of a work item are dealt round-robin to kGMmaWarps issuing warps: one warp walking 27 taps (tap decode + descriptor
+// arithmetic + issue) was the critical path of the stride-2 / transposed / 1x3x3 layers (ncu source view: that warp ~70 % busy,
+// every other warp waiting on it).  Different warps may accumulate into the same TMEM accumulator, so no MMA overwrites:
+// the epilogue leaves every accumulator zeroed after reading it (tcgen05.st) and all MMAs accumulate.
+constexpr int kGMmaWarps = 4;
+constexpr int kThreads = (kEpiWarps + kGMmaWarps + kProdWarps) * 32;  // 384
 constexpr int kMaxTaps = 27;
 
 enum { GEO_S1 = 0, GEO_S2 = 1, GEO_T2 = 2 };
@@ -142,10 +147,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) {
       mbar_init(&bar_full[i], kProdWarps);
-      mbar_init(&bar_empty[i], 1);
+      mbar_init(&bar_empty[i], kGMmaWarps);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_tfull[i], 1);
+      mbar_init(&bar_tfull[i], kGMmaWarps);
       mbar_init(&bar_tempty[i], kEpiWarps);
     }
     mbar_fence_init();
@@ -158,12 +163,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
+  if (warp < kEpiWarps) {                                        // all accumulators start at zero (every MMA accumulates)
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    for (int c0 = 0; c0 < C::TMEM_COLS; c0 += 16) tmem_zero16(lane_base + c0);
+    tmem_st_wait();
+    tc_fence_before_sync();
+  }
+  __syncthreads();
+  tc_fence_after_sync();
 
   const int D = p.D, H = p.H, W = p.W;
 
-  if (warp > kMmaWarp) {
+  if (warp >= kMmaWarp + kGMmaWarps) {
     // =================================== producers: global -> shared ring ===================================
-    const int pwarp = warp - (kMmaWarp + 1);                     // 0..kProdWarps-1
+    const int pwarp = warp - (kMmaWarp + kGMmaWarps);            // 0..kProdWarps-1
     constexpr int PIECES_PER_ROW = C::CWIN * C::NCH;
     uint32_t g = 0;
     int prev_slot = -1;
@@ -214,8 +227,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[prev_slot]);
     }
-  } else if (warp == kMmaWarp) {
-    // ============ MMA issuer: the whole warp runs the (warp-uniform) control flow, one elected lane issues ============
+  } else if (warp >= kMmaWarp) {
+    // ============ MMA issuers: each warp runs the (warp-uniform) control flow of its taps, one elected lane issues =====
+    const int mw = warp - kMmaWarp;
     constexpr uint32_t idesc = umma_idesc_bf16_f32(128, NPAD);
     const uint32_t wbase = smem_u32(s_w);
     const uint32_t sbase0 = smem_u32(s_slots);
@@ -234,9 +248,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         tc_fence_after_sync();
         int base, prog;
         item_planes<GEO>(item, base, prog);
-        uint32_t started = 0u;                                   // per accumulator class: has it been written yet?
         const int nt = p.ntaps[prog];
-        for (int t = 0; t < nt; ++t) {
+        for (int t = mw; t < nt; t += kGMmaWarps) {
           const Tap tp = p.taps[prog][t];
           const int pin = base + tp.dd;
           if (pin < 0 || pin >= D) continue;
@@ -250,7 +263,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           const uint32_t a0 = ((sbase0 + slot * C::SLOT_BYTES) >> 4) + tp.aoff;
           const uint32_t b0 = (wbase + tp.widx * C::W_TAP_BYTES) >> 4;
           const uint32_t acc0 = tmem_base + (as * C::NCLS + tp.cls) * C::NBLK * NPAD;
-          const bool fresh = ((started >> tp.cls) & 1u) == 0u;
           if (leader && !(p.debug & 2)) {
 #pragma unroll
             for (int ks = 0; ks < C::KSTEPS; ++ks) {
@@ -259,12 +271,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
               for (int blk = 0; blk < C::NBLK; ++blk) {
                 if (blk < nblk) {
                   const uint64_t adesc = adesc_hi | static_cast<uint64_t>((a0 + ks * 2 * (C::CH_STRIDE >> 4) + blk * 8) & 0x3FFF);
-                  umma_bf16(acc0 + blk * NPAD, adesc, bdesc, idesc, !(fresh && ks == 0));
+                  umma_bf16(acc0 + blk * NPAD, adesc, bdesc, idesc, true);
                 }
               }
             }
           }
-          started |= 1u << tp.cls;
         }
         // release the input planes that no later work item of this tile needs
         const int lo_cur = max(base + C::LO_OFF, 0);
@@ -335,6 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
               __syncwarp();                                      // tcgen05.ld is .sync.aligned: keep the warp converged
               tmem_ld16(taddr + c0, v);
               tmem_ld_wait();
+              tmem_zero16(taddr + c0);                           // leave the accumulator zeroed for its next work item
               if (!ok || c0 >= p.cout || (p.debug & 4)) continue;
               const int n = min(16, p.cout - c0);
               float f[16];
@@ -409,6 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
             }
           }
         }
+        tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_tempty[as]);
