@@ -130,3 +130,28 @@ def test_fullsize_model_vs_oracle_code_on_gpu(ops):
     print(f"full size: disparity max err {err.max():.4f} mean {err.mean():.5f}; normal max err {n_err.max():.4f} mean {n_err.mean():.5f}")
     assert err.max().item() < 2e-2 * 16.0 and err.mean().item() < 2e-3 * 16.0
     assert n_err.mean().item() < 2e-2
+
+
+@pytest.mark.parametrize("kind,cin,cout", [("s1", 32, 32), ("s1", 64, 32), ("s2", 32, 64), ("t2", 64, 32)])
+def test_fullsize_conv_random_vs_torch_fp32(ops, kind, cin, cout):
+    """Random weights at the full aggregation size against torch's fp32 convolution of the same bf16-rounded operands (TF32
+    off).  Several MMA-issuing warps accumulate into the same TMEM accumulators: a lost update would show up here as an error
+    of a whole tap's contribution (percent level), far above the bf16 output rounding (2^-9 of the value)."""
+    import torch.nn.functional as F
+    from dualpixelface_b200.layers import KIND_3x3x3, KIND_S2, KIND_T2, TCConv3d
+    shape = (2, 4, 140, 210) if kind == "t2" else (2, D, H4, W4)
+    x = _rand((*shape, cin), 11, relu=False)
+    g = torch.Generator(device="cuda").manual_seed(12)
+    xc = x.permute(0, 4, 1, 2, 3).float()
+    if kind == "t2":
+        w = (torch.randn(cin, cout, 3, 3, 3, device="cuda", generator=g) * 0.05).to(torch.bfloat16).float()
+        want = F.conv_transpose3d(xc, w, stride=2, padding=1, output_padding=1)
+        got = TCConv3d(w, KIND_T2, transposed=True)(x)
+    else:
+        w = (torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) * 0.05).to(torch.bfloat16).float()
+        want = F.conv3d(xc, w, stride=2 if kind == "s2" else 1, padding=1)
+        got = TCConv3d(w, KIND_S2 if kind == "s2" else KIND_3x3x3)(x)
+    err = (got.permute(0, 4, 1, 2, 3).float() - want).abs()
+    scale = want.abs().max().item()
+    print(f"{kind} {cin}->{cout}: max abs err {err.max().item():.4g} (output max {scale:.3g}), mean {err.mean().item():.3g}")
+    assert err.max().item() < 6e-3 * scale and err.mean().item() < 1e-3 * scale
