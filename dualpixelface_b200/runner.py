@@ -138,6 +138,8 @@ class Trainer:
                     self.grad_sync(model)
                 opts[0].step()
                 model.global_step += 1
+                logs = ", ".join(f"{k} {float(v.detach()):.4f}" for k, v in out.get("log", {}).items())
+                print(f"epoch {epoch} step {model.global_step}: loss {float(out['loss'].detach()):.4f}" + (f" ({logs})" if logs else ""))
             for s in scheds:
                 s.step()
             if self.workspace_path:
