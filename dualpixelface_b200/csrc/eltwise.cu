@@ -118,10 +118,9 @@ extern "C" int dpf_anm_tail(const void* x, float* out, int B, int K, int H4, int
 // ------------------------------------------------------------------------------------------------------------
 namespace {
 
-__device__ __forceinline__ void bilerp8(const __nv_bfloat16* __restrict__ src, int n, int hs, int ws, int C, int y, int x, int h,
-                                        int w, int c0, float (&f)[8]) {
-  const float sy = (h > 1) ? static_cast<float>(hs - 1) / static_cast<float>(h - 1) * static_cast<float>(y) : 0.f;
-  const float sx = (w > 1) ? static_cast<float>(ws - 1) / static_cast<float>(w - 1) * static_cast<float>(x) : 0.f;
+__device__ __forceinline__ void bilerp8(const __nv_bfloat16* __restrict__ src, int n, int hs, int ws, int C, int y, int x, float ry,
+                                        float rx, int c0, float (&f)[8]) {
+  const float sy = ry * static_cast<float>(y), sx = rx * static_cast<float>(x);      // align_corners=True source coordinates
   const int y0 = min(static_cast<int>(sy), hs - 1), x0 = min(static_cast<int>(sx), ws - 1);
   const int y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
   const float ly = sy - static_cast<float>(y0), lx = sx - static_cast<float>(x0);
@@ -143,6 +142,10 @@ __global__ void __launch_bounds__(256) pyramid_cat_kernel(const __nv_bfloat16* _
                                                           const __nv_bfloat16* __restrict__ f3, __nv_bfloat16* __restrict__ out,
                                                           int N, int h, int w, int h2, int w2, int h3, int w3, int C) {
   const int c8n = C >> 3;
+  const float ry2 = (h > 1) ? static_cast<float>(h2 - 1) / static_cast<float>(h - 1) : 0.f;
+  const float rx2 = (w > 1) ? static_cast<float>(w2 - 1) / static_cast<float>(w - 1) : 0.f;
+  const float ry3 = (h > 1) ? static_cast<float>(h3 - 1) / static_cast<float>(h - 1) : 0.f;
+  const float rx3 = (w > 1) ? static_cast<float>(w3 - 1) / static_cast<float>(w - 1) : 0.f;
   const long long total = static_cast<long long>(N) * h * w * 3 * c8n;
   for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < total;
        q += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -158,8 +161,8 @@ __global__ void __launch_bounds__(256) pyramid_cat_kernel(const __nv_bfloat16* _
       o = dpf::ld_nc_v4(f1 + ((static_cast<size_t>(n) * h + y) * w + x) * C + c0);
     } else {
       float f[8];
-      if (lvl == 1) bilerp8(f2, n, h2, w2, C, y, x, h, w, c0, f);
-      else bilerp8(f3, n, h3, w3, C, y, x, h, w, c0, f);
+      if (lvl == 1) bilerp8(f2, n, h2, w2, C, y, x, ry2, rx2, c0, f);
+      else bilerp8(f3, n, h3, w3, C, y, x, ry3, rx3, c0, f);
       o.x = dpf::pack_bf16x2(f[0], f[1]); o.y = dpf::pack_bf16x2(f[2], f[3]);
       o.z = dpf::pack_bf16x2(f[4], f[5]); o.w = dpf::pack_bf16x2(f[6], f[7]);
     }
