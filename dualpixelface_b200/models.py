@@ -103,6 +103,7 @@ class _StereoBase(LightningModule):
     def forward(self, batch):
         if not batch["left"].is_cuda:
             raise RuntimeError("the sm_100a hot path needs CUDA tensors; there is no CPU implementation")
+        self.check_input_size(*batch["left"].shape[-2:])
         ref_img, tgt_img = self._select_views(batch)
         self._mark("start")
         ref_fea, tgt_fea = self._features(ref_img, tgt_img)
@@ -125,6 +126,16 @@ class _StereoBase(LightningModule):
         if self.training and "disp" in batch:
             results.update(self.loss_model.forward(results, batch))
         return results
+
+    min_quarter_size = 1          # PSMNet overrides: its 64x64 average-pool branch (psmnet/modules.py:88 of the reference)
+
+    def check_input_size(self, h, w):
+        """Same constraint as the reference: two stride-2 stages at quarter resolution followed by
+        output_padding=1 transposed convs need H and W to be multiples of 16 (stereodpnet/modules.py:208-227)."""
+        if h % 16 or w % 16:
+            raise ValueError(f"input size {h}x{w}: height and width must be multiples of 16")
+        if min(h, w) // 4 < self.min_quarter_size:
+            raise ValueError(f"input size {h}x{w}: this model needs at least {4 * self.min_quarter_size} pixels per side")
 
     def refresh(self):
         """Re-pack kernel-layout weights after parameters changed (load_state_dict calls it)."""
@@ -202,6 +213,7 @@ class STEREODPNET(_StereoBase):
 
 class PSMNET(_StereoBase):
     train_supported = True
+    min_quarter_size = 64
 
     def __init__(self, option):
         super().__init__()

@@ -153,3 +153,14 @@ def test_checkpoint_key_conversion():
     new = _StereoBase.convert_checkpoint_keys(old)
     assert new == {"feature_extraction.fpn.inner_blocks.1.0.weight": 1, "feature_extraction.fpn.layer_blocks.2.0.bias": 2,
                    "feature_extraction.fpn.inner_blocks.0.0.weight": 3, "aggregation.dres0.0.0.weight": 5}
+
+
+def test_input_size_contract():
+    """H, W multiples of 16 (both models); PSMNet additionally needs a 64x64 quarter-resolution map for its pooling branch."""
+    from dualpixelface_b200.models import PSMNET, STEREODPNET
+    STEREODPNET.check_input_size(STEREODPNET, 1120, 1680)
+    PSMNET.check_input_size(PSMNET, 448, 448)
+    with pytest.raises(ValueError):
+        STEREODPNET.check_input_size(STEREODPNET, 1120, 1684)
+    with pytest.raises(ValueError):
+        PSMNET.check_input_size(PSMNET, 128, 256)
