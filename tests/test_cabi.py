@@ -52,3 +52,26 @@ def test_ops_refuse_cpu_tensors():
     x = torch.zeros(1, 4, 4, 32, dtype=torch.bfloat16)
     with pytest.raises(_lib.DpfError):
         ops.costvol_fwd(x, x, [0, 1])
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU or PyTorch fallback: without the built .so the binding raises instead of degrading."""
+    from dualpixelface_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libdpf_sm100.so")
+    with pytest.raises(_lib.DpfError, match="no CPU or PyTorch fallback"):
+        _lib.load()
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under dualpixelface_b200/, src/, main.py may import it (bench.py only in its
+    cpu_baseline / --impl reference legs, __graft_entry__ only in smoke())."""
+    import re
+    from conftest import ROOT
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b", re.M)
+    offenders = [str(p.relative_to(ROOT)) for base in ("dualpixelface_b200", "src") for p in (ROOT / base).rglob("*.py")
+                 if pat.search(p.read_text())]
+    offenders += [f for f in ("main.py",) if pat.search((ROOT / f).read_text())]
+    assert offenders == []
+    bench = (ROOT / "bench.py").read_text()
+    assert len(pat.findall(bench)) == 1 and "def cpu_reference_pairs_per_s" in bench   # the single import lives in the CPU leg
