@@ -146,9 +146,27 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
         vh[ps] = vlive[ps] ? hh : 0;
         vw[ps] = vlive[ps] ? ww : 0;
       }
+      // the (d, h, w) offsets of tap t+1 are requested while tap t is gathered: offset load -> address -> gather would
+      // otherwise be two dependent memory round trips per (voxel, tap)
+      const float* obase[PASSES];
+      float onext[PASSES][3];
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        obase[ps] = p.offset + static_cast<size_t>(vbase + (ud * H + vh[ps]) * W + vw[ps]) * p.off_cstride;
+        onext[ps][0] = __ldg(obase[ps] + 0); onext[ps][1] = __ldg(obase[ps] + 1); onext[ps][2] = __ldg(obase[ps] + 2);
+      }
       for (int tap = 0; tap < kTaps; ++tap, ++g) {
         const int stage = g % kStages;
         const uint32_t ph = (g / kStages) & 1u;
+        float ocur[PASSES][3];
+#pragma unroll
+        for (int ps = 0; ps < PASSES; ++ps) {
+          ocur[ps][0] = onext[ps][0]; ocur[ps][1] = onext[ps][1]; ocur[ps][2] = onext[ps][2];
+          if (tap + 1 < kTaps) {
+            const float* on = obase[ps] + (tap + 1) * 3;
+            onext[ps][0] = __ldg(on + 0); onext[ps][1] = __ldg(on + 1); onext[ps][2] = __ldg(on + 2);
+          }
+        }
         mbar_wait(&bar_empty[stage], ph ^ 1u);
         uint8_t* sa = s_stage + stage * C::STAGE_BYTES;
         if (ptid == 0) {
@@ -160,11 +178,9 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
 #pragma unroll
         for (int ps = 0; ps < PASSES; ++ps) {
           const int r = ps * kVoxPerPass + vsub;             // row inside the work unit (0..255)
-          const int vox = vbase + (ud * H + vh[ps]) * W + vw[ps];
-          const float* op = p.offset + static_cast<size_t>(vox) * p.off_cstride + tap * 3;
-          const float pd = fdz + __ldg(op + 0);
-          const float phh = static_cast<float>(vh[ps] + tj) + __ldg(op + 1);
-          const float pw = static_cast<float>(vw[ps] + tk) + __ldg(op + 2);
+          const float pd = fdz + ocur[ps][0];
+          const float phh = static_cast<float>(vh[ps] + tj) + ocur[ps][1];
+          const float pw = static_cast<float>(vw[ps] + tk) + ocur[ps][2];
           const bool inside = vlive[ps] && pd > -1.f && phh > -1.f && pw > -1.f && pd < static_cast<float>(D) &&
                               phh < static_cast<float>(H) && pw < static_cast<float>(W);
           const float fd = floorf(pd), fh = floorf(phh), fw = floorf(pw);
