@@ -118,55 +118,68 @@ extern "C" int dpf_anm_tail(const void* x, float* out, int B, int K, int H4, int
 // ------------------------------------------------------------------------------------------------------------
 namespace {
 
-__device__ __forceinline__ void bilerp8(const __nv_bfloat16* __restrict__ src, int n, int hs, int ws, int C, int y, int x, float ry,
-                                        float rx, int c0, float (&f)[8]) {
-  const float sy = ry * static_cast<float>(y), sx = rx * static_cast<float>(x);      // align_corners=True source coordinates
-  const int y0 = min(static_cast<int>(sy), hs - 1), x0 = min(static_cast<int>(sx), ws - 1);
-  const int y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
-  const float ly = sy - static_cast<float>(y0), lx = sx - static_cast<float>(x0);
-  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-  const __nv_bfloat16* base = src + static_cast<size_t>(n) * hs * ws * C + c0;
-  const uint4 a = dpf::ld_nc_v4(base + (static_cast<size_t>(y0) * ws + x0) * C);
-  const uint4 b = dpf::ld_nc_v4(base + (static_cast<size_t>(y0) * ws + x1) * C);
-  const uint4 c = dpf::ld_nc_v4(base + (static_cast<size_t>(y1) * ws + x0) * C);
-  const uint4 d = dpf::ld_nc_v4(base + (static_cast<size_t>(y1) * ws + x1) * C);
-  const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w}, uc[4] = {c.x, c.y, c.z, c.w}, ud[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    f[2 * k] = w00 * dpf::bf16_lo(ua[k]) + w01 * dpf::bf16_lo(ub[k]) + w10 * dpf::bf16_lo(uc[k]) + w11 * dpf::bf16_lo(ud[k]);
-    f[2 * k + 1] = w00 * dpf::bf16_hi(ua[k]) + w01 * dpf::bf16_hi(ub[k]) + w10 * dpf::bf16_hi(uc[k]) + w11 * dpf::bf16_hi(ud[k]);
-  }
-}
-
 __global__ void __launch_bounds__(256) pyramid_cat_kernel(const __nv_bfloat16* __restrict__ f1, const __nv_bfloat16* __restrict__ f2,
                                                           const __nv_bfloat16* __restrict__ f3, __nv_bfloat16* __restrict__ out,
                                                           int N, int h, int w, int h2, int w2, int h3, int w3, int C) {
+  // one thread per (pixel, pyramid level): the source coordinates and blend weights are computed once and reused for all
+  // C/8 channel chunks; the three threads of a pixel write its 3*C output channels contiguously
   const int c8n = C >> 3;
+  const long long total = static_cast<long long>(N) * h * w * 3;
   const float ry2 = (h > 1) ? static_cast<float>(h2 - 1) / static_cast<float>(h - 1) : 0.f;
   const float rx2 = (w > 1) ? static_cast<float>(w2 - 1) / static_cast<float>(w - 1) : 0.f;
   const float ry3 = (h > 1) ? static_cast<float>(h3 - 1) / static_cast<float>(h - 1) : 0.f;
   const float rx3 = (w > 1) ? static_cast<float>(w3 - 1) / static_cast<float>(w - 1) : 0.f;
-  const long long total = static_cast<long long>(N) * h * w * 3 * c8n;
   for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < total;
        q += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int piece = static_cast<int>(q % (3 * c8n));
-    long long t = q / (3 * c8n);
+    const int lvl = static_cast<int>(q % 3);
+    long long t = q / 3;
     const int x = static_cast<int>(t % w);
     t /= w;
     const int y = static_cast<int>(t % h);
     const int n = static_cast<int>(t / h);
-    const int lvl = piece / c8n, c0 = (piece % c8n) * 8;
-    uint4 o;
+    __nv_bfloat16* dst = out + ((static_cast<size_t>(n) * h + y) * w + x) * (3 * C) + lvl * C;
     if (lvl == 0) {
-      o = dpf::ld_nc_v4(f1 + ((static_cast<size_t>(n) * h + y) * w + x) * C + c0);
-    } else {
-      float f[8];
-      if (lvl == 1) bilerp8(f2, n, h2, w2, C, y, x, ry2, rx2, c0, f);
-      else bilerp8(f3, n, h3, w3, C, y, x, ry3, rx3, c0, f);
-      o.x = dpf::pack_bf16x2(f[0], f[1]); o.y = dpf::pack_bf16x2(f[2], f[3]);
-      o.z = dpf::pack_bf16x2(f[4], f[5]); o.w = dpf::pack_bf16x2(f[6], f[7]);
+      const __nv_bfloat16* src = f1 + ((static_cast<size_t>(n) * h + y) * w + x) * C;
+      for (int c = 0; c < c8n; ++c) *reinterpret_cast<uint4*>(dst + c * 8) = dpf::ld_nc_v4(src + c * 8);
+      continue;
     }
-    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * h + y) * w + x) * (3 * C) + lvl * C + c0) = o;
+    const __nv_bfloat16* src = lvl == 1 ? f2 : f3;
+    const int hs = lvl == 1 ? h2 : h3, ws = lvl == 1 ? w2 : w3;
+    const float sy = (lvl == 1 ? ry2 : ry3) * static_cast<float>(y), sx = (lvl == 1 ? rx2 : rx3) * static_cast<float>(x);
+    const int y0 = min(static_cast<int>(sy), hs - 1), x0 = min(static_cast<int>(sx), ws - 1);
+    const int y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
+    const float ly = sy - static_cast<float>(y0), lx = sx - static_cast<float>(x0);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const __nv_bfloat16* base = src + static_cast<size_t>(n) * hs * ws * C;
+    const __nv_bfloat16* p00 = base + (static_cast<size_t>(y0) * ws + x0) * C;
+    const __nv_bfloat16* p01 = base + (static_cast<size_t>(y0) * ws + x1) * C;
+    const __nv_bfloat16* p10 = base + (static_cast<size_t>(y1) * ws + x0) * C;
+    const __nv_bfloat16* p11 = base + (static_cast<size_t>(y1) * ws + x1) * C;
+    for (int c = 0; c < c8n; ++c) {
+      const uint4 a = dpf::ld_nc_v4(p00 + c * 8), b = dpf::ld_nc_v4(p01 + c * 8), cc = dpf::ld_nc_v4(p10 + c * 8), d = dpf::ld_nc_v4(p11 + c * 8);
+      const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w}, uc[4] = {cc.x, cc.y, cc.z, cc.w}, ud[4] = {d.x, d.y, d.z, d.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        o[k] = dpf::pack_bf16x2(w00 * dpf::bf16_lo(ua[k]) + w01 * dpf::bf16_lo(ub[k]) + w10 * dpf::bf16_lo(uc[k]) + w11 * dpf::bf16_lo(ud[k]),
+                                w00 * dpf::bf16_hi(ua[k]) + w01 * dpf::bf16_hi(ub[k]) + w10 * dpf::bf16_hi(uc[k]) + w11 * dpf::bf16_hi(ud[k]));
+      *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// per-pixel maximum over the channels of a channels-last bf16 map (ref_feature = ref_fea.max(1)[0], mainmodel.py:104)
+__global__ void __launch_bounds__(256) channel_max_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long npix, int C) {
+  const int c8n = C >> 3;
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < npix;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float m = -INFINITY;
+    for (int c = 0; c < c8n; ++c) {
+      const uint4 u = dpf::ld_nc_v4(x + q * C + c * 8);
+      m = fmaxf(m, fmaxf(fmaxf(fmaxf(dpf::bf16_lo(u.x), dpf::bf16_hi(u.x)), fmaxf(dpf::bf16_lo(u.y), dpf::bf16_hi(u.y))),
+                         fmaxf(fmaxf(dpf::bf16_lo(u.z), dpf::bf16_hi(u.z)), fmaxf(dpf::bf16_lo(u.w), dpf::bf16_hi(u.w)))));
+    }
+    y[q] = m;
   }
 }
 
@@ -177,7 +190,7 @@ extern "C" int dpf_pyramid_cat(const void* f1, const void* f2, const void* f3, v
   DPF_REQUIRE(f1 && f2 && f3 && out, "dpf_pyramid_cat: null pointer");
   DPF_REQUIRE(DPF_ALIGNED16(f1) && DPF_ALIGNED16(f2) && DPF_ALIGNED16(f3) && DPF_ALIGNED16(out), "dpf_pyramid_cat: pointers must be 16-byte aligned");
   DPF_REQUIRE(N > 0 && h > 0 && w > 0 && h2 > 0 && w2 > 0 && h3 > 0 && w3 > 0 && C >= 8 && C % 8 == 0, "dpf_pyramid_cat: bad shape");
-  const long long total = static_cast<long long>(N) * h * w * 3 * (C / 8);
+  const long long total = static_cast<long long>(N) * h * w * 3;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(dpf::sm_count()) * 16));
   pyramid_cat_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(f1), reinterpret_cast<const __nv_bfloat16*>(f2), reinterpret_cast<const __nv_bfloat16*>(f3),
@@ -231,6 +244,13 @@ __global__ void __launch_bounds__(256) fpn_merge_kernel(const __nv_bfloat16* __r
 }
 
 }  // namespace
+
+extern "C" int dpf_channel_max(const void* x, float* y, long long npix, int C, void* stream) {
+  DPF_REQUIRE(x && y && npix > 0 && C >= 8 && C % 8 == 0 && DPF_ALIGNED16(x), "dpf_channel_max: bad arguments (C=%d)", C);
+  const int blocks = static_cast<int>(std::min<long long>((npix + 255) / 256, static_cast<long long>(dpf::sm_count()) * 16));
+  channel_max_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), y, npix, C);
+  return dpf::after_launch("dpf_channel_max");
+}
 
 extern "C" int dpf_fpn_merge(const void* x, const float* bias, const void* top, void* y, int N, int h, int w, int ht, int wt, int C,
                              void* stream) {

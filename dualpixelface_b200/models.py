@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import modules as M
+from . import ops
 from .runner import LightningModule, optimizer_selector, scheduler_selector
 from .synthetic import synthetic_batch
 
@@ -122,7 +123,7 @@ class _StereoBase(LightningModule):
         results = {"pred_depth": torch.stack(cost_f, 1),
                    "prob_depth": torch.stack(cost_p, 1) if cost_p[0] is not None else None,
                    "pred_normal": normal,
-                   "ref_feature": ref_fea.amax(-1).float()}
+                   "ref_feature": ops.channel_max(ref_fea) if ref_fea.shape[-1] % 8 == 0 else ref_fea.amax(-1).float()}
         if self.training and "disp" in batch:
             results.update(self.loss_model.forward(results, batch))
         return results

@@ -295,3 +295,12 @@ def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], slope: float, res: O
         _req(bias, torch.float32, "bias")
     check(lib().dpf_bias_act(_p(x), _p(bias), _p(res), _p(out), npix, c, cstride, y_coff, float(slope), _stream()), "dpf_bias_act")
     return out
+
+
+def channel_max(x: torch.Tensor) -> torch.Tensor:
+    """x [..., C] bf16 contiguous -> [...] fp32, maximum over the channels (ref_feature of the model output)."""
+    _req(x, torch.bfloat16, "x")
+    c = x.shape[-1]
+    y = torch.empty(x.shape[:-1], device=x.device, dtype=torch.float32)
+    check(lib().dpf_channel_max(_p(x), _p(y), x.numel() // c, c, _stream()), "dpf_channel_max")
+    return y

@@ -184,6 +184,9 @@ int dpf_pyramid_cat(const void* f1, const void* f2, const void* f3, void* out, i
  * y[N,h,w,C] = x + bias + nearest_upsample(top[N,ht,wt,C]); bf16 channels-last, one pass. */
 int dpf_fpn_merge(const void* x, const float* bias, const void* top, void* y, int N, int h, int w, int ht, int wt, int C,
                   void* stream);
+/* ref_feature = ref_fea.max(1)[0] (src/model/stereodpnet/mainmodel.py:104): per-pixel maximum over the C channels of a
+ * channels-last bf16 map x[npix][C] -> y[npix] fp32. */
+int dpf_channel_max(const void* x, float* y, long long npix, int C, void* stream);
 
 /* ANM tail: bilinear x4 upsample (align_corners) -> sigmoid -> mean over K -> *2-1 in one pass.  Replaces final_layer and
  * the mean / rescale of ANM.forward (src/model/stereodpnet/normal_module.py:69-72,185-190).
