@@ -117,6 +117,10 @@ class FusedSDPEncoder:
     def __init__(self, enc):
         fc = enc.firstconv
         self.first = [_fold(fc[i][0], fc[i][1]) for i in (0, 2, 4)]
+        # 3 -> 8 zero-padded input channels (the model stages its images into an 8-channel channels-last buffer)
+        self.in_channels = 8
+        w0 = self.first[0]["w"]
+        self.first[0]["w"] = F.pad(w0, (0, 0, 0, 0, 0, self.in_channels - w0.shape[1])).contiguous(memory_format=torch.channels_last)
         self.block1 = _Block(enc.block1)
         self.inter1 = [_Block(b) for b in enc.interblock1]
         self.block2 = _Block(enc.block2)
@@ -128,6 +132,8 @@ class FusedSDPEncoder:
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         """x [N,3,H,W] -> features [N,C,H/4,W/4] bf16, channels-last memory format."""
         x = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        if x.shape[1] < self.in_channels:
+            x = F.pad(x, (0, 0, 0, 0, 0, self.in_channels - x.shape[1])).contiguous(memory_format=torch.channels_last)
         for f in self.first:
             x = _conv_bias_relu(x, f)
         o1 = self.block1(x)
