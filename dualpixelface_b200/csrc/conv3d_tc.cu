@@ -73,6 +73,13 @@ struct ConvKParams {
   int nw;                         // number of weight tiles resident
   int tiles_h, tiles_w, ntiles;
   int debug;                      // DPF_CONV_DEBUG bits: 1 skip loads, 2 skip MMAs, 4 skip stores (timing experiments)
+  // ---- kd-fused kernel only (defaults = dense 3-D tensor): strided views and the row-streamed 2-D mode -------------
+  long long xs_b, xs_d, xs_h;     // voxel strides of the input: batch, plane, row (a row is W-contiguous)
+  long long ys_b, ys_d, ys_h;     // voxel strides of the output and of the residual
+  int halo;                       // 1: planes -1 and D exist (rows of a neighbouring stream) and are read; 0: they are padding
+  int center_row_only;            // 1: the rows of a plane are independent streams -> only the kh = 1 in-plane taps
+  int lin_d, lin_h, lin_max;      // lin_max > 0: (plane pl, row h) exists only if 0 <= pl*lin_d + h*lin_h < lin_max
+  float slope;                    // activation when relu != 0: v > 0 ? v : slope * v   (0 = ReLU)
   int ntaps[2];
   Tap taps[2][kMaxTaps];          // program per work-item parity (only the transposed kind uses program 1)
 };
@@ -548,16 +555,17 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
       const int th = (tile / p.tiles_w) % p.tiles_h;
       const int b = tile / (p.tiles_w * p.tiles_h);
       const int h0 = th * 16 - 1, w0 = tw * WT - 1;
-      for (int pl = 0; pl < D; ++pl, ++g) {
+      for (int pl = -p.halo; pl < D + p.halo; ++pl, ++g) {
         const int slot = g % NS;
         mbar_wait(&bar_empty[slot], ((g / NS) & 1u) ^ 1u);
         const uint32_t sbase = smem_u32(s_slots + slot * C::SLOT_BYTES);
-        const __nv_bfloat16* xplane = p.x + (static_cast<size_t>(b) * D + pl) * H * static_cast<size_t>(W) * p.x_cstride + p.x_coff;
+        const long long plane_off = static_cast<long long>(b) * p.xs_b + static_cast<long long>(pl) * p.xs_d;
         if (!(p.debug & 1)) {                                    // row-based copy, see the generic kernel
           for (int row = pwarp; row < 18; row += kProdWarps) {
             const int h = h0 + row;
-            const bool hok = (h >= 0) && (h < H);
-            const __nv_bfloat16* xrow = xplane + static_cast<size_t>(hok ? h : 0) * W * p.x_cstride;
+            const bool hok = (h >= 0) && (h < H) &&
+                             (p.lin_max == 0 || static_cast<unsigned>(pl * p.lin_d + h * p.lin_h) < static_cast<unsigned>(p.lin_max));
+            const __nv_bfloat16* xrow = p.x + (hok ? (plane_off + static_cast<long long>(h) * p.xs_h) * p.x_cstride : 0) + p.x_coff;
 #pragma unroll
             for (int q = lane; q < PIECES_PER_ROW; q += 32) {
               const int col = q / C::NCH, c8 = q % C::NCH;
@@ -592,21 +600,27 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
     const uint64_t adesc_hi = umma_desc_nosw(0, C::CH_STRIDE, C::WP * 16);
     const uint64_t bdesc_hi = umma_desc_nosw(0, C::W_ROWS * 16, 128);
     const bool leader = elect_one();
-    uint32_t g_base = 0;
+    // Input plane pl feeds output planes pl+1-kd (kd = 0,1,2) that lie in [0, D).  Input planes are counted for the slot ring
+    // (g_in), output planes for the accumulator ring (g_out); with halo planes (row-streamed 2-D mode) pl runs from -1 to D.
+    uint32_t g_in = 0, g_out = 0;
+    const int HALO = p.halo;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int tw = tile % p.tiles_w;
       const int nblk = min(C::NBLK, (p.Mw - tw * WT + 7) >> 3);
-      for (int pl = 0; pl < D; ++pl) {
-        const uint32_t P = g_base + pl;
-        const uint32_t slot = P % NS;
+      for (int pl = -HALO; pl < D + HALO; ++pl, ++g_in) {
+        const uint32_t slot = g_in % NS;
         // accumulator stages touched for the first time by this input plane must have been drained (and zeroed)
-        if (pl == 0) mbar_wait(&bar_tempty[(R - P % R) % R], (P / R) & 1u);
-        if (pl + 1 < D) mbar_wait(&bar_tempty[(R - (P + 1) % R) % R], ((P + 1) / R) & 1u);
-        mbar_wait(&bar_full[slot], (P / NS) & 1u);
+        if (HALO == 0 && pl == 0) mbar_wait(&bar_tempty[(R - g_out % R) % R], (g_out / R) & 1u);
+        if (pl + 1 < D) {
+          const uint32_t Qn = g_out + static_cast<uint32_t>(pl + 1);
+          mbar_wait(&bar_tempty[(R - Qn % R) % R], (Qn / R) & 1u);
+        }
+        mbar_wait(&bar_full[slot], (g_in / NS) & 1u);
         tc_fence_after_sync();
-        const int kd_lo = (pl + 1 < D) ? 0 : 1, kd_hi = (pl >= 1) ? 2 : 1;
+        const int kd_lo = (pl + 1 < D) ? 0 : pl + 2 - D, kd_hi = min(2, pl + 1);
         const int n_kd = kd_hi - kd_lo + 1;
-        const uint32_t s_first = (R - (P + 1 - kd_lo) % R) % R;     // stage of output plane P+1-kd_lo; next kd -> next stage
+        const uint32_t Qf = g_out + static_cast<uint32_t>(pl + 1 - kd_lo);
+        const uint32_t s_first = (R - Qf % R) % R;                   // stage of output plane pl+1-kd_lo; next kd -> next stage
         const int run1 = min(n_kd, static_cast<int>(R - s_first)), run2 = n_kd - run1;
         const uint32_t idesc1 = umma_idesc_bf16_f32(128, run1 * NPAD);
         const uint32_t idesc2 = umma_idesc_bf16_f32(128, (run2 > 0 ? run2 : 1) * NPAD);
@@ -614,6 +628,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
         if (leader && !(p.debug & 2)) {
 #pragma unroll 1
           for (int kh = 0; kh < 3; ++kh) {
+            if (p.center_row_only && kh != 1) continue;
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
               const uint32_t a0 = a_slot + kh * C::WP + kw;
@@ -638,12 +653,18 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
         }
         if (leader) {
           umma_commit(&bar_empty[slot]);                               // this input plane is fully consumed
-          if (pl >= 1) umma_commit(&bar_tfull[(R - (P - 1) % R) % R]);  // output plane pl-1 complete
-          if (pl == D - 1) umma_commit(&bar_tfull[(R - P % R) % R]);    // last plane of the tile complete
+          if (pl >= 1) {                                               // output plane pl-1 complete
+            const uint32_t Qd = g_out + static_cast<uint32_t>(pl - 1);
+            umma_commit(&bar_tfull[(R - Qd % R) % R]);
+          }
+          if (HALO == 0 && pl == D - 1) {                              // no plane D: the last output plane is complete too
+            const uint32_t Qd = g_out + static_cast<uint32_t>(pl);
+            umma_commit(&bar_tfull[(R - Qd % R) % R]);
+          }
         }
         __syncwarp();
       }
-      g_base += D;
+      g_out += D;
     }
   } else {
     // =================================== epilogue (8 warps: 2 per TMEM lane quarter) =======================
@@ -695,9 +716,11 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
           const int item = i * 2 + half;
           const int blk = item / CHUNKS, c0 = (item % CHUNKS) * 16;
           const int w = tw * WT + blk * 8 + wcol;
-          const bool ok = (item < ITEMS) && (blk < nblk) && (h < H) && (w < W);
+          const bool ok = (item < ITEMS) && (blk < nblk) && (h < H) && (w < W) &&
+                          (p.lin_max == 0 || static_cast<unsigned>(d * p.lin_d + h * p.lin_h) < static_cast<unsigned>(p.lin_max));
           if (!ok || c0 >= p.cout || (p.debug & 4)) continue;
-          const size_t vox = ((static_cast<size_t>(b) * D + d) * H + h) * static_cast<size_t>(W) + w;
+          const size_t vox = static_cast<size_t>(static_cast<long long>(b) * p.ys_b + static_cast<long long>(d) * p.ys_d +
+                                                 static_cast<long long>(h) * p.ys_h + w);
           const int n = min(16, p.cout - c0);
           float f[16];
 #pragma unroll
@@ -758,8 +781,9 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
               f[12] += bf16_lo(r1.z); f[13] += bf16_hi(r1.z); f[14] += bf16_lo(r1.w); f[15] += bf16_hi(r1.w);
             }
             if (p.relu) {
+              const float sl = p.slope;                              // 0 = ReLU, else LeakyReLU / single-parameter PReLU
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f) + sl * fminf(f[j], 0.f);
             }
             uint4 o0, o1;
             o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]); o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
@@ -933,6 +957,9 @@ extern "C" int dpf_conv3d_fwd(const dpf_conv3d_args* a, void* stream) {
     kp.nw = 27;
     kp.Mh = a->H; kp.Mw = a->W; kp.items = kp.Do;
   }
+  kp.xs_h = a->W; kp.xs_d = static_cast<long long>(a->H) * a->W; kp.xs_b = kp.xs_d * a->D;   // dense [B,D,H,W] views
+  kp.ys_h = kp.xs_h; kp.ys_d = kp.xs_d; kp.ys_b = kp.xs_b;
+  kp.halo = 0; kp.center_row_only = 0; kp.lin_d = kp.lin_h = kp.lin_max = 0; kp.slope = 0.f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int npad = npad_for(a->Cout);
   if (geo == GEO_S1) {
@@ -965,4 +992,39 @@ extern "C" int dpf_conv3d_fwd(const dpf_conv3d_args* a, void* stream) {
     if (a->Cin == 32 && npad == 32) return launch<GEO_T2, 32, 32, 8, 4>(kp, st);
   }
   return dpf::fail("dpf_conv3d_fwd: no kernel for kind=%d Cin=%d Cout=%d", a->kind, a->Cin, a->Cout);
+}
+
+// 2-D 3x3 convolution (stride 1, pad 1) on channels-last images, on the kd-fused kernel: the image is read as 16 independent
+// row streams (H' = 16 segments of L = ceil(H/16) consecutive image rows, stream position = "depth"), so that a GEMM block is
+// 16 streams x 8 pixels, the image's kh taps are the fused depth taps (N = 3*Cout, accumulator ring over output rows) and only
+// the centre in-plane row taps are issued.  Planes -1 and L of a stream are the neighbouring streams' rows (halo planes).
+extern "C" int dpf_conv2d_fwd(const void* x, const void* w, void* y, const float* scale, const float* shift, const void* residual,
+                              int N, int H, int W, int Cin, int Cout, int x_cstride, int x_coff, int y_cstride, int y_coff,
+                              int relu, float slope, void* stream) {
+  DPF_REQUIRE(x && w && y, "dpf_conv2d_fwd: null tensor pointer");
+  DPF_REQUIRE(DPF_ALIGNED16(x) && DPF_ALIGNED16(w) && DPF_ALIGNED16(y), "dpf_conv2d_fwd: pointers must be 16-byte aligned");
+  DPF_REQUIRE(Cin == 32 && Cout >= 8 && Cout <= 32 && Cout % 8 == 0, "dpf_conv2d_fwd: Cin=%d Cout=%d (built: Cin 32, Cout <= 32 per launch)", Cin, Cout);
+  DPF_REQUIRE(N > 0 && H > 0 && W > 0, "dpf_conv2d_fwd: bad shape");
+  DPF_REQUIRE(x_cstride % 8 == 0 && x_coff % 8 == 0 && x_coff + Cin <= x_cstride && y_cstride % 8 == 0 && y_coff % 8 == 0 &&
+              y_coff + Cout <= y_cstride, "dpf_conv2d_fwd: bad channel windows");
+  const int L = (H + 15) / 16;
+  ConvKParams kp{};
+  kp.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  kp.w = reinterpret_cast<const __nv_bfloat16*>(w);
+  kp.y = y; kp.scale = scale; kp.shift = shift; kp.residual = residual;
+  kp.B = N; kp.D = L; kp.H = 16; kp.W = W;
+  kp.Do = L; kp.Ho = 16; kp.Wo = W; kp.Mh = 16; kp.Mw = W; kp.items = L;
+  kp.x_cstride = x_cstride; kp.x_coff = x_coff;
+  kp.cout = Cout; kp.y_f32 = 0; kp.y_cstride = y_cstride; kp.y_coff = y_coff; kp.relu = relu; kp.res_pre = 0; kp.nw = 27;
+  kp.xs_h = static_cast<long long>(L) * W; kp.xs_d = W; kp.xs_b = static_cast<long long>(H) * W;
+  kp.ys_h = kp.xs_h; kp.ys_d = kp.xs_d; kp.ys_b = kp.xs_b;
+  kp.halo = 1; kp.center_row_only = 1; kp.lin_d = 1; kp.lin_h = L; kp.lin_max = H; kp.slope = slope;
+  { const char* e = getenv("DPF_CONV_DEBUG"); kp.debug = e ? atoi(e) : 0; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int npad = npad_for(Cout);
+  const bool wide24 = ((W + 23) / 24) * 24 <= ((W + 15) / 16) * 16;
+  if (npad == 32 && wide24) return launch_fused<32, 32, 24, 4, 5>(kp, st);
+  if (npad == 32) return launch_fused<32, 32, 16, 4, 8>(kp, st);
+  if (wide24) return launch_fused<32, 16, 24, 4, 8>(kp, st);
+  return launch_fused<32, 16, 16, 4, 8>(kp, st);
 }

@@ -21,13 +21,33 @@ def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d | None):
     w, b = conv.weight, conv.bias
     if bn is not None:
         w, b = fuse_conv_bn_weights(w, b, bn.running_mean, bn.running_var, bn.eps, bn.weight, bn.bias)
-    w = w.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    wf = w.detach().float()
+    w = wf.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     b = b.detach().float().contiguous() if b is not None else None
-    return dict(w=w, b=b, stride=conv.stride, pad=conv.padding, dil=conv.dilation, groups=conv.groups)
+    f = dict(w=w, b=b, stride=conv.stride, pad=conv.padding, dil=conv.dilation, groups=conv.groups)
+    # 3x3 / stride 1 / dilation 1 / 32 -> <=32 channels: the row-streamed 2-D mode of the kd-fused tcgen05 kernel
+    # (dpf_conv2d_fwd) with the bias + activation (+ skip) tail fused into its epilogue -- no cuDNN launch, no extra pass
+    if (tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 1) and tuple(conv.dilation) == (1, 1) and
+            tuple(conv.padding) == (1, 1) and conv.groups == 1 and conv.in_channels == 32 and conv.out_channels in (16, 32)):
+        f["wp"] = ops.pack_conv2d_weight(wf)
+    return f
 
 
 def _conv(x, f):
     return F.conv2d(x, f["w"], None, f["stride"], f["pad"], f["dil"], f["groups"])
+
+
+def _conv_act(x, f, slope, res=None, out=None, y_coff=0):
+    """conv + bias (+ res) + activation on an NCHW view of channels-last memory: one dpf_conv2d_fwd launch when the layer is
+    eligible, else cuDNN + one dpf_bias_act pass.  `out` (NHWC buffer) / y_coff select a channel window of a wider tensor."""
+    if "wp" in f:
+        xh = x.permute(0, 2, 3, 1)
+        rh = res.permute(0, 2, 3, 1) if res is not None else None
+        y = ops.conv2d_rows(xh if xh.is_contiguous() else xh.contiguous(), f["wp"], f["w"].shape[0], None, f["b"],
+                            rh if rh is None or rh.is_contiguous() else rh.contiguous(), relu=slope != 1.0, slope=slope,
+                            out=out, y_coff=y_coff)
+        return y.permute(0, 3, 1, 2)
+    return ops.bias_act(_conv(x, f), f["b"], slope, res=res, out=out, y_coff=y_coff)
 
 
 def _conv_bias_relu(x, f):
@@ -72,12 +92,12 @@ class _Block:
         self.skip = _fold(blk.conv_skip, None)
 
     def __call__(self, x):
-        a = ops.bias_act(_conv(x, self.c1), self.c1["b"], self.s1)
-        y = ops.bias_act(_conv(a, self.c2), self.c2["b"], self.s2)
+        a = _conv_act(x, self.c1, self.s1)
+        y = _conv_act(a, self.c2, self.s2)
         n, c, h, w = y.shape
         cat = torch.empty(n, h, w, 3 * c, device=y.device, dtype=torch.bfloat16)
         for i, f in enumerate(self.dil):
-            ops.bias_act(_conv(y, f), f["b"], 1.0, out=cat, y_coff=i * c)
+            _conv_act(y, f, 1.0, out=cat, y_coff=i * c)
         t = ops.bias_act(_conv(cat.permute(0, 3, 1, 2), self.c3), self.c3["b"], self.s3, res=a)       # prelu(conv3 + a)
         u = ops.bias_act(_conv(t, self.c4), self.c4["b"], self.s4)
         v = ops.bias_act(_conv(_conv(u, self.dw), self.pw), self.pw["b"], self.s5)
@@ -135,7 +155,7 @@ class FusedSDPEncoder:
         if x.shape[1] < self.in_channels:
             x = F.pad(x, (0, 0, 0, 0, 0, self.in_channels - x.shape[1])).contiguous(memory_format=torch.channels_last)
         for f in self.first:
-            x = _conv_bias_relu(x, f)
+            x = _conv_act(x, f, 0.0) if "wp" in f else _conv_bias_relu(x, f)
         o1 = self.block1(x)
         o2 = o1
         for b in self.inter1:

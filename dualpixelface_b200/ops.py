@@ -304,3 +304,36 @@ def channel_max(x: torch.Tensor) -> torch.Tensor:
     y = torch.empty(x.shape[:-1], device=x.device, dtype=torch.float32)
     check(lib().dpf_channel_max(_p(x), _p(y), x.numel() // c, c, _stream()), "dpf_channel_max")
     return y
+
+
+def pack_conv2d_weight(w: torch.Tensor) -> torch.Tensor:
+    """nn.Conv2d weight [Cout,32,3,3] -> the packed 3x3x3 layout of the kd-fused kernel with the image's kh on the depth taps
+    and only the centre in-plane row populated (dpf_conv2d_fwd)."""
+    cout, cin, kh, kw = w.shape
+    assert (kh, kw) == (3, 3)
+    w3 = torch.zeros(cout, cin, 3, 3, 3, device=w.device, dtype=torch.float32)
+    w3[:, :, :, 1, :] = w.detach().float()
+    return pack_conv_weight(w3)
+
+
+def conv2d_rows(x: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional[torch.Tensor] = None,
+                shift: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, relu: bool = False,
+                slope: float = 0.0, out: Optional[torch.Tensor] = None, y_coff: int = 0, x_coff: int = 0) -> torch.Tensor:
+    """3x3 stride-1 conv on channels-last images: x [N,H,W,Cx] bf16 (32 input channels from x_coff) -> y [N,H,W,Cy]
+    (cout channels at y_coff), y = act(conv * scale + shift + residual), act = LeakyReLU(slope) when relu (slope 0 = ReLU)."""
+    _req(x, torch.bfloat16, "x"); _req(w_packed, torch.bfloat16, "w_packed")
+    n, h, w, cx = x.shape
+    if out is None:
+        out = torch.empty(n, h, w, cout, device=x.device, dtype=torch.bfloat16)
+    _req(out, torch.bfloat16, "out")
+    assert out.shape[:3] == (n, h, w)
+    if residual is not None:
+        _req(residual, torch.bfloat16, "residual")
+        assert residual.shape == out.shape
+    for t, nm in ((scale, "scale"), (shift, "shift")):
+        if t is not None:
+            _req(t, torch.float32, nm)
+            assert t.numel() == cout
+    check(lib().dpf_conv2d_fwd(_p(x), _p(w_packed), _p(out), _p(scale), _p(shift), _p(residual), n, h, w, 32, cout, cx, x_coff,
+                               out.shape[-1], y_coff, int(relu), float(slope), _stream()), "dpf_conv2d_fwd")
+    return out

@@ -297,3 +297,28 @@ def test_fpn_merge_matches_torch():
     cl = lambda t: t.cuda().contiguous(memory_format=torch.channels_last)
     got = fpn_merge(cl(lat), bias.cuda(), cl(top)).cpu()
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("shape,cout", [((2, 37, 53), 32), ((1, 16, 24), 32), ((3, 70, 105), 16), ((2, 280, 420), 32)])
+def test_conv2d_rows_matches_torch(ops, shape, cout):
+    """dpf_conv2d_fwd (row-streamed 2-D mode of the kd-fused kernel: 16 row streams, halo planes, centre-row taps) against
+    torch's fp32 conv2d of the same bf16 operands, with bias, residual and LeakyReLU; exact delta-weight check included."""
+    n, h, w = shape
+    g = torch.Generator().manual_seed(71)
+    x = torch.randn(n, 32, h, w, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(cout, 32, 3, 3, generator=g) * 0.06).to(torch.bfloat16)
+    bias = torch.randn(cout, generator=g) * 0.1
+    res = torch.randn(n, cout, h, w, generator=g).to(torch.bfloat16)
+    want = F.leaky_relu(F.conv2d(x.float(), wt.float(), bias, padding=1) + res.float(), 0.05)
+    xc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    got = ops.conv2d_rows(xc, ops.pack_conv2d_weight(wt.cuda()), cout, None, bias.cuda(), res.permute(0, 2, 3, 1).contiguous().cuda(),
+                          relu=True, slope=0.05)
+    err = (got.permute(0, 3, 1, 2).float().cpu() - want).abs()
+    assert err.max().item() < 6e-3 * want.abs().max().item(), err.max().item()
+    # delta weights: the (kh, kw) = (0, 2) tap copies channel c of pixel (y-1, x+1): exact, exercises every stream boundary
+    wd = torch.zeros(cout, 32, 3, 3)
+    wd[torch.arange(cout), torch.arange(cout), 0, 2] = 1.0
+    got = ops.conv2d_rows(xc, ops.pack_conv2d_weight(wd.cuda()), cout).permute(0, 3, 1, 2).cpu()
+    want = torch.zeros(n, cout, h, w, dtype=torch.bfloat16)
+    want[:, :, 1:, :-1] = x[:, :cout, :-1, 1:]
+    assert torch.equal(got, want)
