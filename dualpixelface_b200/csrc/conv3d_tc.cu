@@ -1003,7 +1003,8 @@ extern "C" int dpf_conv2d_fwd(const void* x, const void* w, void* y, const float
                               int relu, float slope, void* stream) {
   DPF_REQUIRE(x && w && y, "dpf_conv2d_fwd: null tensor pointer");
   DPF_REQUIRE(DPF_ALIGNED16(x) && DPF_ALIGNED16(w) && DPF_ALIGNED16(y), "dpf_conv2d_fwd: pointers must be 16-byte aligned");
-  DPF_REQUIRE(Cin == 32 && Cout >= 8 && Cout <= 32 && Cout % 8 == 0, "dpf_conv2d_fwd: Cin=%d Cout=%d (built: Cin 32, Cout <= 32 per launch)", Cin, Cout);
+  DPF_REQUIRE((Cin == 32 || Cin == 64) && Cout >= 8 && Cout <= 32 && Cout % 8 == 0,
+              "dpf_conv2d_fwd: Cin=%d Cout=%d (built: Cin 32 | 64, Cout <= 32 per launch, multiple of 8)", Cin, Cout);
   DPF_REQUIRE(N > 0 && H > 0 && W > 0, "dpf_conv2d_fwd: bad shape");
   DPF_REQUIRE(x_cstride % 8 == 0 && x_coff % 8 == 0 && x_coff + Cin <= x_cstride && y_cstride % 8 == 0 && y_coff % 8 == 0 &&
               y_coff + Cout <= y_cstride, "dpf_conv2d_fwd: bad channel windows");
@@ -1023,6 +1024,7 @@ extern "C" int dpf_conv2d_fwd(const void* x, const void* w, void* y, const float
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int npad = npad_for(Cout);
   const bool wide24 = ((W + 23) / 24) * 24 <= ((W + 15) / 16) * 16;
+  if (Cin == 64) return npad == 32 ? launch_fused<64, 32, 8, 4, 16>(kp, st) : launch_fused<64, 16, 8, 4, 16>(kp, st);
   if (npad == 32 && wide24) return launch_fused<32, 32, 24, 4, 5>(kp, st);
   if (npad == 32) return launch_fused<32, 32, 16, 4, 8>(kp, st);
   if (wide24) return launch_fused<32, 16, 24, 4, 8>(kp, st);

@@ -29,7 +29,8 @@ def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d | None):
     # (dpf_conv2d_fwd) with the bias + activation (+ skip) tail fused into its epilogue -- no cuDNN launch, no extra pass
     if (tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 1) and tuple(conv.dilation) == (1, 1) and
             tuple(conv.padding) == (1, 1) and conv.groups == 1 and conv.in_channels == 32 and conv.out_channels in (16, 32)):
-        f["wp"] = ops.pack_conv2d_weight(wf)
+        # (64-channel layers and multi-chunk outputs are supported by the kernel but measured slower than cuDNN here)
+        f["wp"] = ops.conv2d_rows_plan(wf)
     return f
 
 
@@ -43,9 +44,9 @@ def _conv_act(x, f, slope, res=None, out=None, y_coff=0):
     if "wp" in f:
         xh = x.permute(0, 2, 3, 1)
         rh = res.permute(0, 2, 3, 1) if res is not None else None
-        y = ops.conv2d_rows(xh if xh.is_contiguous() else xh.contiguous(), f["wp"], f["w"].shape[0], None, f["b"],
-                            rh if rh is None or rh.is_contiguous() else rh.contiguous(), relu=slope != 1.0, slope=slope,
-                            out=out, y_coff=y_coff)
+        y = ops.conv2d_rows_multi(xh if xh.is_contiguous() else xh.contiguous(), f["wp"], f["b"],
+                                  rh if rh is None or rh.is_contiguous() else rh.contiguous(), relu=slope != 1.0, slope=slope,
+                                  out=out, y_coff=y_coff)
         return y.permute(0, 3, 1, 2)
     return ops.bias_act(_conv(x, f), f["b"], slope, res=res, out=out, y_coff=y_coff)
 

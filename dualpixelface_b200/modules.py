@@ -527,6 +527,11 @@ class ANM(nn.Module):
                 p[f"aff{i}"] = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, conv_bias=dc.bias)
             p["nconv"] = [(m[0].weight.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
                            m[0].dilation[0]) for m in self.n_convs]
+            # dilation-1 layers with 32 | 64 input channels run on the row-streamed 2-D mode of the tcgen05 engine with the
+            # LeakyReLU fused (dpf_conv2d_fwd); the dilated ones stay cuDNN + dpf_bias_act
+            p["nconv_rows"] = [ops.conv2d_rows_plan(m[0].weight.detach().float())
+                               if (m[0].dilation[0] == 1 and m[0].in_channels in (32, 64) and m[0].out_channels in (16, 32)) else None
+                               for m in self.n_convs]
             self._plan = p
         return self._plan
 
@@ -551,7 +556,11 @@ class ANM(nn.Module):
             f2 = ops.dcn3d(f1, off2, p["w2"], p["cpad2"], p["aff2"][0], p["aff2"][1], relu=True)
             # shared 2-D normal convs on (b*k) slices: cuDNN, bf16 channels-last (adjacent op)
             x = f2.view(b * self.k, f2.shape[2], f2.shape[3], f2.shape[4]).permute(0, 3, 1, 2)
-            for w2d, dil in p["nconv"]:
+            for (w2d, dil), rows in zip(p["nconv"], p["nconv_rows"]):
+                if rows is not None:
+                    xh = x.permute(0, 2, 3, 1)
+                    x = ops.conv2d_rows_multi(xh if xh.is_contiguous() else xh.contiguous(), rows, relu=True, slope=0.1).permute(0, 3, 1, 2)
+                    continue
                 x = F.conv2d(x, w2d, None, 1, dil, dil)                                # cuDNN, bf16 channels-last
                 x = ops.bias_act(x, None, 0.1) if x.shape[1] % 8 == 0 else F.leaky_relu(x, 0.1)   # LeakyReLU(0.1)
             # fused x4 bilinear upsample + sigmoid + mean over the k sampled planes + rescale to [-1, 1]

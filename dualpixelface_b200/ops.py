@@ -307,8 +307,8 @@ def channel_max(x: torch.Tensor) -> torch.Tensor:
 
 
 def pack_conv2d_weight(w: torch.Tensor) -> torch.Tensor:
-    """nn.Conv2d weight [Cout,32,3,3] -> the packed 3x3x3 layout of the kd-fused kernel with the image's kh on the depth taps
-    and only the centre in-plane row populated (dpf_conv2d_fwd)."""
+    """nn.Conv2d weight [Cout<=32, 32|64, 3,3] -> the packed 3x3x3 layout of the kd-fused kernel with the image's kh on the
+    depth taps and only the centre in-plane row populated (dpf_conv2d_fwd)."""
     cout, cin, kh, kw = w.shape
     assert (kh, kw) == (3, 3)
     w3 = torch.zeros(cout, cin, 3, 3, 3, device=w.device, dtype=torch.float32)
@@ -334,6 +334,27 @@ def conv2d_rows(x: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optio
         if t is not None:
             _req(t, torch.float32, nm)
             assert t.numel() == cout
-    check(lib().dpf_conv2d_fwd(_p(x), _p(w_packed), _p(out), _p(scale), _p(shift), _p(residual), n, h, w, 32, cout, cx, x_coff,
+    cin = w_packed.shape[1] * 8
+    check(lib().dpf_conv2d_fwd(_p(x), _p(w_packed), _p(out), _p(scale), _p(shift), _p(residual), n, h, w, cin, cout, cx, x_coff,
                                out.shape[-1], y_coff, int(relu), float(slope), _stream()), "dpf_conv2d_fwd")
+    return out
+
+
+def conv2d_rows_plan(weight: torch.Tensor):
+    """Per-launch packed weights of a 3x3 conv with 32 | 64 input channels and any multiple-of-8 output width: output-channel
+    chunks of <= 32 -> [(packed, y_coff, n)]."""
+    cout = weight.shape[0]
+    return [(pack_conv2d_weight(weight[co:co + 32]), co, min(32, cout - co)) for co in range(0, cout, 32)]
+
+
+def conv2d_rows_multi(x, plan, bias=None, residual=None, relu=False, slope=0.0, out=None, y_coff=0):
+    """conv2d_rows over the output-channel chunks of `plan`; out [N,H,W,Cy] receives them at y_coff."""
+    cout = sum(n for _, _, n in plan)
+    if out is None:
+        out = torch.empty(*x.shape[:3], cout, device=x.device, dtype=torch.bfloat16)
+    for wp, co, n in plan:
+        sh = bias[co:co + n].contiguous() if bias is not None else None
+        if residual is not None and (residual.shape[-1] != out.shape[-1] or y_coff != 0):
+            raise _lib.DpfError("conv2d_rows_multi: the residual must have the layout of the output tensor")
+        conv2d_rows(x, wp, n, None, sh, residual, relu, slope, out, y_coff + co)
     return out

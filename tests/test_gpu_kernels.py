@@ -322,3 +322,14 @@ def test_conv2d_rows_matches_torch(ops, shape, cout):
     want = torch.zeros(n, cout, h, w, dtype=torch.bfloat16)
     want[:, :, 1:, :-1] = x[:, :cout, :-1, 1:]
     assert torch.equal(got, want)
+
+
+def test_conv2d_rows_cin64_multi_chunk(ops):
+    """64 input channels and a 96-channel output (three 32-wide launches), LeakyReLU(0.1): the ANM n_convs[0] shape class."""
+    g = torch.Generator().manual_seed(72)
+    x = torch.randn(2, 64, 33, 45, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(96, 64, 3, 3, generator=g) * 0.04).to(torch.bfloat16)
+    want = F.leaky_relu(F.conv2d(x.float(), wt.float(), None, padding=1), 0.1)
+    got = ops.conv2d_rows_multi(x.permute(0, 2, 3, 1).contiguous().cuda(), ops.conv2d_rows_plan(wt.float().cuda()), relu=True, slope=0.1)
+    err = (got.permute(0, 3, 1, 2).float().cpu() - want).abs()
+    assert err.max().item() < 6e-3 * want.abs().max().item(), err.max().item()
