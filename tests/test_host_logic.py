@@ -164,3 +164,33 @@ def test_input_size_contract():
         STEREODPNET.check_input_size(STEREODPNET, 1120, 1684)
     with pytest.raises(ValueError):
         PSMNET.check_input_size(PSMNET, 128, 256)
+
+
+def test_conv2d_weight_packing_puts_kh_on_the_depth_taps():
+    """dpf_conv2d_fwd reuses the 3x3x3 weight layout: the image kernel's kh becomes the (fused) depth tap, kw stays, and only the
+    centre in-plane row is populated."""
+    from dualpixelface_b200 import ops
+    w = torch.arange(32 * 32 * 9, dtype=torch.float32).reshape(32, 32, 3, 3) / 1000.0
+    packed = ops.pack_conv2d_weight(w)                       # [27 taps][Cin/8][Npad][8]
+    assert packed.shape == (27, 4, 32, 8)
+    full = packed.float().permute(0, 1, 3, 2).reshape(3, 3, 3, 32, 32)          # [kd][kh'][kw][ci][co]
+    assert float(full[:, 0].abs().max()) == 0.0 and float(full[:, 2].abs().max()) == 0.0
+    want = w.to(torch.bfloat16).float().permute(2, 3, 1, 0)                      # [kh][kw][ci][co]
+    assert torch.equal(full[:, 1], want)
+    plan = ops.conv2d_rows_plan(torch.zeros(96, 64, 3, 3))
+    assert [(co, n, tuple(p.shape)) for p, co, n in plan] == [(0, 32, (27, 8, 32, 8)), (32, 32, (27, 8, 32, 8)), (64, 32, (27, 8, 32, 8))]
+
+
+def test_fused_encoder_routes_the_32_channel_convs():
+    """Eval plan of the StereoDPNet encoder: the 3x3 / stride-1 / dilation-1 32 -> 32 convs (firstconv 2-3, conv1 / conv2 / first
+    dilated branch of the 32-channel DPBlocks) carry a dpf_conv2d_fwd plan, everything else stays on cuDNN."""
+    from dualpixelface_b200.encoder_fused import FusedSDPEncoder
+    from dualpixelface_b200.runner import load_config, model_selector
+    model = model_selector(load_config("eval_faceDP", "pytest", make_dirs=False))
+    enc = FusedSDPEncoder(model.feature_extraction)
+    routed = sum("wp" in f for f in enc.first)
+    blocks = [enc.block1, *enc.inter1, enc.block2, *enc.inter2, enc.block3]
+    for b in blocks:
+        routed += sum("wp" in f for f in (b.c1, b.c2, *b.dil, b.c3, b.c4, b.pw, b.skip))
+    assert routed == 2 + 3 * 3            # firstconv[2], firstconv[4]; block1, interblock1[0], block2 (c = 32): conv1, conv2, dil[0]
+    assert "wp" not in enc.first[0] and all("wp" not in f for f in enc.last)
