@@ -57,7 +57,7 @@ SIGNATURES = {
     "dpf_dcn3d_fwd": (c_int, [c_void_p] * 6 + [c_int] * 9 + [c_void_p]),
     "dpf_dcn3d_bwd_data": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),
     "dpf_dcn3d_bwd_weight": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
-    "dpf_conv2d_fwd": (c_int, [c_void_p] * 6 + [c_int] * 10 + [c_float, c_void_p]),
+    "dpf_conv2d_fwd": (c_int, [c_void_p] * 6 + [c_int] * 11 + [c_float, c_void_p]),
     "dpf_channel_max": (c_int, [c_void_p, c_void_p, C.c_longlong, c_int, c_void_p]),
     "dpf_fpn_merge": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "dpf_pyramid_cat": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p]),

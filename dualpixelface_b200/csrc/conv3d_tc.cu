@@ -466,10 +466,10 @@ constexpr int kFMmaWarp = kFEpiWarps;
 constexpr int kFMmaWarps = 4;
 constexpr int kFThreads = (kFEpiWarps + kFMmaWarps + kProdWarps) * 32;   // 512
 
-template <int CIN, int NPAD, int WT, int NS, int R>
+template <int CIN, int NPAD, int WT, int NS, int R, int DILW = 1>
 struct FCfg {
   static constexpr int NCH = CIN / 8;
-  static constexpr int WP = WT + 2;
+  static constexpr int WP = WT + 2 * DILW;                       // window columns: DILW = column dilation (2-D mode only)
   static constexpr int PLANE_BYTES = 18 * WP * 16;
   static constexpr int WANT = (NCH == 4) ? 32 : 16;
   static constexpr int CH_STRIDE = PLANE_BYTES + ((WANT - (PLANE_BYTES % 128)) + 128) % 128;
@@ -488,9 +488,9 @@ struct FCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
 
-template <int CIN, int NPAD, int WT, int NS, int R>
+template <int CIN, int NPAD, int WT, int NS, int R, int DILW = 1>
 __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __grid_constant__ ConvKParams p) {
-  using C = FCfg<CIN, NPAD, WT, NS, R>;
+  using C = FCfg<CIN, NPAD, WT, NS, R, DILW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
   uint8_t* s_w = smem;
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
       const int tw = tile % p.tiles_w;
       const int th = (tile / p.tiles_w) % p.tiles_h;
       const int b = tile / (p.tiles_w * p.tiles_h);
-      const int h0 = th * 16 - 1, w0 = tw * WT - 1;
+      const int h0 = th * 16 - 1, w0 = tw * WT - DILW;
       for (int pl = -p.halo; pl < D + p.halo; ++pl, ++g) {
         const int slot = g % NS;
         mbar_wait(&bar_empty[slot], ((g / NS) & 1u) ^ 1u);
@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
             if (p.center_row_only && kh != 1) continue;
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
-              const uint32_t a0 = a_slot + kh * C::WP + kw;
+              const uint32_t a0 = a_slot + kh * C::WP + kw * DILW;
               const uint32_t b0 = wbase + (kh * 3 + kw) * (C::W_GROUP_BYTES >> 4) + kd_lo * NPAD;
 #pragma unroll
               for (int ks = 0; ks < C::KSTEPS; ++ks) {
@@ -812,13 +812,13 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
   }
 }
 
-template <int CIN, int NPAD, int WT, int NS, int R>
+template <int CIN, int NPAD, int WT, int NS, int R, int DILW = 1>
 int launch_fused(ConvKParams kp, cudaStream_t st) {
-  using C = FCfg<CIN, NPAD, WT, NS, R>;
+  using C = FCfg<CIN, NPAD, WT, NS, R, DILW>;
   kp.tiles_h = (kp.Mh + 15) / 16;
   kp.tiles_w = (kp.Mw + WT - 1) / WT;
   kp.ntiles = kp.B * kp.tiles_h * kp.tiles_w;
-  auto kern = conv3d_kdfused_kernel<CIN, NPAD, WT, NS, R>;
+  auto kern = conv3d_kdfused_kernel<CIN, NPAD, WT, NS, R, DILW>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -994,39 +994,51 @@ extern "C" int dpf_conv3d_fwd(const dpf_conv3d_args* a, void* stream) {
   return dpf::fail("dpf_conv3d_fwd: no kernel for kind=%d Cin=%d Cout=%d", a->kind, a->Cin, a->Cout);
 }
 
-// 2-D 3x3 convolution (stride 1, pad 1) on channels-last images, on the kd-fused kernel: the image is read as 16 independent
-// row streams (H' = 16 segments of L = ceil(H/16) consecutive image rows, stream position = "depth"), so that a GEMM block is
-// 16 streams x 8 pixels, the image's kh taps are the fused depth taps (N = 3*Cout, accumulator ring over output rows) and only
-// the centre in-plane row taps are issued.  Planes -1 and L of a stream are the neighbouring streams' rows (halo planes).
+// 2-D 3x3 convolution (stride 1, pad = dilation) on channels-last images, on the kd-fused kernel: the image is read as 16
+// independent row streams (H' = 16 segments of L consecutive rows, stream position = "depth"), so that a GEMM block is 16 streams
+// x 8 pixels, the image's kh taps are the fused depth taps (N = 3*Cout, accumulator ring over output rows) and only the centre
+// in-plane row taps are issued.  Planes -1 and L of a stream are the neighbouring streams' rows (halo planes).
+// Dilation d: the rows of one residue class (row mod d) form a dilation-1 problem of their own (plane stride d*W), so the kh
+// dilation costs d launches over 1/d of the rows each; the kw dilation is a template parameter of the window / tap offsets.
 extern "C" int dpf_conv2d_fwd(const void* x, const void* w, void* y, const float* scale, const float* shift, const void* residual,
                               int N, int H, int W, int Cin, int Cout, int x_cstride, int x_coff, int y_cstride, int y_coff,
-                              int relu, float slope, void* stream) {
+                              int dil, int relu, float slope, void* stream) {
   DPF_REQUIRE(x && w && y, "dpf_conv2d_fwd: null tensor pointer");
   DPF_REQUIRE(DPF_ALIGNED16(x) && DPF_ALIGNED16(w) && DPF_ALIGNED16(y), "dpf_conv2d_fwd: pointers must be 16-byte aligned");
   DPF_REQUIRE((Cin == 32 || Cin == 64) && Cout >= 8 && Cout <= 32 && Cout % 8 == 0,
               "dpf_conv2d_fwd: Cin=%d Cout=%d (built: Cin 32 | 64, Cout <= 32 per launch, multiple of 8)", Cin, Cout);
+  DPF_REQUIRE(dil == 1 || ((dil == 3 || dil == 5) && Cin == 32), "dpf_conv2d_fwd: dilation %d (built: 1; 3 and 5 for Cin = 32)", dil);
   DPF_REQUIRE(N > 0 && H > 0 && W > 0, "dpf_conv2d_fwd: bad shape");
   DPF_REQUIRE(x_cstride % 8 == 0 && x_coff % 8 == 0 && x_coff + Cin <= x_cstride && y_cstride % 8 == 0 && y_coff % 8 == 0 &&
               y_coff + Cout <= y_cstride, "dpf_conv2d_fwd: bad channel windows");
-  const int L = (H + 15) / 16;
-  ConvKParams kp{};
-  kp.x = reinterpret_cast<const __nv_bfloat16*>(x);
-  kp.w = reinterpret_cast<const __nv_bfloat16*>(w);
-  kp.y = y; kp.scale = scale; kp.shift = shift; kp.residual = residual;
-  kp.B = N; kp.D = L; kp.H = 16; kp.W = W;
-  kp.Do = L; kp.Ho = 16; kp.Wo = W; kp.Mh = 16; kp.Mw = W; kp.items = L;
-  kp.x_cstride = x_cstride; kp.x_coff = x_coff;
-  kp.cout = Cout; kp.y_f32 = 0; kp.y_cstride = y_cstride; kp.y_coff = y_coff; kp.relu = relu; kp.res_pre = 0; kp.nw = 27;
-  kp.xs_h = static_cast<long long>(L) * W; kp.xs_d = W; kp.xs_b = static_cast<long long>(H) * W;
-  kp.ys_h = kp.xs_h; kp.ys_d = kp.xs_d; kp.ys_b = kp.xs_b;
-  kp.halo = 1; kp.center_row_only = 1; kp.lin_d = 1; kp.lin_h = L; kp.lin_max = H; kp.slope = slope;
-  { const char* e = getenv("DPF_CONV_DEBUG"); kp.debug = e ? atoi(e) : 0; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int npad = npad_for(Cout);
   const bool wide24 = ((W + 23) / 24) * 24 <= ((W + 15) / 16) * 16;
-  if (Cin == 64) return npad == 32 ? launch_fused<64, 32, 8, 4, 16>(kp, st) : launch_fused<64, 16, 8, 4, 16>(kp, st);
-  if (npad == 32 && wide24) return launch_fused<32, 32, 24, 4, 5>(kp, st);
-  if (npad == 32) return launch_fused<32, 32, 16, 4, 8>(kp, st);
-  if (wide24) return launch_fused<32, 16, 24, 4, 8>(kp, st);
-  return launch_fused<32, 16, 16, 4, 8>(kp, st);
+  for (int res = 0; res < dil && res < H; ++res) {
+    const int Hres = (H - res + dil - 1) / dil;                 // rows of this residue class
+    const int L = (Hres + 15) / 16;
+    ConvKParams kp{};
+    const size_t row0 = static_cast<size_t>(res) * W;           // first voxel of the class
+    kp.x = reinterpret_cast<const __nv_bfloat16*>(x) + row0 * x_cstride;
+    kp.w = reinterpret_cast<const __nv_bfloat16*>(w);
+    kp.y = reinterpret_cast<__nv_bfloat16*>(y) + row0 * y_cstride;
+    kp.scale = scale; kp.shift = shift;
+    kp.residual = residual ? reinterpret_cast<const __nv_bfloat16*>(residual) + row0 * y_cstride : nullptr;
+    kp.B = N; kp.D = L; kp.H = 16; kp.W = W;
+    kp.Do = L; kp.Ho = 16; kp.Wo = W; kp.Mh = 16; kp.Mw = W; kp.items = L;
+    kp.x_cstride = x_cstride; kp.x_coff = x_coff;
+    kp.cout = Cout; kp.y_f32 = 0; kp.y_cstride = y_cstride; kp.y_coff = y_coff; kp.relu = relu; kp.res_pre = 0; kp.nw = 27;
+    kp.xs_d = static_cast<long long>(dil) * W; kp.xs_h = kp.xs_d * L; kp.xs_b = static_cast<long long>(H) * W;
+    kp.ys_h = kp.xs_h; kp.ys_d = kp.xs_d; kp.ys_b = kp.xs_b;
+    kp.halo = 1; kp.center_row_only = 1; kp.lin_d = 1; kp.lin_h = L; kp.lin_max = Hres; kp.slope = slope;
+    { const char* e = getenv("DPF_CONV_DEBUG"); kp.debug = e ? atoi(e) : 0; }
+    int rc;
+    if (dil == 3) rc = npad == 32 ? launch_fused<32, 32, 24, 4, 5, 3>(kp, st) : launch_fused<32, 16, 24, 4, 8, 3>(kp, st);
+    else if (dil == 5) rc = npad == 32 ? launch_fused<32, 32, 24, 4, 5, 5>(kp, st) : launch_fused<32, 16, 24, 4, 8, 5>(kp, st);
+    else if (Cin == 64) rc = npad == 32 ? launch_fused<64, 32, 8, 4, 16>(kp, st) : launch_fused<64, 16, 8, 4, 16>(kp, st);
+    else if (npad == 32) rc = wide24 ? launch_fused<32, 32, 24, 4, 5>(kp, st) : launch_fused<32, 32, 16, 4, 8>(kp, st);
+    else rc = wide24 ? launch_fused<32, 16, 24, 4, 8>(kp, st) : launch_fused<32, 16, 16, 4, 8>(kp, st);
+    if (rc) return rc;
+  }
+  return 0;
 }

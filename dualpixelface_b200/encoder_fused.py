@@ -25,10 +25,10 @@ def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d | None):
     w = wf.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     b = b.detach().float().contiguous() if b is not None else None
     f = dict(w=w, b=b, stride=conv.stride, pad=conv.padding, dil=conv.dilation, groups=conv.groups)
-    # 3x3 / stride 1 / dilation 1 / 32 -> <=32 channels: the row-streamed 2-D mode of the kd-fused tcgen05 kernel
+    # 3x3 / stride 1 / dilation 1, 3 or 5 / 32 -> <=32 channels: the row-streamed 2-D mode of the kd-fused tcgen05 kernel
     # (dpf_conv2d_fwd) with the bias + activation (+ skip) tail fused into its epilogue -- no cuDNN launch, no extra pass
-    if (tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 1) and tuple(conv.dilation) == (1, 1) and
-            tuple(conv.padding) == (1, 1) and conv.groups == 1 and conv.in_channels == 32 and conv.out_channels in (16, 32)):
+    if (tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 1) and tuple(conv.dilation) in ((1, 1), (3, 3), (5, 5)) and
+            tuple(conv.padding) == tuple(conv.dilation) and conv.groups == 1 and conv.in_channels == 32 and conv.out_channels in (16, 32)):
         # (64-channel layers and multi-chunk outputs are supported by the kernel but measured slower than cuDNN here)
         f["wp"] = ops.conv2d_rows_plan(wf)
     return f
@@ -46,7 +46,7 @@ def _conv_act(x, f, slope, res=None, out=None, y_coff=0):
         rh = res.permute(0, 2, 3, 1) if res is not None else None
         y = ops.conv2d_rows_multi(xh if xh.is_contiguous() else xh.contiguous(), f["wp"], f["b"],
                                   rh if rh is None or rh.is_contiguous() else rh.contiguous(), relu=slope != 1.0, slope=slope,
-                                  out=out, y_coff=y_coff)
+                                  out=out, y_coff=y_coff, dil=f["dil"][0])
         return y.permute(0, 3, 1, 2)
     return ops.bias_act(_conv(x, f), f["b"], slope, res=res, out=out, y_coff=y_coff)
 

@@ -318,8 +318,8 @@ def pack_conv2d_weight(w: torch.Tensor) -> torch.Tensor:
 
 def conv2d_rows(x: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional[torch.Tensor] = None,
                 shift: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, relu: bool = False,
-                slope: float = 0.0, out: Optional[torch.Tensor] = None, y_coff: int = 0, x_coff: int = 0) -> torch.Tensor:
-    """3x3 stride-1 conv on channels-last images: x [N,H,W,Cx] bf16 (32 input channels from x_coff) -> y [N,H,W,Cy]
+                slope: float = 0.0, out: Optional[torch.Tensor] = None, y_coff: int = 0, x_coff: int = 0, dil: int = 1) -> torch.Tensor:
+    """3x3 stride-1 conv (dilation dil, padding dil) on channels-last images: x [N,H,W,Cx] bf16 (32 input channels from x_coff) -> y [N,H,W,Cy]
     (cout channels at y_coff), y = act(conv * scale + shift + residual), act = LeakyReLU(slope) when relu (slope 0 = ReLU)."""
     _req(x, torch.bfloat16, "x"); _req(w_packed, torch.bfloat16, "w_packed")
     n, h, w, cx = x.shape
@@ -336,7 +336,7 @@ def conv2d_rows(x: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optio
             assert t.numel() == cout
     cin = w_packed.shape[1] * 8
     check(lib().dpf_conv2d_fwd(_p(x), _p(w_packed), _p(out), _p(scale), _p(shift), _p(residual), n, h, w, cin, cout, cx, x_coff,
-                               out.shape[-1], y_coff, int(relu), float(slope), _stream()), "dpf_conv2d_fwd")
+                               out.shape[-1], y_coff, int(dil), int(relu), float(slope), _stream()), "dpf_conv2d_fwd")
     return out
 
 
@@ -347,7 +347,7 @@ def conv2d_rows_plan(weight: torch.Tensor):
     return [(pack_conv2d_weight(weight[co:co + 32]), co, min(32, cout - co)) for co in range(0, cout, 32)]
 
 
-def conv2d_rows_multi(x, plan, bias=None, residual=None, relu=False, slope=0.0, out=None, y_coff=0):
+def conv2d_rows_multi(x, plan, bias=None, residual=None, relu=False, slope=0.0, out=None, y_coff=0, dil=1):
     """conv2d_rows over the output-channel chunks of `plan`; out [N,H,W,Cy] receives them at y_coff."""
     cout = sum(n for _, _, n in plan)
     if out is None:
@@ -356,5 +356,5 @@ def conv2d_rows_multi(x, plan, bias=None, residual=None, relu=False, slope=0.0, 
         sh = bias[co:co + n].contiguous() if bias is not None else None
         if residual is not None and (residual.shape[-1] != out.shape[-1] or y_coff != 0):
             raise _lib.DpfError("conv2d_rows_multi: the residual must have the layout of the output tensor")
-        conv2d_rows(x, wp, n, None, sh, residual, relu, slope, out, y_coff + co)
+        conv2d_rows(x, wp, n, None, sh, residual, relu, slope, out, y_coff + co, dil=dil)
     return out

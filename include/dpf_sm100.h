@@ -188,7 +188,7 @@ int dpf_fpn_merge(const void* x, const float* bias, const void* top, void* y, in
  * channels-last bf16 map x[npix][C] -> y[npix] fp32. */
 int dpf_channel_max(const void* x, float* y, long long npix, int C, void* stream);
 
-/* 2-D 3x3 convolution (stride 1, pad 1, dilation 1) + per-channel affine + residual + ReLU / LeakyReLU on channels-last bf16
+/* 2-D 3x3 convolution (stride 1, dilation dil in {1,3,5}, pad = dil) + per-channel affine + residual + ReLU / LeakyReLU on channels-last bf16
  * images, on the kd-fused tcgen05 kernel (the image's kh taps are the fused taps; see conv3d_tc.cu).  Replaces the
  * nn.Conv2d + BatchNorm2d (folded) + PReLU / ReLU triples of the StereoDPNet encoder blocks
  * (src/model/stereodpnet/modules.py:21-54, convbn of src/module/asm/basics.py:17-22) for Cin = 32:
@@ -197,7 +197,7 @@ int dpf_channel_max(const void* x, float* y, long long npix, int C, void* stream
  * Cout <= 32 per launch; act(v) = relu ? (v > 0 ? v : slope*v) : v. */
 int dpf_conv2d_fwd(const void* x, const void* w, void* y, const float* scale, const float* shift, const void* residual,
                    int N, int H, int W, int Cin, int Cout, int x_cstride, int x_coff, int y_cstride, int y_coff,
-                   int relu, float slope, void* stream);
+                   int dil, int relu, float slope, void* stream);
 
 /* ANM tail: bilinear x4 upsample (align_corners) -> sigmoid -> mean over K -> *2-1 in one pass.  Replaces final_layer and
  * the mean / rescale of ANM.forward (src/model/stereodpnet/normal_module.py:69-72,185-190).

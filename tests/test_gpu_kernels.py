@@ -333,3 +333,26 @@ def test_conv2d_rows_cin64_multi_chunk(ops):
     got = ops.conv2d_rows_multi(x.permute(0, 2, 3, 1).contiguous().cuda(), ops.conv2d_rows_plan(wt.float().cuda()), relu=True, slope=0.1)
     err = (got.permute(0, 3, 1, 2).float().cpu() - want).abs()
     assert err.max().item() < 6e-3 * want.abs().max().item(), err.max().item()
+
+
+@pytest.mark.parametrize("dil,shape", [(3, (2, 37, 53)), (5, (1, 70, 105)), (3, (2, 280, 420)), (5, (1, 16, 24))])
+def test_conv2d_rows_dilated(ops, dil, shape):
+    """Dilated 3x3 conv (DPBlock branches, dilation 3 / 5): residue classes of rows as separate dilation-1 launches, column
+    dilation as tap offsets; against torch fp32 and an exact delta-weight check across the class / stream boundaries."""
+    n, h, w = shape
+    g = torch.Generator().manual_seed(73)
+    x = torch.randn(n, 32, h, w, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(32, 32, 3, 3, generator=g) * 0.06).to(torch.bfloat16)
+    bias = torch.randn(32, generator=g) * 0.1
+    want = F.conv2d(x.float(), wt.float(), bias, padding=dil, dilation=dil)
+    xc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    got = ops.conv2d_rows(xc, ops.pack_conv2d_weight(wt.cuda()), 32, None, bias.cuda(), dil=dil)
+    err = (got.permute(0, 3, 1, 2).float().cpu() - want).abs()
+    assert err.max().item() < 6e-3 * want.abs().max().item(), err.max().item()
+    wd = torch.zeros(32, 32, 3, 3)
+    wd[torch.arange(32), torch.arange(32), 2, 0] = 1.0                   # y[r, c] = x[r + dil, c - dil]
+    got = ops.conv2d_rows(xc, ops.pack_conv2d_weight(wd.cuda()), 32, dil=dil).permute(0, 3, 1, 2).cpu()
+    want = torch.zeros(n, 32, h, w, dtype=torch.bfloat16)
+    if h > dil and w > dil:
+        want[:, :, :h - dil, dil:] = x[:, :, dil:, :w - dil]
+    assert torch.equal(got, want)

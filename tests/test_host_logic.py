@@ -182,8 +182,8 @@ def test_conv2d_weight_packing_puts_kh_on_the_depth_taps():
 
 
 def test_fused_encoder_routes_the_32_channel_convs():
-    """Eval plan of the StereoDPNet encoder: the 3x3 / stride-1 / dilation-1 32 -> 32 convs (firstconv 2-3, conv1 / conv2 / first
-    dilated branch of the 32-channel DPBlocks) carry a dpf_conv2d_fwd plan, everything else stays on cuDNN."""
+    """Eval plan of the StereoDPNet encoder: the 3x3 / stride-1 32 -> 32 convs with dilation 1, 3 or 5 (firstconv 2-3, conv1 / conv2 /
+    the three dilated branches of the 32-channel DPBlocks) carry a dpf_conv2d_fwd plan, everything else stays on cuDNN."""
     from dualpixelface_b200.encoder_fused import FusedSDPEncoder
     from dualpixelface_b200.runner import load_config, model_selector
     model = model_selector(load_config("eval_faceDP", "pytest", make_dirs=False))
@@ -192,5 +192,5 @@ def test_fused_encoder_routes_the_32_channel_convs():
     blocks = [enc.block1, *enc.inter1, enc.block2, *enc.inter2, enc.block3]
     for b in blocks:
         routed += sum("wp" in f for f in (b.c1, b.c2, *b.dil, b.c3, b.c4, b.pw, b.skip))
-    assert routed == 2 + 3 * 3            # firstconv[2], firstconv[4]; block1, interblock1[0], block2 (c = 32): conv1, conv2, dil[0]
+    assert routed == 2 + 3 * 5            # firstconv[2], firstconv[4]; block1, interblock1[0], block2 (c = 32): conv1, conv2, dil[0..2]
     assert "wp" not in enc.first[0] and all("wp" not in f for f in enc.last)
