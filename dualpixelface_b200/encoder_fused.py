@@ -127,10 +127,10 @@ class _FPN:
 
     def __call__(self, feats):
         last = ops.bias_act(_conv(feats[-1], self.inner[-1]), self.inner[-1]["b"], 1.0)
-        outs = [ops.bias_act(_conv(last, self.layer[-1]), self.layer[-1]["b"], 1.0)]
+        outs = [_conv_act(last, self.layer[-1], 1.0)]
         for i in range(len(feats) - 2, -1, -1):
             last = fpn_merge(_conv(feats[i], self.inner[i]), self.inner[i]["b"], last)
-            outs.insert(0, ops.bias_act(_conv(last, self.layer[i]), self.layer[i]["b"], 1.0))
+            outs.insert(0, _conv_act(last, self.layer[i], 1.0))
         return outs
 
 
