@@ -16,6 +16,11 @@ from torch.nn.utils.fusion import fuse_conv_bn_weights
 from . import ops
 
 
+# conv3 of a DPBlock as three chained 32-channel windows works (tests/test_gpu_kernels.py::test_conv2d_rows_channel_windows_chain)
+# but measured slower than cuDNN + one dpf_bias_act pass (encoder 5.37 -> 5.70 ms): off.
+CHAIN_CONV3 = False
+
+
 def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d | None):
     """(weight bf16 channels_last, bias fp32 | None, conv hyper-parameters)."""
     w, b = conv.weight, conv.bias
@@ -87,6 +92,15 @@ class _Block:
         self.c2, self.s2 = _fold(blk.conv2[0][0], blk.conv2[0][1]), _slope(blk.conv2[1])
         self.dil = [_fold(m[0], m[1]) for m in blk.conv_dilate]
         self.c3, self.s3 = _fold(blk.conv3[0], blk.conv3[1]), _slope(blk.prelu)
+        # conv3 (96 -> 32 over the concatenated branches): three 32-channel input windows of the cat buffer, chained through the
+        # residual input of dpf_conv2d_fwd -- bias and the skip tensor enter with the first window, the PReLU leaves with the last
+        c3 = blk.conv3[0]
+        if (CHAIN_CONV3 and tuple(c3.kernel_size) == (3, 3) and tuple(c3.stride) == (1, 1) and tuple(c3.dilation) == (1, 1) and
+                tuple(c3.padding) == (1, 1) and c3.groups == 1 and c3.in_channels == 96 and c3.out_channels == 32):
+            from torch.nn.utils.fusion import fuse_conv_bn_weights as _fuse
+            bn = blk.conv3[1]
+            wf, _ = _fuse(c3.weight, c3.bias, bn.running_mean, bn.running_var, bn.eps, bn.weight, bn.bias)
+            self.c3_windows = [ops.pack_conv2d_weight(wf.detach().float()[:, k:k + 32]) for k in (0, 32, 64)]
         self.c4, self.s4 = _fold(blk.conv4[0][0], blk.conv4[0][1]), _slope(blk.conv4[1])
         self.dw = _fold(blk.conv5.depthwise, None)
         self.pw, self.s5 = _fold(blk.conv5.pointwise, blk.conv5.bn), _slope(blk.conv5.prelu)
@@ -99,7 +113,14 @@ class _Block:
         cat = torch.empty(n, h, w, 3 * c, device=y.device, dtype=torch.bfloat16)
         for i, f in enumerate(self.dil):
             _conv_act(y, f, 1.0, out=cat, y_coff=i * c)
-        t = ops.bias_act(_conv(cat.permute(0, 3, 1, 2), self.c3), self.c3["b"], self.s3, res=a)       # prelu(conv3 + a)
+        if hasattr(self, "c3_windows"):                                                               # prelu(conv3 + a)
+            ah = a.permute(0, 2, 3, 1)
+            t = ops.conv2d_rows(cat, self.c3_windows[0], c, None, self.c3["b"], ah if ah.is_contiguous() else ah.contiguous(), x_coff=0)
+            t = ops.conv2d_rows(cat, self.c3_windows[1], c, None, None, t, x_coff=c)
+            t = ops.conv2d_rows(cat, self.c3_windows[2], c, None, None, t, relu=self.s3 != 1.0, slope=self.s3, x_coff=2 * c)
+            t = t.permute(0, 3, 1, 2)
+        else:
+            t = ops.bias_act(_conv(cat.permute(0, 3, 1, 2), self.c3), self.c3["b"], self.s3, res=a)
         u = ops.bias_act(_conv(t, self.c4), self.c4["b"], self.s4)
         v = ops.bias_act(_conv(_conv(u, self.dw), self.pw), self.pw["b"], self.s5)
         return ops.bias_act(_conv(x, self.skip), self.skip["b"], 1.0, res=v)                         # + weighted skip

@@ -356,3 +356,21 @@ def test_conv2d_rows_dilated(ops, dil, shape):
     if h > dil and w > dil:
         want[:, :, :h - dil, dil:] = x[:, :, dil:, :w - dil]
     assert torch.equal(got, want)
+
+
+def test_conv2d_rows_channel_windows_chain(ops):
+    """96 -> 32 conv as three 32-channel input windows (x_coff) chained through the residual input: bias + skip enter with the
+    first window, the activation leaves with the last (DPBlock conv3 over the concatenated branches)."""
+    g = torch.Generator().manual_seed(74)
+    x = torch.randn(2, 96, 35, 52, generator=g).to(torch.bfloat16)
+    skip = torch.randn(2, 32, 35, 52, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(32, 96, 3, 3, generator=g) * 0.04).to(torch.bfloat16)
+    bias = torch.randn(32, generator=g) * 0.1
+    want = F.leaky_relu(F.conv2d(x.float(), wt.float(), bias, padding=1) + skip.float(), 0.05)
+    xc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    wins = [ops.pack_conv2d_weight(wt.float().cuda()[:, k:k + 32]) for k in (0, 32, 64)]
+    t = ops.conv2d_rows(xc, wins[0], 32, None, bias.cuda(), skip.permute(0, 2, 3, 1).contiguous().cuda(), x_coff=0)
+    t = ops.conv2d_rows(xc, wins[1], 32, None, None, t, x_coff=32)
+    t = ops.conv2d_rows(xc, wins[2], 32, None, None, t, relu=True, slope=0.05, x_coff=64)
+    err = (t.permute(0, 3, 1, 2).float().cpu() - want).abs()
+    assert err.max().item() < 1.5e-2 * want.abs().max().item(), err.max().item()      # two extra bf16 roundings of the partial sums

@@ -194,3 +194,4 @@ def test_fused_encoder_routes_the_32_channel_convs():
         routed += sum("wp" in f for f in (b.c1, b.c2, *b.dil, b.c3, b.c4, b.pw, b.skip))
     assert routed == 2 + 3 * 5            # firstconv[2], firstconv[4]; block1, interblock1[0], block2 (c = 32): conv1, conv2, dil[0..2]
     assert "wp" not in enc.first[0] and all("wp" not in f for f in enc.last)
+    assert not any(hasattr(b, "c3_windows") for b in blocks)       # the chained-window conv3 is built but switched off (slower)
