@@ -20,6 +20,7 @@ from .synthetic import synthetic_batch
 class _StereoBase(LightningModule):
     predict_normal = False
     train_supported = False
+    data_seed_offset = 0              # Trainer.fit sets rank * const under torchrun: every rank draws its own synthetic pairs
 
     def _common_init(self, option):
         from .losses import LossModel
@@ -150,11 +151,45 @@ class _StereoBase(LightningModule):
             raise ValueError(f"input size {h}x{w}: this model needs at least {4 * self.min_quarter_size} pixels per side")
 
     def refresh(self):
-        """Re-pack kernel-layout weights after parameters changed (load_state_dict calls it)."""
+        """Re-pack kernel-layout weights after parameters changed.  The eval-mode plans (folded BatchNorm running statistics +
+        packed weights of PSMNetHGAggregation / ANM / CostVolumeSDP, the fused encoder copy) are built lazily on the first eval
+        forward; load_state_dict(), every train()/eval() transition and every .to()/.cuda()/.half() (``_apply``) drop them, so
+        eval -> train N steps -> eval never runs on pre-training weights."""
         self.__dict__.pop("_enc_fused", None)
+        self.__dict__.pop("_in_buf", None)
         for m in self.modules():
             if m is not self and hasattr(m, "refresh"):
                 m.refresh()
+
+    def train(self, mode: bool = True):
+        self.refresh()                       # an optimizer step may have happened since the plans were packed
+        return super().train(mode)
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        self.refresh()
+        return out
+
+    def reference_init(self):
+        """Weight initialisation of the reference constructors (src/model/stereodpnet/mainmodel.py:49-64 and the loops inside
+        the hourglass / aggregation / PSMNet encoder, stereodpnet/modules.py:229-239,298-308, psmnet/modules.py:112-127):
+        N(0, sqrt(2 / (prod(kernel) * C_out))) for every Conv2d / Conv3d / ConvTranspose3d -- this includes, as in the
+        reference, the zero-initialised `conv_offset` convolutions of the deformable layers, whose offsets are therefore
+        non-zero at random init -- BatchNorm weight 1 / bias 0, Linear bias 0.  Convolution biases, PReLU slopes, the
+        InstanceNorm affine and the DeformConvPack weight Parameter keep their module defaults, as they do in the reference."""
+        import math
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.Conv3d, nn.ConvTranspose3d)):
+                n = m.out_channels
+                for k in m.kernel_size:
+                    n *= k
+                m.weight.data.normal_(0, math.sqrt(2.0 / n))
+            elif isinstance(m, (nn.BatchNorm2d, nn.BatchNorm3d)):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+            elif isinstance(m, nn.Linear):
+                m.bias.data.zero_()
+        self.refresh()
 
     @staticmethod
     def convert_checkpoint_keys(state_dict):
@@ -181,7 +216,8 @@ class _StereoBase(LightningModule):
     def _synthetic_loader(self, training, batch_size):
         h, w = getattr(self.option, "synthetic_size", (448, 448))
         n = int(getattr(self.option, "synthetic_batches", 2))
-        return [synthetic_batch(batch_size, h, w, training=training, seed=i) for i in range(n)]
+        off = int(self.data_seed_offset)
+        return [synthetic_batch(batch_size, h, w, training=training, seed=off + i) for i in range(n)]
 
     def train_dataloader(self):
         return self._synthetic_loader(True, self.option.batch_size)
@@ -221,6 +257,7 @@ class STEREODPNET(_StereoBase):
         self.aggregation = M.PSMNetHGAggregation(option.model.inplanes)
         self.normal_estimator = M.ANM(option, self.mindisp, self.maxdisp) if self.predict_normal else None
         self.regression_layer = M.disp_regression(self.mindisp, self.maxdisp, self.level)
+        self.reference_init()
 
 
 class PSMNET(_StereoBase):
@@ -234,3 +271,4 @@ class PSMNET(_StereoBase):
         self.cost_volume = M.CostVolumePSM(option, self.mindisp, self.maxdisp)
         self.aggregation = M.PSMNetHGAggregation(option)
         self.regression_layer = M.disp_regression(self.mindisp, self.maxdisp, self.level)
+        self.reference_init()

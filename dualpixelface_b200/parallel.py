@@ -2,7 +2,8 @@
 
 The path shards by independent image pairs (SURVEY.md 8e): inference needs NO data-path collective (weak scaling);
 training adds one exchange per step, the gradient all-reduce (3.67 M / 5.22 M fp32 parameters = 14.7 / 20.9 MB), issued
-per bucket as soon as the bucket's gradients exist so that it overlaps the rest of the backward.  A single
+per bucket from post-accumulate-grad hooks as soon as the bucket's gradients exist, so that it overlaps the rest of the
+backward (``GradSync``); with `accelerator: "ddp"` the BatchNorm partial sums are all-reduced too (train_ops.set_sync_bn).  A single
 high-resolution pair (BASELINE config 5) is split into row tiles with per-layer halo exchange between row neighbours;
 ``row_tiles`` / ``exchange_row_halo`` are the host-side pieces of that path.
 """
@@ -45,32 +46,85 @@ def make_buckets(params: Sequence[torch.nn.Parameter], bucket_bytes: int = 8 << 
     return buckets
 
 
-def make_grad_sync(model: torch.nn.Module, bucket_bytes: int = 8 << 20, group=None) -> Callable[[torch.nn.Module], None]:
-    """Returns f(model) that averages gradients over ranks: flatten each bucket, async all-reduce (SUM), unflatten / world.
+class GradSync:
+    """Bucketed gradient all-reduce that overlaps the backward pass.
 
-    All buckets are launched before any is waited on, so the collectives pipeline on the NCCL stream.
+    Every bucket owns a persistent flat fp32 buffer.  A post-accumulate-grad hook per parameter copies the finished gradient
+    into its slice of the bucket (no torch.cat); the hook that completes a bucket launches its asynchronous all-reduce (SUM)
+    right there, i.e. WHILE autograd is still running the backward of the earlier layers (buckets are filled in reverse
+    registration order, the order in which gradients become ready).  ``sync()`` -- called once after ``backward()`` -- launches
+    the buckets that did not fill (parameters without a gradient this step contribute zeros), waits for all of them and writes
+    the averaged gradients back with one multi-tensor copy per bucket.  ``launched_in_backward`` counts the buckets whose
+    collective was issued from a hook (tests assert it is > 0).
     """
-    buckets = make_buckets(list(model.parameters()), bucket_bytes)
 
-    def sync(_model=None):
-        world = dist.get_world_size(group)
-        pending = []
-        for bucket in buckets:
-            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            pending.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, bucket))
-        for work, flat, bucket in pending:
-            work.wait()
-            flat.div_(world)
-            off = 0
+    def __init__(self, model: torch.nn.Module, bucket_bytes: int = 8 << 20, group=None):
+        self.group = group
+        self.buckets = make_buckets(list(model.parameters()), bucket_bytes)
+        self.flat, self.views, self.where = [], [], {}
+        for bi, bucket in enumerate(self.buckets):
+            n = sum(p.numel() for p in bucket)
+            flat = torch.zeros(n, device=bucket[0].device, dtype=torch.float32)
+            off, views = 0, []
+            for pi, p in enumerate(bucket):
+                views.append(flat[off:off + p.numel()].view_as(p))
+                self.where[p] = (bi, pi)
+                off += p.numel()
+            self.flat.append(flat)
+            self.views.append(views)
+        self._ready = [set() for _ in self.buckets]
+        self._work = [None] * len(self.buckets)
+        self.launched_in_backward = 0
+        self._handles = [p.register_post_accumulate_grad_hook(self._hook) for b in self.buckets for p in b]
+
+    def _launch(self, bi: int):
+        self._work[bi] = dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _hook(self, p: torch.nn.Parameter):
+        bi, pi = self.where[p]
+        if self._work[bi] is not None or pi in self._ready[bi]:
+            return                                       # second accumulation into the same grad: picked up by sync()'s fallback
+        self.views[bi][pi].copy_(p.grad)
+        self._ready[bi].add(pi)
+        if len(self._ready[bi]) == len(self.buckets[bi]):
+            self._launch(bi)
+            self.launched_in_backward += 1
+
+    def __call__(self, _model=None):
+        world = dist.get_world_size(self.group)
+        for bi, bucket in enumerate(self.buckets):       # buckets that never filled: absent gradients count as zeros
+            if self._work[bi] is None:
+                for pi, p in enumerate(bucket):
+                    if pi not in self._ready[bi]:
+                        if p.grad is None:
+                            self.views[bi][pi].zero_()
+                        else:
+                            self.views[bi][pi].copy_(p.grad)
+                self._launch(bi)
+        for bi, bucket in enumerate(self.buckets):
+            self._work[bi].wait()
+            self.flat[bi].div_(world)
             for p in bucket:
-                n = p.numel()
                 if p.grad is None:
                     p.grad = torch.empty_like(p)
-                p.grad.copy_(flat[off:off + n].view_as(p))
-                off += n
+            torch._foreach_copy_([p.grad for p in bucket], self.views[bi])
+            self._work[bi] = None
+            self._ready[bi].clear()
 
-    return sync
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+
+
+def make_grad_sync(model: torch.nn.Module, bucket_bytes: int = 8 << 20, group=None) -> GradSync:
+    """Install the overlapping bucketed gradient all-reduce on `model`; call the returned object once after backward()."""
+    return GradSync(model, bucket_bytes, group)
+
+
+def broadcast_module_state(model: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Rank `src`'s parameters and buffers to every rank (what DDP does at construction), so that replicas start identical."""
+    for t in list(model.parameters()) + list(model.buffers()):
+        dist.broadcast(t.data, src, group=group)
 
 
 def row_tiles(height: int, world: int, unit: int = 16) -> List[Tuple[int, int]]:

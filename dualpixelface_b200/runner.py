@@ -74,13 +74,51 @@ def model_selector(option, root: Path | str = "."):
     """src/model/<name>/mainmodel.py must define class <NAME upper> (model_selector.py:8-28 of the reference)."""
     ns = run_path(str(Path(root) / "src" / "model" / option.model_name / "mainmodel.py"))
     model = ns[option.model_name.upper()](option)
-    if option.load_model is not None and option.mode != "train":
-        ckpt = torch.load(option.load_model, map_location="cpu")
-        sd = ckpt.get("state_dict", ckpt.get("model"))
-        if sd is None:
-            raise NotImplementedError("wrong checkpoint")
+    # The reference guards this with `option.mode is not 'train'` (model_selector.py:18) -- an identity comparison with a
+    # literal that is true for every config string read from JSON, so a given --load_model is loaded in EVERY mode
+    # (fine-tuning / resuming in train mode included).  Same behaviour here, stated instead of accidental.
+    if option.load_model is not None:
+        sd = load_checkpoint_state(option.load_model)
         model.load_state_dict(sd, strict=option.load_strict)
     return model
+
+
+class _AnyObject:
+    """Stand-in for classes a Lightning checkpoint pickles next to the weights (the reference calls save_hyperparameters(),
+    so 'hyper_parameters' holds its config object `config_.config_manager.obj`, not importable here)."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {"state": state})
+
+
+def load_checkpoint_state(path):
+    """state_dict of a checkpoint file: the repo's own {'state_dict', 'epoch'} files, the reference's released
+    pytorch_lightning checkpoints ({'state_dict', 'hyper_parameters': <pickled config object>, 'callbacks', ...}) and plain
+    {'model': ...} files.  Tensors-only files load with the safe `weights_only=True`; a file that pickles foreign classes is
+    re-read with an unpickler that maps every class it cannot import to an inert stand-in, and only 'state_dict' is kept."""
+    import pickle
+    try:
+        ckpt = torch.load(path, map_location="cpu", weights_only=True)
+    except pickle.UnpicklingError:
+        class _Unpickler(pickle.Unpickler):
+            def find_class(self, module, name):
+                if module.split(".")[0] in ("torch", "collections", "numpy", "builtins", "_codecs"):
+                    return super().find_class(module, name)
+                return _AnyObject
+
+        class _Pickle:
+            Unpickler = _Unpickler
+            __name__ = "pickle"
+            load = staticmethod(lambda f, **kw: _Unpickler(f, **kw).load())
+
+        ckpt = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_Pickle)
+    sd = ckpt.get("state_dict", ckpt.get("model")) if isinstance(ckpt, dict) else None
+    if sd is None:
+        raise NotImplementedError("wrong checkpoint")
+    return {k: v for k, v in sd.items() if torch.is_tensor(v)}
 
 
 def optimizer_selector(params, option):
@@ -115,6 +153,13 @@ class Trainer:
     def __init__(self, max_epochs=1, device="cuda", workspace_path=None, grad_sync=None):
         self.max_epochs, self.device, self.workspace_path, self.grad_sync = max_epochs, device, workspace_path, grad_sync
 
+    @staticmethod
+    def _rank_world():
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
+
     def test(self, model, verbose=True):
         model.to(self.device).eval()
         outs = []
@@ -127,6 +172,13 @@ class Trainer:
 
     def fit(self, model):
         model.to(self.device).train()
+        rank, world = self._rank_world()
+        if world > 1:
+            import torch.distributed as dist
+            from .parallel import broadcast_module_state
+            broadcast_module_state(model)                      # replicas start identical (what DDP does at construction)
+            if hasattr(model, "data_seed_offset"):
+                model.data_seed_offset = rank * 100003         # every rank draws its own synthetic pairs
         opts, scheds = model.configure_optimizers()
         for epoch in range(self.max_epochs):
             model.current_epoch = epoch
@@ -142,6 +194,8 @@ class Trainer:
                 print(f"epoch {epoch} step {model.global_step}: loss {float(out['loss'].detach()):.4f}" + (f" ({logs})" if logs else ""))
             for s in scheds:
                 s.step()
-            if self.workspace_path:
+            if self.workspace_path and rank == 0:              # one writer; the other ranks wait so nobody reads a partial file
                 torch.save({"state_dict": model.state_dict(), "epoch": epoch},
                            Path(self.workspace_path) / f"checkpoint_epoch={epoch:02d}.ckpt")
+            if world > 1:
+                dist.barrier()

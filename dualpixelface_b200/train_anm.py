@@ -19,7 +19,7 @@ from .layers import KIND_3x3x3, TCConv3d
 from .ops_dcn_bwd import DCNFn
 from .ops_tail import anm_tail
 from .ops_wgrad import conv3d_wgrad
-from .train_ops import _affine_act, _bn_bwd, _npix
+from .train_ops import _affine_act, _bn_bwd, _npix, batch_stats
 
 
 class GatherFn(Function):
@@ -81,10 +81,7 @@ class BNActFn(Function):
 
     @staticmethod
     def forward(ctx, z, gamma, beta, conv_bias, bn):
-        c, n = z.shape[-1], _npix(z)
-        st = ops.channel_stats(z.view(1, n, c))[0]
-        mean = st[:, 0] / n
-        var = (st[:, 1] / n - mean * mean).clamp_min(0.0)
+        mean, var, n = batch_stats(z)
         inv_std = torch.rsqrt(var + bn.eps)
         a = (gamma.float() * inv_std).contiguous()
         b = (beta.float() - mean * a).contiguous()

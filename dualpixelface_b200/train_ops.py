@@ -30,6 +30,43 @@ def _npix(t):
     return t.numel() // t.shape[-1]
 
 
+# SyncBN (the reference's `accelerator: "ddp"` sets Trainer(sync_batchnorm=True), config_/config_manager.py:57, main.py:55):
+# when enabled, the per-channel partial sums of every train-mode BatchNorm on the 3-D path (forward: sum z, sum z^2; backward:
+# sum g, sum g*z) are all-reduced over the data-parallel group, so that the statistics are those of the GLOBAL batch.  The
+# tensors are [2C] fp32 (256-512 B); they are issued on the compute stream's NCCL communicator, in program order on every rank.
+SYNC_BN = {"enabled": False, "group": None}
+
+
+def set_sync_bn(enabled: bool, group=None):
+    SYNC_BN["enabled"], SYNC_BN["group"] = bool(enabled), group
+
+
+def _sync_world() -> int:
+    import torch.distributed as dist
+    if SYNC_BN["enabled"] and dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(SYNC_BN["group"])
+    return 1
+
+
+def _sync_sums(t: torch.Tensor) -> torch.Tensor:
+    """In-place SUM all-reduce of BatchNorm partial sums when SyncBN is on; identity otherwise."""
+    if _sync_world() > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=SYNC_BN["group"])
+    return t
+
+
+def batch_stats(z: torch.Tensor):
+    """(mean, biased var, global element count per channel) of a channels-last bf16 activation over all positions of the
+    (global, when SyncBN is on) batch."""
+    c, n = z.shape[-1], _npix(z)
+    st = _sync_sums(ops.channel_stats(z.view(1, n, c))[0])
+    n = n * _sync_world()
+    mean = st[:, 0] / n
+    var = (st[:, 1] / n - mean * mean).clamp_min(0.0)
+    return mean, var, n
+
+
 def _affine_act(z, scale, bias, res, slope):
     y = torch.empty_like(z)
     _lib.check(ops.lib().dpf_affine_act(ops._p(z), ops._p(scale), ops._p(bias), ops._p(res), ops._p(y), _npix(z), z.shape[-1],
@@ -42,14 +79,19 @@ def _bn_bwd(dy, y, z, a, mean, inv_std, relu, want_dres):
     sums = torch.empty(2 * c, device=z.device, dtype=torch.float32)
     _lib.check(ops.lib().dpf_bn_bwd_reduce(ops._p(dy), ops._p(y), ops._p(z), ops._p(sums), n, c, int(relu), ops._stream()),
                "dpf_bn_bwd_reduce")
+    # SyncBN: the mean-gradient terms of dz are sums over the GLOBAL batch; dgamma / dbeta stay LOCAL sums (the gradient
+    # all-reduce averages them like every other parameter gradient -- the convention of torch.nn.SyncBatchNorm)
+    dgamma, dbeta = inv_std * (sums[c:] - mean * sums[:c]), sums[:c].clone()
+    _sync_sums(sums)
+    ng = n * _sync_world()
     s1, s2 = sums[:c], sums[c:]
     centred = s2 - mean * s1
-    coef = torch.cat([a, s1 / n, inv_std * inv_std * centred / n, mean]).contiguous()
+    coef = torch.cat([a, s1 / ng, inv_std * inv_std * centred / ng, mean]).contiguous()
     dz = torch.empty_like(z)
     dres = torch.empty_like(z) if want_dres else None
     _lib.check(ops.lib().dpf_bn_bwd_apply(ops._p(dy), ops._p(y), ops._p(z), ops._p(coef), ops._p(dz), ops._p(dres), n, c, int(relu),
                                           ops._stream()), "dpf_bn_bwd_apply")
-    return dz, dres, inv_std * centred, s1          # dz, dres, dgamma, dbeta
+    return dz, dres, dgamma, dbeta
 
 
 def _wgrad(x, dz, weight, kind):
@@ -81,10 +123,7 @@ class ConvBNAct(Function):
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, residual, cfg: LayerCfg):
         z = TCConv3d(weight, cfg.kind, transposed=cfg.kind == KIND_T2)(x)
-        c, n = z.shape[-1], _npix(z)
-        st = ops.channel_stats(z.view(1, n, c))[0]
-        mean = st[:, 0] / n
-        var = (st[:, 1] / n - mean * mean).clamp_min(0.0)
+        mean, var, n = batch_stats(z)
         eps = cfg.bn.eps if cfg.bn is not None else 1e-5
         inv_std = torch.rsqrt(var + eps)
         a = (gamma.float() * inv_std).contiguous()

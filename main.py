@@ -24,8 +24,13 @@ def main():
     grad_sync = None
     if int(os.environ.get("WORLD_SIZE", 1)) > 1:
         from dualpixelface_b200.parallel import init_distributed, make_grad_sync
+        from dualpixelface_b200.train_ops import set_sync_bn
         init_distributed()
-        grad_sync = make_grad_sync(model)
+        model.to(f"cuda:{local_rank}")
+        if opt.sync_batch and opt.mode == "train":             # accelerator "ddp" => Trainer(sync_batchnorm=True) in the reference
+            set_sync_bn(True)                                  # 3-D path: partial sums all-reduced inside the BN Functions
+            model.feature_extraction = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model.feature_extraction)
+        grad_sync = make_grad_sync(model)                      # hooks launch the bucket all-reduces during backward
     runner = Trainer(max_epochs=opt.epoch, device=f"cuda:{local_rank}",
                      workspace_path=opt.workspace_path if opt.mode == "train" else None, grad_sync=grad_sync)
     if opt.mode == "train":

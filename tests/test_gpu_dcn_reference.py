@@ -22,8 +22,12 @@ ARGS = (3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1)     # kernel, stride, pad, 
 
 @pytest.fixture(scope="module")
 def dcn():
-    if not REF_SO.is_file():
-        pytest.skip("oracle/_ref/DCN.so not built (python oracle/build_ref_dcn.py needs /root/reference)")
+    if not REF_SO.is_file():                    # never skip: this is the only pin of the D3D restatement -- build it or fail
+        from oracle.build_ref_dcn import build
+        if build() is None or not REF_SO.is_file():
+            pytest.fail("oracle/_ref/DCN.so is missing and /root/reference is not present to build it: run "
+                        "`python -c 'import __graft_entry__ as g; g.build()'` where the reference sources exist; the .so is "
+                        "git-ignored but travels to the GPU box with the snapshot")
     loader = importlib.machinery.ExtensionFileLoader("DCN", str(REF_SO))
     mod = importlib.util.module_from_spec(importlib.util.spec_from_loader("DCN", loader))
     loader.exec_module(mod)

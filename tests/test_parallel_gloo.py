@@ -25,7 +25,7 @@ def _worker(rank, world, port, ret):
     try:
         torch.manual_seed(0)
         model = torch.nn.Sequential(torch.nn.Conv3d(4, 8, 3), torch.nn.BatchNorm3d(8), torch.nn.Conv3d(8, 1, 1))
-        sync = parallel.make_grad_sync(model, bucket_bytes=1024)
+        sync = parallel.make_grad_sync(model, bucket_bytes=100)
         x = torch.randn(2, 4, 5, 6, 7, generator=torch.Generator().manual_seed(10 + rank))
         model(x).square().mean().backward()
         local = [p.grad.clone() for p in model.parameters()]
@@ -34,6 +34,22 @@ def _worker(rank, world, port, ret):
         for g, lst in zip(local, gathered):
             dist.all_gather(lst, g)
         ok_grad = all(torch.allclose(p.grad, sum(lst) / world, atol=1e-6) for p, lst in zip(model.parameters(), gathered))
+        # the collectives of the filled buckets were issued from the hooks, i.e. during backward (not from sync())
+        ok_hooks = sync.launched_in_backward == len(sync.buckets) >= 2
+        # second step: state was reset; a parameter without a gradient contributes zeros; set_to_none grads are re-created
+        for p in model.parameters():
+            p.grad = None
+        head = torch.nn.Conv3d(8, 1, 1)
+        head.weight.data.copy_(model[2].weight.data); head.bias.data.copy_(model[2].bias.data)
+        y = model[1](model[0](x))
+        (y.detach() * 0 + head(y)).mean().backward()            # model[2] gets no gradient in this step
+        local2 = [None if p.grad is None else p.grad.clone() for p in model.parameters()]
+        sync(model)
+        for p, g in zip(model.parameters(), local2):
+            g = torch.zeros_like(p) if g is None else g
+            lst = [torch.zeros_like(g) for _ in range(world)]
+            dist.all_gather(lst, g)
+            ok_grad = ok_grad and torch.allclose(p.grad, sum(lst) / world, atol=1e-6)
         # row-tile halo exchange: global image rows 0..7 split in two, halo 1
         full = torch.arange(8.0).view(1, 8, 1).repeat(1, 1, 3)
         mine = full[:, rank * 4:(rank + 1) * 4]
@@ -42,7 +58,7 @@ def _worker(rank, world, port, ret):
                           full[:, (rank + 1) * 4:(rank + 1) * 4 + 1] if rank + 1 < world else torch.zeros(1, 1, 3)], 1)
         got_w = parallel.exchange_row_halo(mine.contiguous(), 1, 1, wrap=True)
         want_w = torch.cat([full[:, (rank * 4 - 1) % 8].unsqueeze(1), mine, full[:, ((rank + 1) * 4) % 8].unsqueeze(1)], 1)
-        ret[rank] = bool(ok_grad and torch.equal(got, want) and torch.equal(got_w, want_w))
+        ret[rank] = (bool(ok_grad), bool(ok_hooks), bool(torch.equal(got, want) and torch.equal(got_w, want_w)))
     finally:
         dist.destroy_process_group()
 
@@ -52,4 +68,4 @@ def test_grad_sync_and_halo_exchange_world2():
     mgr = mp.get_context("spawn").Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
-    assert dict(ret) == {0: True, 1: True}
+    assert dict(ret) == {0: (True, True, True), 1: (True, True, True)}      # (gradients, overlap, halos)
