@@ -12,9 +12,17 @@
 // as the bf16 A tile in the UMMA no-swizzle K-major layout; the tap's weight tile [CINP x 64] is streamed next to it by a
 // 1-D TMA bulk copy.  One elected lane issues the tcgen05.mma; accumulators are double-buffered in TMEM so the
 // epilogue of a unit overlaps the gather of the next.
+//
+// Offsets (STAGED path, off_cstride a multiple of 4 and >= 84): the kernel is bound by L1 data-pipe wavefronts (ncu r01: 74 % of
+// the LSU wavefront peak), and a quarter of them were the OFFSET loads: 3 scalar LDGs per (voxel, tap) in which the 4 lanes of a
+// voxel read the same word, i.e. 8 lines = 8 wavefronts per warp instruction for 32 useful bytes (profiles/r02_dcn3d_source.txt).
+// The unit's 256 x 81 offsets are now staged in shared memory by 16-byte cp.async in two halves (taps 0-11 | taps 12-26, each
+// half re-filled for the NEXT unit while the other half is in use), with voxel pitches of 36 / 52 words so that a warp's 8 voxels
+// hit 8 different banks: an offset read is one LDS wavefront instead of 8.
 #include "../../include/dpf_sm100.h"
 #include "dpf_common.cuh"
 #include "dpf_ptx.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -32,6 +40,11 @@ constexpr int kBlocks = 2;                                    // GEMM blocks (12
 #endif
 constexpr int kStages = DPF_DCN_STAGES;
 constexpr int kTaps = 27;
+// staged offsets: half A = taps 0..11 (36 floats per voxel), half B = taps 12..26 (45 floats, copied as 48 and padded to 52)
+constexpr int kSplitTap = 12;
+constexpr int kOffPitchA = 36, kOffPitchB = 52;              // words; 36 mod 32 = 4, 52 mod 32 = 20: 8 consecutive voxels -> 8 banks
+constexpr int kOffPiecesA = 9, kOffPiecesB = 12;             // 16-byte pieces per voxel
+constexpr int kOffBytes = 256 * (kOffPitchA + kOffPitchB) * 4;
 
 struct DcnParams {
   const __nv_bfloat16* x;
@@ -45,7 +58,7 @@ struct DcnParams {
   int nunits, tiles_h, tiles_w;
 };
 
-template <int CINP>
+template <int CINP, bool STAGED = false>
 struct DCfg {
   static constexpr int NCH = CINP / 8;
   static constexpr int KSTEPS = CINP / 16;
@@ -55,8 +68,11 @@ struct DCfg {
   static constexpr int W_TAP_BYTES = NCH * kNOut * 16;               // [chunk][64 rows][16 B]
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + W_TAP_BYTES;
   static constexpr int TMEM_COLS = 256;                              // 2 stages x 2 blocks x 64 columns
-  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 2 * kNOut * 4 + (2 * kStages + 4) * 8 + 16 + 128;
+  static constexpr int BASE_BYTES = kStages * STAGE_BYTES + 2 * kNOut * 4 + (2 * kStages + 4) * 8 + 16;
+  static constexpr int OFF_AT = (BASE_BYTES + 15) & ~15;             // staged offsets (16-byte aligned)
+  static constexpr int SMEM_BYTES = (STAGED ? OFF_AT + kOffBytes : BASE_BYTES) + 128;
   static_assert(CINP % 16 == 0, "CINP must be a multiple of 16");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
 
 // unit -> (d, h0, w0, b): depth fastest, so that consecutive units of a CTA share two of their three input planes
@@ -69,9 +85,42 @@ __device__ __forceinline__ void unit_coords(int unit, const DcnParams& p, int& d
   b = t / p.tiles_h;
 }
 
-template <int CINP>
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// producers only (16 warps): named barrier 1
+__device__ __forceinline__ void prod_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kProdWarps * 32) : "memory"); }
+
+// cp.async one half (pieces per voxel NP, first float F0, smem pitch PITCH words) of a unit's offsets
+template <int NP, int F0, int PITCH>
+__device__ __forceinline__ void stage_offsets(const DcnParams& p, int unit, int ptid, float* s_dst) {
+  int ud, uh0, uw0, ub;
+  {
+    ud = unit % p.D;
+    int t = unit / p.D;
+    uw0 = (t % p.tiles_w) * 16;
+    t /= p.tiles_w;
+    uh0 = (t % p.tiles_h) * 16;
+    ub = t / p.tiles_h;
+  }
+  const long long plane = (static_cast<long long>(ub) * p.D + ud) * p.H;
+  const uint32_t dst0 = smem_u32(s_dst);
+  for (int i = ptid; i < 256 * NP; i += kProdWarps * 32) {
+    const int r = i / NP, q = i - r * NP;
+    const int hh = uh0 + (r >> 4), ww = uw0 + (r & 15);
+    const bool ok = (hh < p.H) && (ww < p.W);
+    const float* src = ok ? p.offset + ((plane + hh) * p.W + ww) * p.off_cstride + F0 + 4 * q : p.offset;
+    cp_async16_zfill(dst0 + (r * PITCH + 4 * q) * 4, src, ok);
+  }
+  cp_async_commit();
+}
+
+template <int CINP, bool STAGED>
 __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constant__ DcnParams p) {
-  using C = DCfg<CINP>;
+  using C = DCfg<CINP, STAGED>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
   uint8_t* s_stage = smem;
@@ -82,6 +131,8 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
   uint64_t* bar_tfull = bar_empty + kStages;
   uint64_t* bar_tempty = bar_tfull + 2;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  float* s_offA = reinterpret_cast<float*>(smem + C::OFF_AT);            // [256][kOffPitchA]   (STAGED only)
+  float* s_offB = s_offA + 256 * kOffPitchA;                             // [256][kOffPitchB]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -130,6 +181,12 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
     const char* xbytes = reinterpret_cast<const char*>(p.x);
     const uint32_t lane_off = (lane_live ? cq : 0) * 32u;
     uint32_t g = 0;
+    if (STAGED && unit_lo < unit_hi) {                       // both halves of the first unit
+      stage_offsets<kOffPiecesA, 0, kOffPitchA>(p, unit_lo, ptid, s_offA);
+      stage_offsets<kOffPiecesB, 3 * kSplitTap, kOffPitchB>(p, unit_lo, ptid, s_offB);
+      cp_async_wait<1>();                                    // half A landed (half B may still be in flight)
+      prod_barrier();
+    }
     for (int unit = unit_lo; unit < unit_hi; ++unit) {
       // unit = 16 x 16 spatial tile of one depth plane; row r of the unit -> (h0 + r/16, w0 + r%16).  Voxel
       // coordinates of this thread's PASSES rows are decoded once per unit and reused by all 27 taps.
@@ -150,21 +207,39 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
       // otherwise be two dependent memory round trips per (voxel, tap)
       const float* obase[PASSES];
       float onext[PASSES][3];
+      if (!STAGED) {
 #pragma unroll
-      for (int ps = 0; ps < PASSES; ++ps) {
-        obase[ps] = p.offset + static_cast<size_t>(vbase + (ud * H + vh[ps]) * W + vw[ps]) * p.off_cstride;
-        onext[ps][0] = __ldg(obase[ps] + 0); onext[ps][1] = __ldg(obase[ps] + 1); onext[ps][2] = __ldg(obase[ps] + 2);
+        for (int ps = 0; ps < PASSES; ++ps) {
+          obase[ps] = p.offset + static_cast<size_t>(vbase + (ud * H + vh[ps]) * W + vw[ps]) * p.off_cstride;
+          onext[ps][0] = __ldg(obase[ps] + 0); onext[ps][1] = __ldg(obase[ps] + 1); onext[ps][2] = __ldg(obase[ps] + 2);
+        }
       }
       for (int tap = 0; tap < kTaps; ++tap, ++g) {
         const int stage = g % kStages;
         const uint32_t ph = (g / kStages) & 1u;
         float ocur[PASSES][3];
+        if (STAGED) {
+          if (tap == kSplitTap) {
+            // half B of this unit has landed and every producer is past its last read of half A: refill A for the next unit
+            cp_async_wait<0>();
+            prod_barrier();
+            if (unit + 1 < unit_hi) stage_offsets<kOffPiecesA, 0, kOffPitchA>(p, unit + 1, ptid, s_offA);
+          }
+          const uint32_t so = (tap < kSplitTap) ? smem_u32(s_offA + 3 * tap) : smem_u32(s_offB + 3 * (tap - kSplitTap));
+          const int pitch = (tap < kSplitTap) ? kOffPitchA : kOffPitchB;
 #pragma unroll
-        for (int ps = 0; ps < PASSES; ++ps) {
-          ocur[ps][0] = onext[ps][0]; ocur[ps][1] = onext[ps][1]; ocur[ps][2] = onext[ps][2];
-          if (tap + 1 < kTaps) {
-            const float* on = obase[ps] + (tap + 1) * 3;
-            onext[ps][0] = __ldg(on + 0); onext[ps][1] = __ldg(on + 1); onext[ps][2] = __ldg(on + 2);
+          for (int ps = 0; ps < PASSES; ++ps) {
+            const uint32_t o = so + static_cast<uint32_t>((ps * kVoxPerPass + vsub) * pitch) * 4u;
+            ocur[ps][0] = lds_f32(o); ocur[ps][1] = lds_f32(o + 4); ocur[ps][2] = lds_f32(o + 8);
+          }
+        } else {
+#pragma unroll
+          for (int ps = 0; ps < PASSES; ++ps) {
+            ocur[ps][0] = onext[ps][0]; ocur[ps][1] = onext[ps][1]; ocur[ps][2] = onext[ps][2];
+            if (tap + 1 < kTaps) {
+              const float* on = obase[ps] + (tap + 1) * 3;
+              onext[ps][0] = __ldg(on + 0); onext[ps][1] = __ldg(on + 1); onext[ps][2] = __ldg(on + 2);
+            }
           }
         }
         mbar_wait(&bar_empty[stage], ph ^ 1u);
@@ -251,6 +326,12 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_full[stage]);
       }
+      if (STAGED && unit + 1 < unit_hi) {
+        // half A of the next unit has landed; every producer is past its last read of half B: refill B for the next unit
+        cp_async_wait<0>();
+        prod_barrier();
+        stage_offsets<kOffPiecesB, 3 * kSplitTap, kOffPitchB>(p, unit + 1, ptid, s_offB);
+      }
     }
   } else if (warp == kMmaWarp) {
     // ======================================= MMA issuer =====================================================
@@ -336,10 +417,10 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
   }
 }
 
-template <int CINP>
+template <int CINP, bool STAGED>
 int launch_dcn(const DcnParams& p, cudaStream_t st) {
-  using C = DCfg<CINP>;
-  auto kern = dcn3d_kernel<CINP>;
+  using C = DCfg<CINP, STAGED>;
+  auto kern = dcn3d_kernel<CINP, STAGED>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -378,6 +459,10 @@ extern "C" int dpf_dcn3d_fwd(const void* x, const float* offset, const void* w, 
   p.tiles_w = (W + 15) / 16;
   p.nunits = B * D * p.tiles_h * p.tiles_w;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (Cin_pad == 32) return launch_dcn<32>(p, st);
-  return launch_dcn<64>(p, st);
+  // staged offsets need 16-byte aligned voxel rows that hold floats 0..83 (the 81 real offsets + padding)
+  static int staged_env = -1;
+  if (staged_env < 0) { const char* e = getenv("DPF_DCN_STAGED"); staged_env = e ? atoi(e) : 1; }
+  const bool staged = staged_env && off_cstride % 4 == 0 && off_cstride >= 84 && (reinterpret_cast<uintptr_t>(offset) & 15u) == 0;
+  if (Cin_pad == 32) return staged ? launch_dcn<32, true>(p, st) : launch_dcn<32, false>(p, st);
+  return staged ? launch_dcn<64, true>(p, st) : launch_dcn<64, false>(p, st);
 }

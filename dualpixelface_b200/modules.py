@@ -551,7 +551,7 @@ class ANM(nn.Module):
             idx, coord, minmax = ops.anm_select(disp.contiguous(), kinv, batch["abvalue"].float().contiguous(), self.levels, self.k)
             fv = ops.anm_gather(out3, idx, coord, minmax, 64)                          # [B,K,H4,W4,64]
             off1 = p["off1"](fv, shift=p["offb1"], out_f32=True)
-            f1 = ops.dcn3d(fv, off1, p["w1"], p["cpad1"], p["aff1"][0], p["aff1"][1], relu=True)
+            f1 = ops.dcn3d(fv, off1, p["w1"], p["cpad1"], p["aff1"][0], p["aff1"][1], relu=True, cin_real=self.deform_conv1.weight.shape[1])
             off2 = p["off2"](f1, shift=p["offb2"], out_f32=True)
             f2 = ops.dcn3d(f1, off2, p["w2"], p["cpad2"], p["aff2"][0], p["aff2"][1], relu=True)
             # shared 2-D normal convs on (b*k) slices: cuDNN, bf16 channels-last (adjacent op)

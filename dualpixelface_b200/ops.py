@@ -248,8 +248,9 @@ def anm_select(disp: torch.Tensor, kinv: torch.Tensor, abvalue: torch.Tensor, le
 
 
 def dcn3d(x: torch.Tensor, offset: torch.Tensor, w_packed: torch.Tensor, cin_pad: int, scale: Optional[torch.Tensor] = None,
-          shift: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
-    """3-D deformable conv 3x3x3 (stride 1, pad 1): x [B,D,H,W,Cs] bf16, offset [B,D,H,W,>=81] fp32 -> [B,D,H,W,64] bf16."""
+          shift: Optional[torch.Tensor] = None, relu: bool = False, cin_real: Optional[int] = None) -> torch.Tensor:
+    """3-D deformable conv 3x3x3 (stride 1, pad 1): x [B,D,H,W,Cs] bf16, offset [B,D,H,W,>=81] fp32 -> [B,D,H,W,64] bf16.
+    `cin_real` (<= cin_pad) is the layer's true input width; it only enters the algorithmic-FLOP accounting of the timing hook."""
     _req(x, torch.bfloat16, "x"); _req(offset, torch.float32, "offset"); _req(w_packed, torch.bfloat16, "w_packed")
     b, d, h, w, cs = x.shape
     assert offset.shape[:4] == (b, d, h, w) and offset.shape[-1] >= 81 and offset.is_contiguous()
@@ -257,7 +258,7 @@ def dcn3d(x: torch.Tensor, offset: torch.Tensor, w_packed: torch.Tensor, cin_pad
     tm = _timing_begin()
     check(lib().dpf_dcn3d_fwd(_p(x), _p(offset), _p(w_packed), _p(scale), _p(shift), _p(y), b, d, h, w, cin_pad, cs,
                               offset.shape[-1], 64, int(relu), _stream()), "dpf_dcn3d_fwd")
-    _timing_end(tm, "dcn3d 64->64", 2.0 * 27 * 64 * 64 * b * d * h * w, "flop")
+    _timing_end(tm, "dcn3d_kernel<64>", 2.0 * 27 * (cin_real or cin_pad) * 64 * b * d * h * w, "flop")
     return y
 
 

@@ -19,7 +19,7 @@ from .layers import KIND_3x3x3, TCConv3d
 from .ops_dcn_bwd import DCNFn
 from .ops_tail import anm_tail
 from .ops_wgrad import conv3d_wgrad
-from .train_ops import _affine_act, _bn_bwd, _npix, batch_stats
+from .train_ops import _affine_act, _bn_bwd, _npix, _teacher, batch_stats
 
 
 class GatherFn(Function):
@@ -85,7 +85,7 @@ class BNActFn(Function):
         inv_std = torch.rsqrt(var + bn.eps)
         a = (gamma.float() * inv_std).contiguous()
         b = (beta.float() - mean * a).contiguous()
-        y = _affine_act(z, a, b, None, 0.0)
+        y = _teacher(bn, _affine_act(z, a, b, None, 0.0))
         if bn.track_running_stats:
             m = bn.momentum
             unb = var * (n / max(n - 1, 1))

@@ -67,6 +67,23 @@ def batch_stats(z: torch.Tensor):
     return mean, var, n
 
 
+# Test hook (tests/test_gpu_teacher_forced.py): {id(BatchNorm module): the ORACLE's output of that layer, channels-last bf16}.
+# A layer found here still runs its full forward on the kernels, but hands the oracle's activation downstream and to its own
+# backward (ReLU mask), so that a gradient comparison isolates the backward kernels from bf16-induced ReLU-mask flips and from
+# accumulated forward error.  TEACHER_ERR records the layer's own forward error against the teacher.  None in production.
+TEACHER = None
+TEACHER_ERR = {}
+
+
+def _teacher(bn, y):
+    if TEACHER is None or bn is None or id(bn) not in TEACHER:
+        return y
+    t = TEACHER[id(bn)]
+    assert t.shape == y.shape and t.dtype == y.dtype, (t.shape, y.shape)
+    TEACHER_ERR[id(bn)] = float((y.float() - t.float()).abs().max() / t.float().abs().max().clamp_min(1e-6))
+    return t.clone()
+
+
 def _affine_act(z, scale, bias, res, slope):
     y = torch.empty_like(z)
     _lib.check(ops.lib().dpf_affine_act(ops._p(z), ops._p(scale), ops._p(bias), ops._p(res), ops._p(y), _npix(z), z.shape[-1],
@@ -128,7 +145,7 @@ class ConvBNAct(Function):
         inv_std = torch.rsqrt(var + eps)
         a = (gamma.float() * inv_std).contiguous()
         b = (beta.float() - mean * a).contiguous()
-        y = _affine_act(z, a, b, residual, 0.0 if cfg.relu else 1.0)
+        y = _teacher(cfg.bn, _affine_act(z, a, b, residual, 0.0 if cfg.relu else 1.0))
         if cfg.bn is not None and cfg.bn.track_running_stats:
             m = cfg.bn.momentum
             cfg.bn.running_mean.mul_(1 - m).add_(mean, alpha=m)

@@ -254,10 +254,14 @@ def test_conv_transposed(ops, cin, cout, shape):
     assert strided_case(ops, cin, cout, shape, 12, transposed=True, residual=True) < 1e-2
 
 
-@pytest.mark.parametrize("cin", [35, 64])
-def test_dcn3d(ops, cin):
+@pytest.mark.parametrize("cin,shape,off_c", [(35, (2, 4, 10, 13), 81), (64, (2, 4, 10, 13), 81), (35, (2, 4, 10, 13), 96),
+                                             (64, (2, 4, 70, 69), 96), (35, (1, 4, 150, 101), 84)])
+def test_dcn3d(ops, cin, shape, off_c):
+    """off_c = 81: offsets read straight from global memory; off_c = 96 / 84 (16-byte aligned voxel rows): the staged path --
+    offsets double-buffered in shared memory by halves; the larger shapes give every CTA several work units, which exercises
+    the refill-while-in-use protocol of the two halves."""
     g = torch.Generator().manual_seed(13)
-    b, d, h, w = 2, 4, 10, 13
+    b, d, h, w = shape
     cpad, cs = 64, 64
     x = torch.randn(b, cin, d, h, w, generator=g).to(torch.bfloat16)
     off = (torch.rand(b, 81, d, h, w, generator=g) - 0.5) * 3.0                       # up to +-1.5 voxels, crosses borders
@@ -266,7 +270,9 @@ def test_dcn3d(ops, cin):
     want = F.relu(O.deform_conv3d(x.float(), off, wt.float(), bias))
     xp = torch.zeros(b, d, h, w, cs, dtype=torch.bfloat16)
     xp[..., :cin] = ndhwc(x)
-    got = ops.dcn3d(xp.cuda(), off.permute(0, 2, 3, 4, 1).contiguous().cuda(), ops.pack_conv_weight(wt.cuda(), cin_pad=cpad), cpad,
+    offp = torch.full((b, d, h, w, off_c), 7.0)                                       # pad channels: garbage that must not be read
+    offp[..., :81] = off.permute(0, 2, 3, 4, 1)
+    got = ops.dcn3d(xp.cuda(), offp.cuda(), ops.pack_conv_weight(wt.cuda(), cin_pad=cpad), cpad,
                     torch.ones(64).cuda(), bias.cuda(), relu=True)
     torch.cuda.synchronize()
     assert rel_err(from_ndhwc(got), want) < 2e-2        # the gathered A tile is rounded to bf16 before the MMA

@@ -195,3 +195,72 @@ def test_fused_encoder_routes_the_32_channel_convs():
     assert routed == 2 + 3 * 5            # firstconv[2], firstconv[4]; block1, interblock1[0], block2 (c = 32): conv1, conv2, dil[0..2]
     assert "wp" not in enc.first[0] and all("wp" not in f for f in enc.last)
     assert not any(hasattr(b, "c3_windows") for b in blocks)       # the chained-window conv3 is built but switched off (slower)
+
+
+def test_reference_weight_init_statistics():
+    """Constructors reproduce the reference initialisation (stereodpnet/mainmodel.py:49-64 + the hourglass loops): N(0, sqrt(2 /
+    (prod(kernel) * C_out))) for Conv2d / Conv3d / ConvTranspose3d -- including the re-randomised conv_offset of the deformable
+    layers -- BatchNorm weight 1 / bias 0; conv biases and the D3D weight Parameter keep their defaults."""
+    import math
+    from dualpixelface_b200.runner import load_config, model_selector
+    torch.manual_seed(1)
+    model = model_selector(load_config("train_faceDP", "pytest", make_dirs=False))
+    checked = 0
+    for name, m in model.named_modules():
+        if isinstance(m, (torch.nn.Conv2d, torch.nn.Conv3d, torch.nn.ConvTranspose3d)) and m.weight.numel() >= 4096:
+            want = math.sqrt(2.0 / (m.out_channels * math.prod(m.kernel_size)))
+            assert abs(float(m.weight.std()) / want - 1.0) < 0.08, (name, float(m.weight.std()), want)
+            assert abs(float(m.weight.mean())) < 0.1 * want, name
+            checked += 1
+        elif isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)):
+            assert float(m.weight.min()) == 1.0 == float(m.weight.max()) and float(m.bias.abs().max()) == 0.0
+    assert checked > 60
+    off = model.normal_estimator.deform_conv1.conv_offset
+    assert float(off.weight.std()) > 0.02 and float(off.bias.abs().max()) == 0.0      # probe in SURVEY 8a-7: std 0.030, bias 0
+
+
+def test_plan_caches_are_dropped_on_mode_change_and_move():
+    """the eval-mode plans (packed weights + folded running statistics) must not survive train()/eval()/.to()."""
+    from dualpixelface_b200.runner import load_config, model_selector
+    model = model_selector(load_config("eval_faceDP", "pytest", make_dirs=False))
+    def poison():
+        model.aggregation._plan = {"stale": 1}
+        model.normal_estimator._plan = {"stale": 1}
+        model.cost_volume._packed = {"stale": 1}
+        model.__dict__["_enc_fused"] = "stale"
+    def clean():
+        return (model.aggregation._plan is None and model.normal_estimator._plan is None and model.cost_volume._packed is None
+                and "_enc_fused" not in model.__dict__)
+    for change in (lambda: model.train(), lambda: model.eval(), lambda: model.to(torch.float32), lambda: model.float(),
+                   lambda: model.load_state_dict(model.state_dict())):
+        poison()
+        change()
+        assert clean()
+
+
+def test_lightning_style_checkpoint_loads(tmp_path):
+    """The reference's released checkpoints are pytorch_lightning files written after save_hyperparameters(): they pickle the
+    config object under 'hyper_parameters'.  torch >= 2.6 defaults to weights_only=True, which rejects that; the loader falls
+    back to an unpickler that stubs unknown classes and keeps only the tensors of 'state_dict'."""
+    import sys, types
+    from dualpixelface_b200.runner import load_checkpoint_state
+    mod = types.ModuleType("config_fake_manager")
+    class obj:                                             # stands in for config_.config_manager.obj
+        def __init__(self, d):
+            self.__dict__.update(d)
+    obj.__module__ = "config_fake_manager"; obj.__qualname__ = "obj"
+    mod.obj = obj
+    sys.modules["config_fake_manager"] = mod
+    sd = {"aggregation.dres0.0.0.weight": torch.randn(4, 3), "normal_estimator.grid": torch.zeros(2)}
+    path = tmp_path / "checkpoint_epoch=03.ckpt"
+    torch.save({"state_dict": sd, "epoch": 3, "hyper_parameters": {"option": obj({"mode": "train", "model": obj({"level": 8})})},
+                "pytorch-lightning_version": "1.4.9"}, path)
+    del sys.modules["config_fake_manager"]                  # the class is NOT importable at load time
+    got = load_checkpoint_state(path)
+    assert set(got) == set(sd) and torch.equal(got["aggregation.dres0.0.0.weight"], sd["aggregation.dres0.0.0.weight"])
+    plain = tmp_path / "plain.ckpt"
+    torch.save({"model": sd}, plain)
+    assert set(load_checkpoint_state(plain)) == set(sd)
+    torch.save({"weights": sd}, plain)
+    with pytest.raises(NotImplementedError):
+        load_checkpoint_state(plain)
