@@ -65,7 +65,7 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 
 def test_product_never_imports_the_oracle():
     """oracle/ is test infrastructure: nothing under dualpixelface_b200/, src/, main.py may import it (bench.py only in its
-    cpu_baseline / --impl reference legs, __graft_entry__ only in smoke())."""
+    cpu_baseline / --impl reference / gpu_eager_oracle baseline legs, __graft_entry__ only in smoke())."""
     import re
     from conftest import ROOT
     pat = re.compile(r"^\s*(from|import)\s+oracle\b", re.M)
@@ -73,5 +73,9 @@ def test_product_never_imports_the_oracle():
                  if pat.search(p.read_text())]
     offenders += [f for f in ("main.py",) if pat.search((ROOT / f).read_text())]
     assert offenders == []
+    # bench.py: only inside its two stated-BASELINE legs (the CPU port and the oracle's torch code run eagerly on the GPU), never in
+    # the functions that produce `value` / `e2e` / `train`
     bench = (ROOT / "bench.py").read_text()
-    assert len(pat.findall(bench)) == 1 and "def cpu_reference_pairs_per_s" in bench   # the single import lives in the CPU leg
+    funcs = re.split(r"^def ", bench, flags=re.M)
+    importing = sorted(f.split("(")[0] for f in funcs if pat.search(f))
+    assert importing == ["cpu_reference_pairs_per_s", "gpu_eager_oracle_block"]
