@@ -39,7 +39,8 @@ SIGNATURES = {
     "dpf_costvol_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int_p, c_void_p]),
     "dpf_asm_sample_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dpf_asm_blend_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "dpf_channel_stats": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p]),
+    "dpf_channel_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p]),
+    "dpf_channel_stats_ws_floats": (c_ll, [c_int, c_ll, c_int]),
     "dpf_conv3d_fwd": (c_int, [C.POINTER(ConvArgs), c_void_p]),
     "dpf_conv3d_weight_elems": (c_ll, [c_int, c_int, c_int]),
     "dpf_regress_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
@@ -58,6 +59,10 @@ SIGNATURES = {
     "dpf_dcn3d_bwd_data": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),
     "dpf_dcn3d_bwd_weight": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "dpf_conv2d_fwd": (c_int, [c_void_p] * 6 + [c_int] * 11 + [c_float, c_void_p]),
+    "dpf_conv2d_tc_npad": (c_int, [c_int]),
+    "dpf_conv2d_tc_weight_elems": (c_ll, [c_int, c_int]),
+    "dpf_conv2d_tc_fwd": (c_int, [c_void_p] * 6 + [c_int] * 11 + [c_float, c_void_p]),
+    "dpf_anm_tail_tile": (c_int, [c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
     "dpf_channel_max": (c_int, [c_void_p, c_void_p, C.c_longlong, c_int, c_void_p]),
     "dpf_fpn_merge": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "dpf_pyramid_cat": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p]),

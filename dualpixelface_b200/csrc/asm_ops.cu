@@ -64,17 +64,21 @@ __global__ void __launch_bounds__(256) asm_sample_kernel(const __nv_bfloat16* __
   }
 }
 
-// x [B,P,C] bf16 -> stats [B,C,2] (sum, sumsq).  grid (chunks, B), block 256 = (256/c8n) position lanes x c8n pieces.
-__global__ void __launch_bounds__(256) channel_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats,
-                                                            long long P, int C) {
-  extern __shared__ float red[];                 // [2][C]
+// x [B,P,C] bf16 -> stats [B,C,2] (sum, sumsq), DETERMINISTIC: no floating-point atomics anywhere.
+//   pass 1, grid (chunks, B), block 256 = (256/c8n) position lanes x c8n 16-byte pieces: every thread sums its positions in a
+//           fixed order, the block combines its lanes in lane order through shared memory and writes ONE partial row
+//           ws[b][chunk][2C];
+//   pass 2, grid B, block 2C: thread i adds the chunk partials of its column in chunk order.
+// The summation tree depends only on (P, C, chunks), never on scheduling, so the InstanceNorm / BatchNorm statistics -- and
+// everything downstream of them -- are bit-identical from run to run.
+__global__ void __launch_bounds__(256) channel_stats_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ ws,
+                                                                    long long P, int C) {
+  extern __shared__ float part[];                // [lanes][2C]
   const int c8n = C >> 3;
   const int b = blockIdx.y;
   const int piece = threadIdx.x % c8n;
   const int lanes = blockDim.x / c8n;
   const int pl = threadIdx.x / c8n;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ss[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (pl < lanes) {
     const __nv_bfloat16* xb = x + static_cast<size_t>(b) * P * C;
@@ -87,15 +91,29 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const __nv_bfloat16*
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      atomicAdd(&red[piece * 8 + k], s[k]);
-      atomicAdd(&red[C + piece * 8 + k], ss[k]);
+      part[pl * 2 * C + piece * 8 + k] = s[k];
+      part[pl * 2 * C + C + piece * 8 + k] = ss[k];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(&stats[(static_cast<size_t>(b) * C + i) * 2 + 0], red[i]);
-    atomicAdd(&stats[(static_cast<size_t>(b) * C + i) * 2 + 1], red[C + i]);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += part[l * 2 * C + i];
+    ws[(static_cast<size_t>(b) * gridDim.x + blockIdx.x) * 2 * C + i] = acc;
   }
+}
+
+__global__ void channel_stats_final_kernel(const float* __restrict__ ws, float* __restrict__ stats, int chunks, int C) {
+  const int b = blockIdx.x, i = threadIdx.x;     // i in [0, 2C): column of the partial rows
+  float acc = 0.f;
+  for (int ch = 0; ch < chunks; ++ch) acc += ws[(static_cast<size_t>(b) * chunks + ch) * 2 * C + i];
+  const int c = i < C ? i : i - C;
+  stats[(static_cast<size_t>(b) * C + c) * 2 + (i < C ? 0 : 1)] = acc;
+}
+
+inline int channel_stats_chunks(int B, long long P, int C) {
+  const int lanes = 256 / (C / 8);
+  return static_cast<int>(std::min<long long>((P + lanes * 8 - 1) / (lanes * 8), static_cast<long long>(dpf::sm_count()) * 8 / B + 1));
 }
 
 // samples/logits [B,S,H,W,C] bf16; vol [B,D,H,W,Cvol]
@@ -165,16 +183,22 @@ extern "C" int dpf_asm_sample_fwd(const void* x, void* out, int B, int H4, int W
   return dpf::after_launch("dpf_asm_sample_fwd");
 }
 
-extern "C" int dpf_channel_stats(const void* x, float* stats, int B, long long P, int C, void* stream) {
-  DPF_REQUIRE(x && stats, "dpf_channel_stats: null pointer");
+extern "C" long long dpf_channel_stats_ws_floats(int B, long long P, int C) {
+  if (B <= 0 || P <= 0 || C < 8 || C % 8) return 0;
+  return static_cast<long long>(B) * channel_stats_chunks(B, P, C) * 2 * C;
+}
+
+extern "C" int dpf_channel_stats(const void* x, float* stats, float* ws, int B, long long P, int C, void* stream) {
+  DPF_REQUIRE(x && stats && ws, "dpf_channel_stats: null pointer (ws = caller-owned workspace of dpf_channel_stats_ws_floats() floats)");
   DPF_REQUIRE(DPF_ALIGNED16(x), "dpf_channel_stats: x must be 16-byte aligned");
   DPF_REQUIRE(C >= 8 && C % 8 == 0 && C <= 256 && (256 % (C / 8)) == 0 && B > 0 && B <= 65535 && P > 0, "dpf_channel_stats: bad shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(stats, 0, static_cast<size_t>(B) * C * 2 * sizeof(float), st);
-  if (e != cudaSuccess) return dpf::fail("dpf_channel_stats: memset: %s", cudaGetErrorString(e));
   const int lanes = 256 / (C / 8);
-  const int chunks = static_cast<int>(std::min<long long>((P + lanes * 8 - 1) / (lanes * 8), static_cast<long long>(dpf::sm_count()) * 8 / B + 1));
-  channel_stats_kernel<<<dim3(chunks, B), 256, 2 * C * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(x), stats, P, C);
+  const int chunks = channel_stats_chunks(B, P, C);
+  channel_stats_partial_kernel<<<dim3(chunks, B), 256, static_cast<size_t>(lanes) * 2 * C * sizeof(float), st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ws, P, C);
+  if (int rc = dpf::after_launch("dpf_channel_stats")) return rc;
+  channel_stats_final_kernel<<<B, 2 * C, 0, st>>>(ws, stats, chunks, C);
   return dpf::after_launch("dpf_channel_stats");
 }
 

@@ -40,11 +40,15 @@ using namespace dpf;
 constexpr int kEpiWarps = 4;
 constexpr int kProdWarps = 4;
 constexpr int kMmaWarp = kEpiWarps;                                   // warp 4
-// The taps of a work item are dealt round-robin to kGMmaWarps issuing warps: one warp walking 27 taps (tap decode + descriptor
-// arithmetic + issue) was the critical path of the stride-2 / transposed / 1x3x3 layers (ncu source view: that warp ~70 % busy,
-// every other warp waiting on it).  Different warps may accumulate into the same TMEM accumulator, so no MMA overwrites:
-// the epilogue leaves every accumulator zeroed after reading it (tcgen05.st) and all MMAs accumulate.
-constexpr int kGMmaWarps = 4;
+// MMA issue, template parameter NISS (number of issuing warps):
+//   NISS = 1 (default): ONE elected thread issues every MMA of a work item in program order.  MMAs of one thread execute in
+//            issue order, so the fp32 accumulation order -- and with it every output bit -- is fixed: run-to-run deterministic.
+//   NISS = 4 (DPF_CONV_ISSUERS=4): the taps of a work item are dealt round-robin to four issuing warps (one warp walking 27 taps
+//            -- tap decode + descriptor arithmetic + issue -- was the critical path of the stride-2 / transposed / 1x3x3 layers in
+//            round 1).  Warps race into the same TMEM accumulator, so the accumulation ORDER varies from run to run: measured
+//            on a B200 (tests/test_gpu_configs.py), ~1e-4 of the outputs differ by one bf16 ulp between two launches.
+// In both modes no MMA overwrites: the epilogue leaves every accumulator zeroed after reading it (tcgen05.st).
+constexpr int kGMmaWarps = 4;                                         // warps reserved for the role (NISS of them issue)
 constexpr int kThreads = (kEpiWarps + kGMmaWarps + kProdWarps) * 32;  // 384
 constexpr int kMaxTaps = 27;
 
@@ -121,7 +125,7 @@ __device__ __forceinline__ void item_planes(int item, int& base, int& prog) {
   else { base = item >> 1; prog = item & 1; }
 }
 
-template <int GEO, int CIN, int NPAD, int WT, int NS>
+template <int GEO, int CIN, int NPAD, int WT, int NS, int NISS>
 __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_constant__ ConvKParams p) {
   using C = Cfg<GEO, CIN, NPAD, WT, NS>;
   extern __shared__ uint8_t smem_raw[];
@@ -154,10 +158,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) {
       mbar_init(&bar_full[i], kProdWarps);
-      mbar_init(&bar_empty[i], kGMmaWarps);
+      mbar_init(&bar_empty[i], NISS);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_tfull[i], kGMmaWarps);
+      mbar_init(&bar_tfull[i], NISS);
       mbar_init(&bar_tempty[i], kEpiWarps);
     }
     mbar_fence_init();
@@ -234,6 +238,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[prev_slot]);
     }
+  } else if (warp >= kMmaWarp + NISS) {
+    // reserved MMA-role warps that do not issue in this instantiation: nothing to do until the teardown barrier
   } else if (warp >= kMmaWarp) {
     // ============ MMA issuers: each warp runs the (warp-uniform) control flow of its taps, one elected lane issues =====
     const int mw = warp - kMmaWarp;
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         int base, prog;
         item_planes<GEO>(item, base, prog);
         const int nt = p.ntaps[prog];
-        for (int t = mw; t < nt; t += kGMmaWarps) {
+        for (int t = mw; t < nt; t += NISS) {
           const Tap tp = p.taps[prog][t];
           const int pin = base + tp.dd;
           if (pin < 0 || pin >= D) continue;
@@ -273,11 +279,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           if (leader && !(p.debug & 2)) {
 #pragma unroll
             for (int ks = 0; ks < C::KSTEPS; ++ks) {
-              const uint64_t bdesc = bdesc_hi | static_cast<uint64_t>((b0 + ks * 2 * NPAD) & 0x3FFF);
+              // (shared-memory addresses >> 4 are < 2^14: the start-address field cannot overflow, no masking needed)
+              const uint64_t bdesc = bdesc_hi | static_cast<uint64_t>(b0 + ks * 2 * NPAD);
 #pragma unroll
               for (int blk = 0; blk < C::NBLK; ++blk) {
-                if (blk < nblk) {
-                  const uint64_t adesc = adesc_hi | static_cast<uint64_t>((a0 + ks * 2 * (C::CH_STRIDE >> 4) + blk * 8) & 0x3FFF);
+                if (blk == 0 || blk < nblk) {                   // a tile always has its first block (no runtime test)
+                  const uint64_t adesc = adesc_hi | static_cast<uint64_t>(a0 + ks * 2 * (C::CH_STRIDE >> 4) + blk * 8);
                   umma_bf16(acc0 + blk * NPAD, adesc, bdesc, idesc, true);
                 }
               }
@@ -459,11 +466,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
 // ============================================================================================================
 constexpr int kFEpiWarps = 8;                                       // fused kernel: 8 epilogue warps, MMA warps 8-9, 4 producers
 constexpr int kFMmaWarp = kFEpiWarps;
-// The single MMA-issuing thread was the critical path (ncu source view: ~10 uniform-datapath instructions of descriptor
-// arithmetic per tcgen05.mma, the warp 64 % busy issuing while every other warp waits on it).  Four warps issue disjoint
-// quarters of each plane's MMAs: the (128-row block, K-step) pairs are dealt round-robin -- different blocks own different
-// accumulators, K-steps of one block share one (every MMA accumulates into a pre-zeroed stage, so the order is free).
-constexpr int kFMmaWarps = 4;
+// MMA issue (template parameter NISS, see the generic kernel): 1 = one thread, program order, deterministic (default);
+// 4 = the (128-row block, K-step) pairs of a plane are dealt round-robin to four issuing warps -- K-steps of one block then race
+// into one accumulator (every MMA accumulates into a pre-zeroed stage, so any order is CORRECT, but the fp32 rounding differs from
+// run to run).  Round 1 used 4 because the single issuer was the critical path (~10 uniform-datapath instructions of descriptor
+// arithmetic per tcgen05.mma behind a per-MMA branch); the single-issuer loop now has no branch and no address masking, so the
+// compiler can software-pipeline the descriptor arithmetic of consecutive MMAs.
+constexpr int kFMmaWarps = 4;                                       // warps reserved for the role (NISS of them issue)
 constexpr int kFThreads = (kFEpiWarps + kFMmaWarps + kProdWarps) * 32;   // 512
 
 template <int CIN, int NPAD, int WT, int NS, int R, int DILW = 1>
@@ -488,7 +497,7 @@ struct FCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
 
-template <int CIN, int NPAD, int WT, int NS, int R, int DILW = 1>
+template <int CIN, int NPAD, int WT, int NS, int R, int DILW, int NISS>
 __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __grid_constant__ ConvKParams p) {
   using C = FCfg<CIN, NPAD, WT, NS, R, DILW>;
   extern __shared__ uint8_t smem_raw[];
@@ -526,10 +535,10 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) {
       mbar_init(&bar_full[i], kProdWarps);
-      mbar_init(&bar_empty[i], kFMmaWarps);
+      mbar_init(&bar_empty[i], NISS);
     }
     for (int i = 0; i < R; ++i) {
-      mbar_init(&bar_tfull[i], kFMmaWarps);
+      mbar_init(&bar_tfull[i], NISS);
       mbar_init(&bar_tempty[i], kFEpiWarps);
     }
     mbar_fence_init();
@@ -592,8 +601,10 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[prev_slot]);
     }
+  } else if (warp >= kFMmaWarp + NISS) {
+    // reserved MMA-role warps that do not issue in this instantiation
   } else if (warp >= kFMmaWarp) {
-    // =================================== MMA issuers (kFMmaWarps warps, disjoint shares of every plane) ===
+    // =================================== MMA issuers (NISS warps, disjoint shares of every plane) =========
     const int mw = warp - kFMmaWarp;
     const uint32_t wbase = smem_u32(s_w) >> 4;
     const uint32_t sbase0 = smem_u32(s_slots);
@@ -635,13 +646,13 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
               const uint32_t b0 = wbase + (kh * 3 + kw) * (C::W_GROUP_BYTES >> 4) + kd_lo * NPAD;
 #pragma unroll
               for (int ks = 0; ks < C::KSTEPS; ++ks) {
-                const uint64_t bd1 = bdesc_hi | static_cast<uint64_t>((b0 + ks * 2 * C::W_ROWS) & 0x3FFF);
-                const uint64_t bd2 = bdesc_hi | static_cast<uint64_t>((b0 + ks * 2 * C::W_ROWS + run1 * NPAD) & 0x3FFF);
+                const uint64_t bd1 = bdesc_hi | static_cast<uint64_t>(b0 + ks * 2 * C::W_ROWS);
+                const uint64_t bd2 = bdesc_hi | static_cast<uint64_t>(b0 + ks * 2 * C::W_ROWS + run1 * NPAD);
 #pragma unroll
                 for (int blk = 0; blk < C::NBLK; ++blk) {
-                  if ((blk * C::KSTEPS + ks) % kFMmaWarps != mw) continue;           // this warp's share of the plane
-                  if (blk < nblk) {
-                    const uint64_t adesc = adesc_hi | static_cast<uint64_t>((a0 + ks * 2 * (C::CH_STRIDE >> 4) + blk * 8) & 0x3FFF);
+                  if (NISS > 1 && (blk * C::KSTEPS + ks) % NISS != mw) continue;     // this warp's share of the plane
+                  if (blk == 0 || blk < nblk) {                   // a tile always has its first block (no runtime test)
+                    const uint64_t adesc = adesc_hi | static_cast<uint64_t>(a0 + ks * 2 * (C::CH_STRIDE >> 4) + blk * 8);
                     const uint32_t col = tmem_base + blk * (R * NPAD);
                     umma_bf16(col + s_first * NPAD, adesc, bd1, idesc1, true);
                     if (run2 > 0) umma_bf16(col, adesc, bd2, idesc2, true);
@@ -812,13 +823,20 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
   }
 }
 
-template <int CIN, int NPAD, int WT, int NS, int R, int DILW = 1>
-int launch_fused(ConvKParams kp, cudaStream_t st) {
+// DPF_CONV_ISSUERS = 1 (default: deterministic single issuer) | 4 (round-1 four-warp issue, run-to-run rounding differences)
+int conv_issuers() {
+  static int n = 0;
+  if (n == 0) { const char* e = getenv("DPF_CONV_ISSUERS"); n = (e && atoi(e) == 4) ? 4 : 1; }
+  return n;
+}
+
+template <int CIN, int NPAD, int WT, int NS, int R, int DILW, int NISS>
+int launch_fused_n(ConvKParams kp, cudaStream_t st) {
   using C = FCfg<CIN, NPAD, WT, NS, R, DILW>;
   kp.tiles_h = (kp.Mh + 15) / 16;
   kp.tiles_w = (kp.Mw + WT - 1) / WT;
   kp.ntiles = kp.B * kp.tiles_h * kp.tiles_w;
-  auto kern = conv3d_kdfused_kernel<CIN, NPAD, WT, NS, R, DILW>;
+  auto kern = conv3d_kdfused_kernel<CIN, NPAD, WT, NS, R, DILW, NISS>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -830,11 +848,16 @@ int launch_fused(ConvKParams kp, cudaStream_t st) {
   return dpf::after_launch("dpf_conv3d_fwd");
 }
 
+template <int CIN, int NPAD, int WT, int NS, int R, int DILW = 1>
+int launch_fused(const ConvKParams& kp, cudaStream_t st) {
+  return conv_issuers() == 4 ? launch_fused_n<CIN, NPAD, WT, NS, R, DILW, 4>(kp, st) : launch_fused_n<CIN, NPAD, WT, NS, R, DILW, 1>(kp, st);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
-template <int GEO, int CIN, int NPAD, int WT, int NS>
-int launch(ConvKParams kp, cudaStream_t st) {
+template <int GEO, int CIN, int NPAD, int WT, int NS, int NISS>
+int launch_n(ConvKParams kp, cudaStream_t st) {
   using C = Cfg<GEO, CIN, NPAD, WT, NS>;
   // tap start offsets inside a slot chunk-plane (16-byte units); the builders stash (dh << 8 | dw) in aoff
   for (int pr = 0; pr < 2; ++pr)
@@ -849,7 +872,7 @@ int launch(ConvKParams kp, cudaStream_t st) {
   kp.tiles_h = (kp.Mh + 15) / 16;
   kp.tiles_w = (kp.Mw + WT - 1) / WT;
   kp.ntiles = kp.B * kp.tiles_h * kp.tiles_w;
-  auto kern = conv3d_tc_kernel<GEO, CIN, NPAD, WT, NS>;
+  auto kern = conv3d_tc_kernel<GEO, CIN, NPAD, WT, NS, NISS>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -859,6 +882,11 @@ int launch(ConvKParams kp, cudaStream_t st) {
   const int grid = std::min(kp.ntiles, dpf::sm_count());
   kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(kp);
   return dpf::after_launch("dpf_conv3d_fwd");
+}
+
+template <int GEO, int CIN, int NPAD, int WT, int NS>
+int launch(const ConvKParams& kp, cudaStream_t st) {
+  return conv_issuers() == 4 ? launch_n<GEO, CIN, NPAD, WT, NS, 4>(kp, st) : launch_n<GEO, CIN, NPAD, WT, NS, 1>(kp, st);
 }
 
 int npad_for(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : 64); }

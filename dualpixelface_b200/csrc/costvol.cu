@@ -85,6 +85,73 @@ __global__ void __launch_bounds__(kThreads) costvol_fwd_kernel(const __nv_bfloat
   const int total = rows * piecesPerRow;
   const float inv_cpg = (MODE == 2) ? -1.0f / static_cast<float>(C / G) : 0.f;
 
+  if (MODE == 2) {
+    // Group-wise correlation (build_gwc_volume, psmnet/modules.py:215-221,243-262): vol[g] = -mean_{c in group g}(ref[c]*tgt[c]).
+    // C/8 lanes per pixel: a lane loads ONE 16-byte piece of the ref pixel and of the shifted tgt pixel from the staged rows
+    // (conflict-free 128-bit shared loads), multiplies its 8 channels and sums them per group in registers; groups wider than
+    // 8 channels are finished by a warp-shuffle (xor) reduction over the group's lanes; the G results of a pixel are then
+    // collected by shuffles into the lanes that own the pixel's 16-byte output pieces and stored with coalesced 128-bit
+    // streaming stores.  (Round 1 walked the channels with scalar 2-byte shared loads in one thread per output piece: 266 GB/s.)
+    const int lpp = c8;                                          // lanes per pixel (power of two <= 32: C in {8,16,...,256})
+    const int cpg = C / G;                                       // channels per group
+    const int ng = (cpg < 8) ? 8 / cpg : 1;                      // group sums a lane holds
+    const int lpg = (cpg > 8) ? cpg / 8 : 1;                     // lanes per group
+    const int totalLanes = rows * wseg * lpp;
+    const int totalPad = (totalLanes + 31) & ~31;
+    for (int i = 0; i < D; ++i) {
+      const int s = sh.s[i];
+      __nv_bfloat16* vbase = vol + ((static_cast<size_t>(b) * D + i) * H + h0) * static_cast<size_t>(W) * cv;
+      for (int q = threadIdx.x; q < totalPad; q += kThreads) {
+        const bool live = q < totalLanes;
+        const int qq = live ? q : 0;
+        const int pc = qq % lpp;                                 // this lane's 16-byte input piece == the output piece it may own
+        const int pix = qq / lpp;
+        const int r = pix / wseg, px = pix - r * wseg;
+        const int hs = h0 + r + s;
+        const bool valid = live && (hs >= 0) && (hs < H);
+        float gs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (valid) {
+          const uint4 a = *reinterpret_cast<const uint4*>(sref + r * rowBytes + px * (C * 2) + pc * 16);
+          const uint4 t = *reinterpret_cast<const uint4*>(stgt + (r + s - sh.smin) * rowBytes + px * (C * 2) + pc * 16);
+          const float pr[8] = {dpf::bf16_lo(a.x) * dpf::bf16_lo(t.x), dpf::bf16_hi(a.x) * dpf::bf16_hi(t.x),
+                               dpf::bf16_lo(a.y) * dpf::bf16_lo(t.y), dpf::bf16_hi(a.y) * dpf::bf16_hi(t.y),
+                               dpf::bf16_lo(a.z) * dpf::bf16_lo(t.z), dpf::bf16_hi(a.z) * dpf::bf16_hi(t.z),
+                               dpf::bf16_lo(a.w) * dpf::bf16_lo(t.w), dpf::bf16_hi(a.w) * dpf::bf16_hi(t.w)};
+          if (cpg >= 8) {
+            gs[0] = ((pr[0] + pr[1]) + (pr[2] + pr[3])) + ((pr[4] + pr[5]) + (pr[6] + pr[7]));
+          } else if (cpg == 4) {
+            gs[0] = (pr[0] + pr[1]) + (pr[2] + pr[3]); gs[1] = (pr[4] + pr[5]) + (pr[6] + pr[7]);
+          } else if (cpg == 2) {
+            gs[0] = pr[0] + pr[1]; gs[1] = pr[2] + pr[3]; gs[2] = pr[4] + pr[5]; gs[3] = pr[6] + pr[7];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gs[k] = pr[k];
+          }
+        }
+        for (int o = 1; o < lpg; o <<= 1) gs[0] += __shfl_xor_sync(0xffffffffu, gs[0], o);     // groups wider than one lane
+        // lane pc of the pixel assembles output piece pc = groups 8*pc .. 8*pc+7; group g lives in lane g*lpg (slot 0) when
+        // cpg >= 8, else in lane g / ng, slot g % ng = j % ng (ng divides 8): the slot is the same for every reader
+        const int lane = threadIdx.x & 31;
+        const int pixbase = lane - pc;
+        float o8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int g = 8 * pc + j;
+          const int src = pixbase + ((cpg >= 8) ? g * lpg : g / ng);
+          const float mine = (ng == 1) ? gs[0] : (ng == 2 ? gs[j & 1] : (ng == 4 ? gs[j & 3] : gs[j]));
+          o8[j] = __shfl_sync(0xffffffffu, mine, src & 31) * inv_cpg;
+        }
+        if (live && pc < pp) {
+          uint4 v;
+          v.x = dpf::pack_bf16x2(o8[0], o8[1]); v.y = dpf::pack_bf16x2(o8[2], o8[3]);
+          v.z = dpf::pack_bf16x2(o8[4], o8[5]); v.w = dpf::pack_bf16x2(o8[6], o8[7]);
+          dpf::st_cs_v4(vbase + (static_cast<size_t>(r) * W + w0 + px) * cv + pc * 8, v);
+        }
+      }
+    }
+    return;
+  }
+
   for (int i = 0; i < D; ++i) {
     const int s = sh.s[i];
     __nv_bfloat16* vbase = vol + ((static_cast<size_t>(b) * D + i) * H + h0) * static_cast<size_t>(W) * cv;
@@ -103,27 +170,8 @@ __global__ void __launch_bounds__(kThreads) costvol_fwd_kernel(const __nv_bfloat
         if (MODE == 0) {
           v = (pc < c8) ? *reinterpret_cast<const uint4*>(rrow + pc * 16)
                         : *reinterpret_cast<const uint4*>(trow + (pc - c8) * 16);
-        } else if (MODE == 1) {
-          v = sub_bf16x8(*reinterpret_cast<const uint4*>(rrow + pc * 16), *reinterpret_cast<const uint4*>(trow + pc * 16));
         } else {
-          // 8 groups per 16-byte output piece; group g covers channels [g*cpg, (g+1)*cpg)
-          const int cpg = C / G;
-          float acc[8];
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const int c0 = (pc * 8 + g) * cpg;
-            float a = 0.f;
-            for (int c = 0; c < cpg; ++c) {
-              const float x = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rrow)[c0 + c]);
-              const float y = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(trow)[c0 + c]);
-              a = fmaf(x, y, a);
-            }
-            acc[g] = a * inv_cpg;
-          }
-          v.x = dpf::pack_bf16x2(acc[0], acc[1]);
-          v.y = dpf::pack_bf16x2(acc[2], acc[3]);
-          v.z = dpf::pack_bf16x2(acc[4], acc[5]);
-          v.w = dpf::pack_bf16x2(acc[6], acc[7]);
+          v = sub_bf16x8(*reinterpret_cast<const uint4*>(rrow + pc * 16), *reinterpret_cast<const uint4*>(trow + pc * 16));
         }
       }
       dpf::st_cs_v4(vbase + (static_cast<size_t>(r) * W + w0 + px) * cv + pc * 8, v);
@@ -209,7 +257,8 @@ extern "C" int dpf_costvol_fwd(int mode, const void* ref, const void* tgt, void*
   DPF_REQUIRE(B > 0 && H4 > 0 && W4 > 0 && B <= 65535, "dpf_costvol_fwd: bad shape B=%d H4=%d W4=%d", B, H4, W4);
   DPF_REQUIRE(C >= 8 && C % 8 == 0 && C <= 128, "dpf_costvol_fwd: C=%d must be a multiple of 8 in [8,128]", C);
   DPF_REQUIRE(D >= 1 && D <= kMaxD, "dpf_costvol_fwd: D=%d must be in [1,%d]", D, kMaxD);
-  if (mode == 2) DPF_REQUIRE(G >= 8 && G % 8 == 0 && C % G == 0, "dpf_costvol_fwd: gwc needs G %% 8 == 0 and G | C (G=%d C=%d)", G, C);
+  if (mode == 2) DPF_REQUIRE(G >= 8 && G % 8 == 0 && C % G == 0 && ((C / 8) & (C / 8 - 1)) == 0 && ((C / G) & (C / G - 1)) == 0,
+                             "dpf_costvol_fwd: gwc needs G %% 8 == 0, G | C, and C/8, C/G powers of two (G=%d C=%d)", G, C);
   Shifts sh;
   make_shifts(shifts_host, D, &sh);
   DPF_REQUIRE(sh.smax - sh.smin <= 16, "dpf_costvol_fwd: shift span %d too large", sh.smax - sh.smin);

@@ -13,12 +13,14 @@
 // 1-D TMA bulk copy.  One elected lane issues the tcgen05.mma; accumulators are double-buffered in TMEM so the
 // epilogue of a unit overlaps the gather of the next.
 //
-// Offsets (STAGED path, off_cstride a multiple of 4 and >= 84): the kernel is bound by L1 data-pipe wavefronts (ncu r01: 74 % of
-// the LSU wavefront peak), and a quarter of them were the OFFSET loads: 3 scalar LDGs per (voxel, tap) in which the 4 lanes of a
-// voxel read the same word, i.e. 8 lines = 8 wavefronts per warp instruction for 32 useful bytes (profiles/r02_dcn3d_source.txt).
-// The unit's 256 x 81 offsets are now staged in shared memory by 16-byte cp.async in two halves (taps 0-11 | taps 12-26, each
-// half re-filled for the NEXT unit while the other half is in use), with voxel pitches of 36 / 52 words so that a warp's 8 voxels
-// hit 8 different banks: an offset read is one LDS wavefront instead of 8.
+// Offsets, STAGED variant (DPF_DCN_STAGED=1; off_cstride a multiple of 4 and >= 84) -- built, tested, measured, and OFF by default.
+// A quarter of the kernel's L1 wavefronts are the OFFSET loads: 3 scalar LDGs per (voxel, tap) in which the 4 lanes of a voxel read
+// the same word, i.e. 8 lines = 8 wavefronts per warp instruction for 32 useful bytes (profiles/r02_dcn3d_source.txt).  The staged
+// variant keeps the unit's 256 x 81 offsets in shared memory (16-byte cp.async in two halves, taps 0-11 | 12-26, each half
+// re-filled for the NEXT unit while the other is in use; voxel pitches of 36 / 52 words = conflict-free), which does cut the global
+// load wavefronts by 20 % (234 M -> 187 M per launch) -- but the extra 88 KB of shared memory come out of the L1 cache the gather
+// lives on: L1 hit rate 83 % -> 43 %, L2->L1 sectors x3.1, and the launch is not faster alone (3.51 vs 3.40 ms) and 30 % slower inside
+// the model, where the offsets are larger (profiles/r02_dcn3d_staged.txt).  The gather needs its L1 more than its LSU slots.
 #include "../../include/dpf_sm100.h"
 #include "dpf_common.cuh"
 #include "dpf_ptx.cuh"
@@ -461,7 +463,7 @@ extern "C" int dpf_dcn3d_fwd(const void* x, const float* offset, const void* w, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // staged offsets need 16-byte aligned voxel rows that hold floats 0..83 (the 81 real offsets + padding)
   static int staged_env = -1;
-  if (staged_env < 0) { const char* e = getenv("DPF_DCN_STAGED"); staged_env = e ? atoi(e) : 1; }
+  if (staged_env < 0) { const char* e = getenv("DPF_DCN_STAGED"); staged_env = e ? atoi(e) : 0; }
   const bool staged = staged_env && off_cstride % 4 == 0 && off_cstride >= 84 && (reinterpret_cast<uintptr_t>(offset) & 15u) == 0;
   if (Cin_pad == 32) return staged ? launch_dcn<32, true>(p, st) : launch_dcn<32, false>(p, st);
   return staged ? launch_dcn<64, true>(p, st) : launch_dcn<64, false>(p, st);

@@ -69,26 +69,28 @@ extern "C" int dpf_bias_act(const void* x, const float* bias, const void* res, v
 namespace {
 
 __global__ void __launch_bounds__(256) anm_tail_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int K,
-                                                       int H4, int W4) {
-  const int H = 4 * H4, W = 4 * W4;
+                                                       int H4loc, int W4, int cs, int H4glob, int q_row0, int Hout, int y_row0) {
+  const int H = 4 * H4glob, W = 4 * W4;                       // GLOBAL full-resolution size (align_corners scale)
   const int xo = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int yo = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int yl = blockIdx.y * 8 + (threadIdx.x >> 5);        // local output row
   const int b = blockIdx.z;
-  if (xo >= W || yo >= H) return;
-  const float sh = static_cast<float>(H4 - 1) / static_cast<float>(H - 1);
+  if (xo >= W || yl >= Hout) return;
+  const int yo = y_row0 + yl;
+  const float sh = static_cast<float>(H4glob - 1) / static_cast<float>(H - 1);
   const float sw = static_cast<float>(W4 - 1) / static_cast<float>(W - 1);
   const float sy = sh * static_cast<float>(yo), sx = sw * static_cast<float>(xo);
   const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
-  const int y1 = y0 + (y0 < H4 - 1 ? 1 : 0), x1 = x0 + (x0 < W4 - 1 ? 1 : 0);
+  const int y1 = y0 + (y0 < H4glob - 1 ? 1 : 0), x1 = x0 + (x0 < W4 - 1 ? 1 : 0);
   const float ly = sy - static_cast<float>(y0), lx = sx - static_cast<float>(x0);
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const int r0 = min(max(y0 - q_row0, 0), H4loc - 1), r1 = min(max(y1 - q_row0, 0), H4loc - 1);   // rows of the local tile
   float acc[3] = {0.f, 0.f, 0.f};
   for (int k = 0; k < K; ++k) {
-    const __nv_bfloat16* p = x + static_cast<size_t>(b * K + k) * H4 * W4 * 3;
-    const __nv_bfloat16* p00 = p + (static_cast<size_t>(y0) * W4 + x0) * 3;
-    const __nv_bfloat16* p01 = p + (static_cast<size_t>(y0) * W4 + x1) * 3;
-    const __nv_bfloat16* p10 = p + (static_cast<size_t>(y1) * W4 + x0) * 3;
-    const __nv_bfloat16* p11 = p + (static_cast<size_t>(y1) * W4 + x1) * 3;
+    const __nv_bfloat16* p = x + static_cast<size_t>(b * K + k) * H4loc * W4 * cs;
+    const __nv_bfloat16* p00 = p + (static_cast<size_t>(r0) * W4 + x0) * cs;
+    const __nv_bfloat16* p01 = p + (static_cast<size_t>(r0) * W4 + x1) * cs;
+    const __nv_bfloat16* p10 = p + (static_cast<size_t>(r1) * W4 + x0) * cs;
+    const __nv_bfloat16* p11 = p + (static_cast<size_t>(r1) * W4 + x1) * cs;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float v = w00 * __bfloat162float(p00[c]) + w01 * __bfloat162float(p01[c]) + w10 * __bfloat162float(p10[c]) +
@@ -98,17 +100,24 @@ __global__ void __launch_bounds__(256) anm_tail_kernel(const __nv_bfloat16* __re
   }
   const float inv = 2.0f / static_cast<float>(K);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) out[((static_cast<size_t>(b) * 3 + c) * H + yo) * W + xo] = acc[c] * inv - 1.0f;
+  for (int c = 0; c < 3; ++c) out[((static_cast<size_t>(b) * 3 + c) * Hout + yl) * W + xo] = acc[c] * inv - 1.0f;
 }
 
 }  // namespace
 
-extern "C" int dpf_anm_tail(const void* x, float* out, int B, int K, int H4, int W4, void* stream) {
+extern "C" int dpf_anm_tail_tile(const void* x, float* out, int B, int K, int H4loc, int W4, int x_cstride, int H4glob, int q_row0,
+                                 int Hout, int y_row0, void* stream) {
   DPF_REQUIRE(x && out, "dpf_anm_tail: null pointer");
-  DPF_REQUIRE(B > 0 && B <= 65535 && K >= 1 && H4 > 1 && W4 > 1, "dpf_anm_tail: bad shape");
-  dim3 grid((4 * W4 + 31) / 32, (4 * H4 + 7) / 8, B);
-  anm_tail_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, K, H4, W4);
+  DPF_REQUIRE(B > 0 && B <= 65535 && K >= 1 && H4loc >= 1 && W4 > 1 && H4glob > 1 && x_cstride >= 3 && Hout >= 1, "dpf_anm_tail: bad shape");
+  DPF_REQUIRE(q_row0 >= 0 && q_row0 + H4loc <= H4glob && y_row0 >= 0 && y_row0 + Hout <= 4 * H4glob, "dpf_anm_tail: tile outside the image");
+  dim3 grid((4 * W4 + 31) / 32, (Hout + 7) / 8, B);
+  anm_tail_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, K, H4loc, W4,
+                                                                      x_cstride, H4glob, q_row0, Hout, y_row0);
   return dpf::after_launch("dpf_anm_tail");
+}
+
+extern "C" int dpf_anm_tail(const void* x, float* out, int B, int K, int H4, int W4, void* stream) {
+  return dpf_anm_tail_tile(x, out, B, K, H4, W4, 3, H4, 0, 4 * H4, 0, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------

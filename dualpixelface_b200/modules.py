@@ -215,6 +215,8 @@ class CostVolumeSDP(nn.Module):
     ``cached_first_level=True`` (default) reproduces the reference as shipped: subpixel_shift.make_grid caches the grids
     of its first call (src/module/asm/asm.py:29-30,56-57), so every level is sampled with costrange[0]; all D slices
     are identical and are produced by ONE sample / attention / blend pass that writes all D slices.
+    ``cached_first_level=False`` is the evidently intended behaviour -- one shift per level (-1, -0.5, ..., 2.5 rows), including
+    the fractional Fourier (phase) shifts of asm.py:63-75,112-125 (shift_tables.fourier_row_shift).
     """
 
     def __init__(self, option, mindisp, maxdisp):
@@ -237,6 +239,21 @@ class CostVolumeSDP(nn.Module):
             t = shift_tables.build_tables(h, w, disp, direction, self.shifting_layer.modes)
             self._tables[key] = {k: v.to(device) for k, v in t.items()}
         return self._tables[key]
+
+    def sample(self, feat: torch.Tensor, tab: dict, train: bool = False) -> torch.Tensor:
+        """feat [B,H4,W4,C] -> the (up to) three resampled copies [B,S,H4,W4,C]: table samples (nearest, bilinear, integer phase
+        roll) from dpf_asm_sample_fwd; a FRACTIONAL phase shift (cached_first_level=False only) from shift_tables.fourier_row_shift."""
+        s = None
+        if "ri" in tab:
+            if train:
+                from .train_asm import AsmSampleFn
+                s = AsmSampleFn.apply(feat, tab)
+            else:
+                s = ops.asm_sample(feat, tab)
+        if "rot" in tab:
+            ph = shift_tables.fourier_row_shift(feat, tab["rot"]).unsqueeze(1)
+            s = ph if s is None else torch.cat([s, ph], 1)
+        return s
 
     def _pack(self):
         if self._packed is None:
@@ -270,8 +287,8 @@ class CostVolumeSDP(nn.Module):
         levels = [(0, self.level, self.costrange[0])] if self.cached_first_level else \
             [(i, 1, d) for i, d in enumerate(self.costrange)]
         for d0, rep, disp in levels:
-            sf = ops.asm_sample(ref_feat, self._tab(h, w, disp, "forward", ref_feat.device))
-            sb = ops.asm_sample(tar_feat, self._tab(h, w, disp, "backward", ref_feat.device))
+            sf = self.sample(ref_feat, self._tab(h, w, disp, "forward", ref_feat.device))
+            sb = self.sample(tar_feat, self._tab(h, w, disp, "backward", ref_feat.device))
             smp = torch.cat([sf, sb], 0)                                # [2B,S,H,W,C]
             logits, a, dd = self._attend(smp)
             ops.asm_blend(smp[:b], logits[:b], a[:b].contiguous(), dd[:b].contiguous(), vol, d0, rep, 0)
@@ -299,10 +316,24 @@ class CostVolumePSM(nn.Module):
                 from .train_ops import CostVolumeFn
                 return CostVolumeFn.apply(ref_feat, tar_feat, self.shifts, mode, 0)
             return ops.costvol_fwd(ref_feat, tar_feat, self.shifts, mode)
-        c = ref_feat.shape[-1]
-        assert c % self.group_num == 0, "group_num must divide the feature channels (psmnet/modules.py:217)"
-        raise NotImplementedError("gwcnet style (concat | gwc, 2C+G input channels) needs a Cin=2C+G first layer; "
-                                  "ops.costvol_fwd(..., 'gwc', G) builds the correlation volume itself")
+        # gwcnet (psmnet/modules.py:268-271): cat(concat volume [2C], group-wise correlation volume [G]) along the channels, zero
+        # padded to the next multiple of 32 (the conv engine's input-channel window); PSMNetHGAggregation pads its first layer alike
+        c, g = ref_feat.shape[-1], int(self.group_num)
+        if c % g != 0:
+            raise ValueError(f"group_num {g} must divide the {c} feature channels (assert of psmnet/modules.py:217; the shipped "
+                             f"group_num = 40 fails that assert in the reference too)")
+        if g % 8 != 0:
+            raise NotImplementedError(f"group_num {g}: the correlation kernel writes 16-byte pieces (group_num must be a multiple of 8)")
+        if ref_feat.requires_grad or tar_feat.requires_grad:
+            from .train_ops import CostVolumeFn
+            vc = CostVolumeFn.apply(ref_feat, tar_feat, self.shifts, "concat", 0)
+            vg = CostVolumeFn.apply(ref_feat, tar_feat, self.shifts, "gwc", g)
+        else:
+            vc = ops.costvol_fwd(ref_feat, tar_feat, self.shifts, "concat")
+            vg = ops.costvol_fwd(ref_feat, tar_feat, self.shifts, "gwc", g)
+        pad = (-(2 * c + g)) % 32
+        parts = [vc, vg] + ([vc.new_zeros(*vc.shape[:-1], pad)] if pad else [])
+        return torch.cat(parts, -1)
 
 
 # ======================================================================================================
@@ -336,6 +367,7 @@ class PSMNetHGAggregation(nn.Module):
             o = option_or_channels
             c = o.model.inplanes
             first = 2 * c if o.model.cost_volume == "psmnet" else 2 * c + o.model.group_num
+        self.first_pad = (-first) % 32          # gwcnet: 2C+G input channels, zero-padded to the conv engine's 32-channel windows
         self.multiplier = 4
         self.dres0 = nn.Sequential(_cb3(first, c), nn.ReLU(inplace=True), _cb3(c, c), nn.ReLU(inplace=True))
         self.dres1 = nn.Sequential(_cb3(c, c), nn.ReLU(inplace=True), _cb3(c, c))
@@ -347,15 +379,15 @@ class PSMNetHGAggregation(nn.Module):
     def refresh(self):
         self._plan = None
 
-    def _layer(self, seq: nn.Sequential, kind, transposed=False):
+    def _layer(self, seq: nn.Sequential, kind, transposed=False, cin_pad=None):
         conv, bn = seq[0], seq[1]
-        return TCConv3d(conv.weight, kind, transposed), fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+        return TCConv3d(conv.weight, kind, transposed, cin_pad=cin_pad), fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
 
     def _build(self):
         if self._plan is not None:
             return self._plan
         p = {}
-        p["dres0.0"] = self._layer(self.dres0[0], KIND_3x3x3)
+        p["dres0.0"] = self._layer(self.dres0[0], KIND_3x3x3, cin_pad=self.dres0[0][0].in_channels + self.first_pad)
         p["dres0.2"] = self._layer(self.dres0[2], KIND_3x3x3)
         p["dres1.0"] = self._layer(self.dres1[0], KIND_3x3x3)
         p["dres1.2"] = self._layer(self.dres1[2], KIND_3x3x3)
@@ -391,7 +423,10 @@ class PSMNetHGAggregation(nn.Module):
     def _tl(self, seq, kind, x, residual=None, relu=True):
         from .train_ops import ConvBNAct, LayerCfg
         conv, bn = seq[0], seq[1]
-        return ConvBNAct.apply(x, conv.weight, bn.weight, bn.bias, residual, LayerCfg(kind, relu, bn))
+        w = conv.weight
+        if kind != KIND_T2 and x.shape[-1] > w.shape[1]:            # zero-padded input channels (gwcnet first layer)
+            w = F.pad(w, (0, 0, 0, 0, 0, 0, 0, x.shape[-1] - w.shape[1]))
+        return ConvBNAct.apply(x, w, bn.weight, bn.bias, residual, LayerCfg(kind, relu, bn))
 
     def _hourglass_train(self, hg, x, presqu, postsqu, cost0):
         o = self._tl(hg.conv1[0], KIND_S2, x)
@@ -495,14 +530,18 @@ class ANM(nn.Module):
     def __init__(self, option, mindisp, maxdisp):
         super().__init__()
         c = option.model.inplanes
-        if not (option.model.use_deform and option.model.use_sampling):
-            raise NotImplementedError("only use_deform=true, use_sampling=true (the shipped config) is built")
-        self.k = int(option.model.dsample_num)
+        self.use_deform, self.use_sampling = bool(option.model.use_deform), bool(option.model.use_sampling)
+        # use_sampling=false (normal_module.py:159-163): all `level` cost slices with their own disparities instead of the k nearest
+        # ones -- exactly what the select / gather kernels produce for k = level (top-k of all, sorted ascending = every level)
+        self.k = int(option.model.dsample_num) if self.use_sampling else int(option.model.level)
         self.levels = [float(v) for v in cost_range(mindisp, maxdisp, option.model.level).astype(np.float32)]
-        self.deform_conv1 = DeformConvPack(c + 3, 2 * c)
-        self.act1 = nn.Sequential(nn.BatchNorm3d(2 * c), nn.ReLU(inplace=True))
-        self.deform_conv2 = DeformConvPack(2 * c, 2 * c)
-        self.act2 = nn.Sequential(nn.BatchNorm3d(2 * c), nn.ReLU(inplace=True))
+        if self.use_deform:
+            self.deform_conv1 = DeformConvPack(c + 3, 2 * c)
+            self.act1 = nn.Sequential(nn.BatchNorm3d(2 * c), nn.ReLU(inplace=True))
+            self.deform_conv2 = DeformConvPack(2 * c, 2 * c)
+            self.act2 = nn.Sequential(nn.BatchNorm3d(2 * c), nn.ReLU(inplace=True))
+        else:                                  # use_deform=false (normal_module.py:52-56): two plain convbn_3d + ReLU
+            self.original_conv = nn.Sequential(_cb3(c + 3, 2 * c), nn.ReLU(inplace=True), _cb3(2 * c, 2 * c), nn.ReLU(inplace=True))
         self.n_convs = nn.Sequential(_convtext(2 * c, 3 * c, 1), _convtext(3 * c, 3 * c, 2), _convtext(3 * c, 2 * c, 4),
                                      _convtext(2 * c, 2 * c, 8), _convtext(2 * c, c, 1), _convtext(c, 3, 1))
         cr = torch.arange(option.model.level) * ((maxdisp / 4.0 - mindisp / 4.0) / float(option.model.level)) + mindisp / 4.0
@@ -515,7 +554,12 @@ class ANM(nn.Module):
     def _build(self):
         if self._plan is None:
             p = {}
-            for i, (dc, act) in enumerate(((self.deform_conv1, self.act1), (self.deform_conv2, self.act2)), start=1):
+            if not self.use_deform:
+                for i, seq in ((1, self.original_conv[0]), (2, self.original_conv[2])):
+                    conv, bn = seq[0], seq[1]
+                    p[f"oc{i}"] = (TCConv3d(conv.weight, KIND_3x3x3, cin_pad=64),
+                                   fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps))
+            for i, (dc, act) in enumerate(((self.deform_conv1, self.act1), (self.deform_conv2, self.act2)) if self.use_deform else (), start=1):
                 bn = act[0]
                 cin = dc.weight.shape[1]
                 cpad = 64      # gathering 64 (zero-padded) channels measured faster than the 48-channel variant
@@ -525,13 +569,10 @@ class ANM(nn.Module):
                 p[f"w{i}"] = ops.pack_conv_weight(dc.weight.detach(), cin_pad=cpad)
                 p[f"cpad{i}"] = cpad
                 p[f"aff{i}"] = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, conv_bias=dc.bias)
-            p["nconv"] = [(m[0].weight.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
-                           m[0].dilation[0]) for m in self.n_convs]
-            # dilation-1 layers with 32 | 64 input channels run on the row-streamed 2-D mode of the tcgen05 engine with the
-            # LeakyReLU fused (dpf_conv2d_fwd); the dilated ones stay cuDNN + dpf_bias_act
-            p["nconv_rows"] = [ops.conv2d_rows_plan(m[0].weight.detach().float())
-                               if (m[0].dilation[0] == 1 and m[0].in_channels in (32, 64) and m[0].out_channels in (16, 32)) else None
-                               for m in self.n_convs]
+            # the six dilated 3x3 `convtext` layers (64->96->96->64->64->32->3, dilation 1,2,4,8,1,1) on the dedicated 2-D tcgen05
+            # kernel (dpf_conv2d_tc_fwd): one launch per layer, LeakyReLU(0.1) fused, any dilation via residue-class sub-images
+            p["nconv"] = [(ops.pack_conv2d_tc_weight(m[0].weight.detach().float()), m[0].out_channels, m[0].dilation[0])
+                          for m in self.n_convs]
             self._plan = p
         return self._plan
 
@@ -550,22 +591,22 @@ class ANM(nn.Module):
             kinv = torch.inverse(kq).contiguous()
             idx, coord, minmax = ops.anm_select(disp.contiguous(), kinv, batch["abvalue"].float().contiguous(), self.levels, self.k)
             fv = ops.anm_gather(out3, idx, coord, minmax, 64)                          # [B,K,H4,W4,64]
-            off1 = p["off1"](fv, shift=p["offb1"], out_f32=True)
-            f1 = ops.dcn3d(fv, off1, p["w1"], p["cpad1"], p["aff1"][0], p["aff1"][1], relu=True, cin_real=self.deform_conv1.weight.shape[1])
-            off2 = p["off2"](f1, shift=p["offb2"], out_f32=True)
-            f2 = ops.dcn3d(f1, off2, p["w2"], p["cpad2"], p["aff2"][0], p["aff2"][1], relu=True)
-            # shared 2-D normal convs on (b*k) slices: cuDNN, bf16 channels-last (adjacent op)
-            x = f2.view(b * self.k, f2.shape[2], f2.shape[3], f2.shape[4]).permute(0, 3, 1, 2)
-            for (w2d, dil), rows in zip(p["nconv"], p["nconv_rows"]):
-                if rows is not None:
-                    xh = x.permute(0, 2, 3, 1)
-                    x = ops.conv2d_rows_multi(xh if xh.is_contiguous() else xh.contiguous(), rows, relu=True, slope=0.1).permute(0, 3, 1, 2)
-                    continue
-                x = F.conv2d(x, w2d, None, 1, dil, dil)                                # cuDNN, bf16 channels-last
-                x = ops.bias_act(x, None, 0.1) if x.shape[1] % 8 == 0 else F.leaky_relu(x, 0.1)   # LeakyReLU(0.1)
+            if self.use_deform:
+                off1 = p["off1"](fv, shift=p["offb1"], out_f32=True)
+                f1 = ops.dcn3d(fv, off1, p["w1"], p["cpad1"], p["aff1"][0], p["aff1"][1], relu=True, cin_real=self.deform_conv1.weight.shape[1])
+                off2 = p["off2"](f1, shift=p["offb2"], out_f32=True)
+                f2 = ops.dcn3d(f1, off2, p["w2"], p["cpad2"], p["aff2"][0], p["aff2"][1], relu=True)
+            else:
+                off1 = off2 = None
+                f1 = p["oc1"][0](fv, p["oc1"][1][0], p["oc1"][1][1], relu=True)
+                f2 = p["oc2"][0](f1, p["oc2"][1][0], p["oc2"][1][1], relu=True)
+            # shared 2-D normal convs on the (b*k) slices, channels-last, no layout change: [B,K,H4,W4,64] IS [B*K,H4,W4,64]
+            x = f2.view(b * self.k, f2.shape[2], f2.shape[3], f2.shape[4])
+            for wp, cout, dil in p["nconv"]:
+                x = ops.conv2d_tc(x, wp, cout, dil, relu=True, slope=0.1)          # last layer: 3 real + 5 zero channels
             # fused x4 bilinear upsample + sigmoid + mean over the k sampled planes + rescale to [-1, 1]
             from .ops_tail import anm_tail
-            normals.append(anm_tail(x.permute(0, 2, 3, 1).contiguous(), b, self.k))
-            off1s.append(off1[..., :81])
-            off2s.append(off2[..., :81])
+            normals.append(anm_tail(x, b, self.k))
+            off1s.append(off1[..., :81] if off1 is not None else None)
+            off2s.append(off2[..., :81] if off2 is not None else None)
         return normals, off1s, off2s

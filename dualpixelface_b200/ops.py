@@ -206,12 +206,13 @@ def asm_sample(x: torch.Tensor, tables: dict) -> torch.Tensor:
 
 
 def channel_stats(x: torch.Tensor) -> torch.Tensor:
-    """x [B,...,C] bf16 -> [B,C,2] fp32 (sum, sum of squares over all positions)."""
+    """x [B,...,C] bf16 -> [B,C,2] fp32 (sum, sum of squares over all positions); deterministic two-pass reduction."""
     _req(x, torch.bfloat16, "x")
     b, c = x.shape[0], x.shape[-1]
     p = x.numel() // (b * c)
     stats = torch.empty(b, c, 2, device=x.device, dtype=torch.float32)
-    check(lib().dpf_channel_stats(_p(x), _p(stats), b, p, c, _stream()), "dpf_channel_stats")
+    ws = torch.empty(int(lib().dpf_channel_stats_ws_floats(b, p, c)), device=x.device, dtype=torch.float32)   # caller-owned scratch
+    check(lib().dpf_channel_stats(_p(x), _p(stats), _p(ws), b, p, c, _stream()), "dpf_channel_stats")
     return stats
 
 
@@ -358,4 +359,47 @@ def conv2d_rows_multi(x, plan, bias=None, residual=None, relu=False, slope=0.0, 
         if residual is not None and (residual.shape[-1] != out.shape[-1] or y_coff != 0):
             raise _lib.DpfError("conv2d_rows_multi: the residual must have the layout of the output tensor")
         conv2d_rows(x, wp, n, None, sh, residual, relu, slope, out, y_coff + co, dil=dil)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# dedicated 2-D tcgen05 convolution (any dilation, Cin 32 | 64 | 96, Cout <= 96 in one launch): conv2d_tc.cu
+# ----------------------------------------------------------------------------------------------------------
+def pack_conv2d_tc_weight(w: torch.Tensor, cin_pad: Optional[int] = None) -> torch.Tensor:
+    """nn.Conv2d weight [Cout,Cin,3,3] -> bf16 [9 taps (kh,kw)][Cin_pad/8][Npad][8], Npad = ceil16(Cout) (zero padded)."""
+    cout, cin, kh, kw = w.shape
+    assert (kh, kw) == (3, 3)
+    cin_pad = cin_pad or cin
+    assert cin_pad % 8 == 0 and cin_pad >= cin
+    npad = (cout + 15) // 16 * 16
+    buf = torch.zeros(9, cin_pad, npad, device=w.device, dtype=torch.float32)
+    buf[:, :cin, :cout] = w.detach().float().permute(2, 3, 1, 0).reshape(9, cin, cout)
+    return buf.reshape(9, cin_pad // 8, 8, npad).permute(0, 1, 3, 2).contiguous().to(torch.bfloat16)
+
+
+def conv2d_tc(x: torch.Tensor, w_packed: torch.Tensor, cout: int, dil: int = 1, scale: Optional[torch.Tensor] = None,
+              shift: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, relu: bool = False, slope: float = 0.0,
+              out: Optional[torch.Tensor] = None, y_coff: int = 0, x_coff: int = 0) -> torch.Tensor:
+    """3x3 / stride 1 / dilation dil / padding dil conv on channels-last images in ONE launch (dpf_conv2d_tc_fwd):
+    x [N,H,W,Cx] bf16 (Cin = 8 * w_packed.shape[1] channels from x_coff) -> y [N,H,W,Cy] (ceil8(cout) channels at y_coff; the ones
+    beyond cout are exact zeros), y = act(conv * scale + shift + residual), act = LeakyReLU(slope) when relu (slope 0 = ReLU)."""
+    _req(x, torch.bfloat16, "x"); _req(w_packed, torch.bfloat16, "w_packed")
+    n, h, w, cx = x.shape
+    cin = w_packed.shape[1] * 8
+    cst = (cout + 7) // 8 * 8
+    if out is None:
+        out = torch.empty(n, h, w, cst, device=x.device, dtype=torch.bfloat16)
+    _req(out, torch.bfloat16, "out")
+    assert out.shape[:3] == (n, h, w) and w_packed.shape[0] == 9 and w_packed.shape[2] == (cout + 15) // 16 * 16
+    if residual is not None:
+        _req(residual, torch.bfloat16, "residual")
+        assert residual.shape == out.shape
+    for t, nm in ((scale, "scale"), (shift, "shift")):
+        if t is not None:
+            _req(t, torch.float32, nm)
+            assert t.numel() == cout
+    tm = _timing_begin()
+    check(lib().dpf_conv2d_tc_fwd(_p(x), _p(w_packed), _p(out), _p(scale), _p(shift), _p(residual), n, h, w, cin, cout, cx, x_coff,
+                                  out.shape[-1], y_coff, int(dil), int(relu), float(slope), _stream()), "dpf_conv2d_tc_fwd")
+    _timing_end(tm, f"conv2d_tc {cin}->{cout} d{dil}", 2.0 * 9 * cin * cout * n * h * w, "flop")
     return out

@@ -33,7 +33,8 @@ def conv3d_wgrad(x: torch.Tensor, dz: torch.Tensor, kind: int, cin: int | None =
         assert dz.shape[:4] == x.shape[:4], (x.shape, dz.shape)
     kd, kh, kw = _TAPS[kind]
     ntaps = kd * kh * kw
-    kwin = 32 if kind == KIND_S2 else cin               # input-channel window per launch
+    # input-channel window per launch (the kernel takes 32 | 64): wider layers (gwcnet's 96-channel first layer) are split
+    kwin = 32 if kind == KIND_S2 else (cin if cin <= 64 else (64 if cin % 64 == 0 else 32))
     dw = torch.zeros(ntaps, cin, cout, device=x.device, dtype=torch.float32)
     for ci in range(0, cin, kwin):
         for co in range(0, cout, 32):

@@ -132,7 +132,16 @@ def anm_train(anm, out3: torch.Tensor, disp: torch.Tensor, batch: dict):
     idx, coord, minmax = ops.anm_select(disp.detach().contiguous(), kinv, batch["abvalue"].float().contiguous(), anm.levels, anm.k)
     fv = GatherFn.apply(out3, idx, coord, minmax)
     x, offs = fv, []
-    for i, (dc, act) in enumerate(((anm.deform_conv1, anm.act1), (anm.deform_conv2, anm.act2))):
+    if not anm.use_deform:                                     # original_conv: two convbn_3d + ReLU on the conv engine
+        from .train_ops import ConvBNAct, LayerCfg
+        for seq in (anm.original_conv[0], anm.original_conv[2]):
+            conv, bn = seq[0], seq[1]
+            w = conv.weight
+            if x.shape[-1] > w.shape[1]:                           # the gathered volume is zero-padded 35 -> 64 channels
+                w = F.pad(w, (0, 0, 0, 0, 0, 0, 0, x.shape[-1] - w.shape[1]))
+            x = ConvBNAct.apply(x, w, bn.weight, bn.bias, None, LayerCfg(KIND_3x3x3, True, bn))
+        offs = [None, None]
+    for i, (dc, act) in enumerate(((anm.deform_conv1, anm.act1), (anm.deform_conv2, anm.act2)) if anm.use_deform else ()):
         off = OffsetConvFn.apply(x, dc.conv_offset.weight, dc.conv_offset.bias)
         # layer 1 reads the gathered volume: only its 32 cost channels need a gradient (the coordinates are constants)
         z = DCNFn.apply(x, off, dc.weight, 32 if (i == 0 and out3.shape[-1] == 32) else 64)

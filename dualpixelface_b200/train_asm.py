@@ -106,7 +106,7 @@ def asm_volume_train(cv, ref_feat, tar_feat):
     for rep, disp in levels:
         halves, stats = [], []
         for feat, direction in ((ref_feat, "forward"), (tar_feat, "backward")):
-            smp = AsmSampleFn.apply(feat, cv._tab(h, w, disp, direction, feat.device))
+            smp = cv.sample(feat, cv._tab(h, w, disp, direction, feat.device), train=True)
             m = ConvBNAct.apply(smp, conv1.weight, bn1.weight, bn1.bias, None, LayerCfg(KIND_1x3x3, True, bn1))
             stats.append(bn1.__dict__.get("_dpf_last_stats"))
             logits = ConvOnly.apply(m, conv2.weight, KIND_1x1x1)

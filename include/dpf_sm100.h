@@ -64,8 +64,11 @@ int dpf_asm_sample_fwd(const void* x, void* out, int B, int H4, int W4, int C, i
                        const int* ci, const float* cw, void* stream);
 int dpf_asm_blend_fwd(const void* samples, const void* logits, const float* in_a, const float* in_d, void* vol, int B,
                       int H4, int W4, int C, int S, int D_vol, int d0, int D_rep, int ch_off, int Cvol, void* stream);
-/* per-(b,c) sum and sum of squares over all positions of x [B,P,C] bf16 -> stats [B,C,2] fp32 (zeroed by the call). */
-int dpf_channel_stats(const void* x, float* stats, int B, long long P, int C, void* stream);
+/* per-(b,c) sum and sum of squares over all positions of x [B,P,C] bf16 -> stats [B,C,2] fp32 (fully written).  Deterministic:
+ * two passes over a fixed summation tree, no floating-point atomics; ws = caller-owned scratch of
+ * dpf_channel_stats_ws_floats(B, P, C) floats (no hidden allocation). */
+long long dpf_channel_stats_ws_floats(int B, long long P, int C);
+int dpf_channel_stats(const void* x, float* stats, float* ws, int B, long long P, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * (3) 3-D convolution, implicit GEMM on tcgen05 tensor cores (fp32 accumulation in TMEM), with the
@@ -199,10 +202,31 @@ int dpf_conv2d_fwd(const void* x, const void* w, void* y, const float* scale, co
                    int N, int H, int W, int Cin, int Cout, int x_cstride, int x_coff, int y_cstride, int y_coff,
                    int dil, int relu, float slope, void* stream);
 
+/* 2-D 3x3 convolution, stride 1, ANY dilation (pad = dil), Cin in {32, 64, 96}, Cout <= 96 in ONE launch, on a dedicated tcgen05
+ * implicit-GEMM kernel (conv2d_tc.cu: dilation by residue-class sub-images, input channels consumed in 32 / 48-channel windows
+ * that accumulate in TMEM, N = Cout).  Replaces the six bias-free Conv2d + LeakyReLU(0.1) `convtext` layers of ANM
+ * (src/model/stereodpnet/normal_module.py:14-19,59-66: 64->96->96->64->64->32->3, dilation 1,2,4,8,1,1):
+ *   y[n,h,w, y_coff+co] = act( conv(x[..., x_coff:x_coff+Cin]; w)[co] * scale[co] + shift[co] + residual[n,h,w, y_coff+co] )
+ * x [N,H,W,x_cstride], y / residual [N,H,W,y_cstride] bf16 channels-last; w bf16 [9 taps (kh,kw)][Cin/8][Npad][8] with
+ * Npad = dpf_conv2d_tc_npad(Cout) (output channels zero-padded); ceil8(Cout) channels are written (the extra ones are 0).
+ * scale / shift fp32 [Cout] or NULL; act(v) = relu ? (v > 0 ? v : slope*v) : v.  Deterministic (single MMA issuer). */
+int dpf_conv2d_tc_npad(int Cout);
+long long dpf_conv2d_tc_weight_elems(int Cin, int Cout);
+int dpf_conv2d_tc_fwd(const void* x, const void* w, void* y, const float* scale, const float* shift, const void* residual,
+                      int N, int H, int W, int Cin, int Cout, int x_cstride, int x_coff, int y_cstride, int y_coff,
+                      int dil, int relu, float slope, void* stream);
+
 /* ANM tail: bilinear x4 upsample (align_corners) -> sigmoid -> mean over K -> *2-1 in one pass.  Replaces final_layer and
  * the mean / rescale of ANM.forward (src/model/stereodpnet/normal_module.py:69-72,185-190).
  * x [B*K,H4,W4,3] bf16 (channels-last) -> out [B,3,4*H4,4*W4] fp32. */
 int dpf_anm_tail(const void* x, float* out, int B, int K, int H4, int W4, void* stream);
+/* Same op on a ROW TILE of the image and with a channel pitch: x [B*K, H4loc, W4, x_cstride] (3 real channels) holds the
+ * quarter-resolution rows q_row0 .. q_row0+H4loc-1 of an image that is H4glob rows tall; out [B,3,Hout,4*W4] holds the
+ * full-resolution rows y_row0 .. y_row0+Hout-1.  Source coordinates use the GLOBAL align_corners scale (H4glob-1)/(4*H4glob-1),
+ * so the tiles of a row-split image (BASELINE config 5) reproduce the untiled result exactly.  dpf_anm_tail == the call with
+ * x_cstride 3, H4glob = H4loc, q_row0 = y_row0 = 0, Hout = 4*H4loc. */
+int dpf_anm_tail_tile(const void* x, float* out, int B, int K, int H4loc, int W4, int x_cstride, int H4glob, int q_row0,
+                      int Hout, int y_row0, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * (8) Training-mode BatchNorm3d around the convolution (batch statistics; convbn_3d of src/module/asm/basics.py:32-36).

@@ -445,25 +445,37 @@ def anm_coord_volume(disp_sel: torch.Tensor, k_mat: torch.Tensor, abvalue: torch
 
 def anm_forward(out3: torch.Tensor, disp_full: torch.Tensor, k_mat: torch.Tensor, abvalue: torch.Tensor,
                 st: State, p: str, crange: Sequence[float], training: bool, dsample_num: int = 4,
-                stats=None, return_aux: bool = False):
+                stats=None, return_aux: bool = False, use_deform: bool = True, use_sampling: bool = True):
     """ANM.forward for one (cost, disparity) pair, normal_module.py:140-194.
 
     out3 [B,C,D,H4,W4]; disp_full [B,H,W] -> normal [B,3,H,W] in [-1,1].
+    ``use_sampling=False`` (:159-163) keeps all D cost slices with the level disparities; ``use_deform=False`` (:52-56,181-183)
+    replaces the two deformable layers by ``original_conv`` = two convbn_3d + ReLU.
     """
     b, c, d, h, w = out3.shape
     cost = out3.permute(0, 2, 1, 3, 4)                                # b d c h w
     disp_q = F.interpolate(disp_full.unsqueeze(1), scale_factor=0.25, mode="nearest") * 0.25
     crange_t = torch.as_tensor(np.asarray(crange), dtype=torch.float32, device=out3.device).view(1, -1, 1, 1)
-    idx = anm_select_levels(disp_q, crange_t, dsample_num)
-    sel_cost = torch.gather(cost, 1, idx.unsqueeze(2).expand(-1, -1, c, -1, -1))
-    sel_disp = torch.gather(crange_t.expand(b, d, h, w), 1, idx)
+    if use_sampling:
+        idx = anm_select_levels(disp_q, crange_t, dsample_num)
+        sel_cost = torch.gather(cost, 1, idx.unsqueeze(2).expand(-1, -1, c, -1, -1))
+        sel_disp = torch.gather(crange_t.expand(b, d, h, w), 1, idx)
+    else:
+        dsample_num = d
+        idx = torch.arange(d, device=out3.device).view(1, d, 1, 1).expand(b, d, h, w)
+        sel_cost, sel_disp = cost, crange_t.expand(b, d, h, w).to(cost.dtype)
     coord = anm_coord_volume(sel_disp, k_mat, abvalue)
     fv = torch.cat([sel_cost, coord.to(sel_cost.dtype)], dim=2).permute(0, 2, 1, 3, 4).contiguous()  # b c+3 k h w
 
-    f1, off1 = deform_conv_pack(fv, st, p + ".deform_conv1")
-    f1 = F.relu(_bn(f1, st, p + ".act1.0", training, stats_out=stats))
-    f2, off2 = deform_conv_pack(f1, st, p + ".deform_conv2")
-    f2 = F.relu(_bn(f2, st, p + ".act2.0", training, stats_out=stats))
+    if use_deform:
+        f1, off1 = deform_conv_pack(fv, st, p + ".deform_conv1")
+        f1 = F.relu(_bn(f1, st, p + ".act1.0", training, stats_out=stats))
+        f2, off2 = deform_conv_pack(f1, st, p + ".deform_conv2")
+        f2 = F.relu(_bn(f2, st, p + ".act2.0", training, stats_out=stats))
+    else:
+        off1 = off2 = None
+        f1 = F.relu(_convbn3(fv, st, p + ".original_conv.0", 1, training, stats))
+        f2 = F.relu(_convbn3(f1, st, p + ".original_conv.2", 1, training, stats))
 
     feat = f2.permute(0, 2, 1, 3, 4).reshape(b * dsample_num, f2.shape[1], h, w)
     for i, dil in enumerate((1, 2, 4, 8, 1, 1)):                      # convtext stack, normal_module.py:59-66
@@ -609,7 +621,7 @@ def cosine_normal_loss(pred: torch.Tensor, gt: torch.Tensor, mask: torch.Tensor)
 # whole models
 # --------------------------------------------------------------------------------------
 
-SDP_CFG = dict(mindisp=-4, maxdisp=12, level=8, inplanes=32, block_stack=1, dsample_num=4,
+SDP_CFG = dict(mindisp=-4, maxdisp=12, level=8, inplanes=32, block_stack=1, dsample_num=4, use_deform=True, use_sampling=True,
                loss_weight=(1.0, 0.7, 0.5), lambdas=(1.0, 1.0))
 PSM_CFG = dict(mindisp=-4, maxdisp=12, level=8, inplanes=32, cost_volume="psmnet", group_num=40,
                loss_weight=(1.0, 0.7, 0.5), lambdas=(1.0,))
@@ -643,7 +655,8 @@ def stereodpnet_forward(batch: dict, st: State, training: bool, cfg: dict = SDP_
     normal = None
     if predict_normal:
         normal = anm_forward(outs[0], disps[0], batch["K"], batch["abvalue"], st, "normal_estimator", crange,
-                             training, cfg["dsample_num"], stats=stats).unsqueeze(1)
+                             training, cfg["dsample_num"], stats=stats, use_deform=cfg.get("use_deform", True),
+                             use_sampling=cfg.get("use_sampling", True)).unsqueeze(1)
     res = {"pred_depth": torch.stack(disps, 1), "prob_depth": torch.stack(probs, 1), "pred_normal": normal,
            "ref_feature": ref.max(1)[0]}
     if stages is not None:

@@ -53,9 +53,11 @@ def test_costvol_concat_diff_exact(ops, shape):
     assert torch.equal(from_ndhwc(got_d).cpu(), want_d)                               # one bf16 rounding of an fp32 difference
 
 
-@pytest.mark.parametrize("groups", [8, 16, 32])
-def test_costvol_gwc(ops, groups):
-    ref, tgt = feat((2, 32, 20, 33), 23), feat((2, 32, 20, 33), 24)
+@pytest.mark.parametrize("c,groups", [(32, 8), (32, 16), (32, 32), (64, 8), (64, 32), (128, 8), (16, 8)])
+def test_costvol_gwc(ops, c, groups):
+    """every lanes-per-group / groups-per-lane class of the warp-shuffle correlation: 4, 2, 1 channels per group (several group
+    sums per lane), 8 (one lane per group) and 16 (xor-shuffle reduction over two lanes); ragged widths (33 = partial strip)."""
+    ref, tgt = feat((2, c, 20, 33), 23), feat((2, c, 20, 33), 24)
     want = O.psm_gwc_volume(ref.float(), tgt.float(), CR, groups)
     got = ops.costvol_fwd(nhwc(ref).cuda(), nhwc(tgt).cuda(), SHIFTS, "gwc", groups)
     assert rel_err(from_ndhwc(got), want) < 1e-2                                      # 1 bf16 ulp of the output

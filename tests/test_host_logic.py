@@ -51,10 +51,19 @@ def test_nearest_tables_bitexact_at_baseline_resolutions(golden_stages, hw, dire
     assert tb["ci"][0, -1, 0].item() == -1                                   # last column rounds out of bounds
 
 
-def test_fractional_phase_is_refused():
-    with pytest.raises(NotImplementedError):
-        build_tables(16, 24, 0.5, "forward")
-    build_tables(16, 24, 0.5, "forward", (True, True, False))              # fine without the phase sample
+@pytest.mark.parametrize("disp", [-0.5, 0.5, 2.5])
+@pytest.mark.parametrize("direction", ["forward", "backward"])
+def test_fractional_phase_shift_matches_reference(golden_stages, disp, direction):
+    """cached_first_level=False: a fractional Fourier (phase) shift is not a table sample; build_tables hands out the row-frequency
+    rotation and shift_tables.fourier_row_shift evaluates asm.py:112-125 (legacy C2R irfft included) == the reference's samples."""
+    from dualpixelface_b200.shift_tables import fourier_row_shift
+    g = torch.Generator().manual_seed(11)
+    x = torch.relu(torch.randn(2, 4, 16, 24, generator=g))
+    tb = build_tables(16, 24, disp, direction)
+    assert tb["ri"].shape[0] == 2 and tb["rot"].shape == (16,)              # nearest + bilinear tables, phase by FFT
+    got = torch.cat([apply_tables(x, tb), fourier_row_shift(x.permute(0, 2, 3, 1).contiguous(), tb["rot"]).permute(0, 3, 1, 2).unsqueeze(-1)], -1)
+    want = torch.as_tensor(golden_stages[f"shift/{disp}/{direction}"])
+    assert torch.allclose(got[..., 0], want[..., 0], atol=0) and torch.allclose(got[..., 1:], want[..., 1:], atol=1e-5)
 
 
 def test_plan_launches():

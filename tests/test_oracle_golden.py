@@ -153,3 +153,36 @@ def test_whole_model_grads_psmnet(state_shapes):
     for key in ("aggregation.dres0.0.0.weight", "aggregation.classif3.2.weight",
                 "aggregation.dres4.conv6.0.weight", "feature_extraction.firstconv.0.0.weight"):
         close(gold[f"train/grad/{key}"], st[key].grad, 1e-4)
+
+
+# ---- non-default configurations, fixtures from tests/golden/make_golden_variants.py (the unmodified reference with overrides) ----
+def _variant_case(tag, name, cfg):
+    import json
+    gold = np.load(GOLDEN / "variants.npz")
+    shapes = {k: tuple(v) for k, v in json.loads(bytes(gold[f"{tag}/state_keys"]).decode()).items()}
+    st = synth_state(shapes, seed=1)
+    hw = (256, 256) if name == "psmnet" else (64, 96)
+    batch = synthetic_batch(2, hw[0], hw[1], training=True, seed=0)
+    fwd = O.psmnet_forward if name == "psmnet" else O.stereodpnet_forward
+    stats = {}
+    with torch.no_grad():
+        fwd(dict(batch), st, True, cfg=cfg, stats=stats)
+        st = O.calibrate_running_stats(st, stats)
+        res = fwd(dict(batch), st, False, cfg=cfg)
+    return gold, res, shapes
+
+
+@pytest.mark.parametrize("sampling", [True, False])
+def test_oracle_anm_without_deformable_convs(sampling):
+    """use_deform=false (original_conv) x use_sampling=true/false == the reference's STEREODPNET with those overrides."""
+    tag = f"sdp_nodeform_{'sampling' if sampling else 'nosampling'}"
+    gold, res, shapes = _variant_case(tag, "stereodpnet", dict(O.SDP_CFG, use_deform=False, use_sampling=sampling))
+    assert "normal_estimator.original_conv.0.0.weight" in shapes and not any("deform_conv" in k for k in shapes)
+    close(gold[f"{tag}/pred_depth"], res["pred_depth"], 1e-5)
+    close(gold[f"{tag}/pred_normal"], res["pred_normal"], 1e-5)
+
+
+def test_oracle_gwcnet_style():
+    gold, res, shapes = _variant_case("psm_gwcnet8", "psmnet", dict(O.PSM_CFG, cost_volume="gwcnet", group_num=8))
+    assert shapes["aggregation.dres0.0.0.weight"] == (32, 72, 3, 3, 3)
+    close(gold["psm_gwcnet8/pred_depth"], res["pred_depth"], 1e-5)
