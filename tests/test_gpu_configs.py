@@ -66,7 +66,7 @@ def test_config1_psmnet_eval_448():
     err = (got["pred_depth"].float().cpu() - want["pred_depth"]).abs()
     print(f"config 1 (PSMNet 448x448 eval): disparity max err {err.max():.4f} px, mean {err.mean():.5f} px")
     assert got["pred_depth"].shape == (1, 1, 448, 448)
-    assert err.max().item() < 0.40 and err.mean().item() < 0.06
+    assert err.max().item() < 0.30 and err.mean().item() < 0.04       # measured on a B200: 0.147 / 0.0196 px
 
 
 def test_config3_stereodpnet_training_step_1120x1680(fp32_oracle_on_gpu):
@@ -102,16 +102,21 @@ def test_config3_stereodpnet_training_step_1120x1680(fp32_oracle_on_gpu):
     print(f"config 3 (1x1120x1680 train): disparity max err {d_err.max():.4f} px mean {d_err.mean():.5f}; normal max err "
           f"{n_err.max():.4f} mean {n_err.mean():.5f}; peak memory {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
     assert res["pred_depth"].shape == (1, 3, 1120, 1680) and res["pred_normal"].shape == (1, 1, 3, 1120, 1680)
-    assert d_err.max().item() < 0.32 and d_err.mean().item() < 0.032 and n_err.mean().item() < 1e-2
+    assert d_err.max().item() < 0.20 and d_err.mean().item() < 0.016 and n_err.mean().item() < 9.4e-3   # measured 0.098 / 0.0081 / 0.0047
     for name in ("smoothL1_loss", "cosine_loss", "final_loss"):
         g_, r_ = float(res[name].detach()), float(want[name])
         print(f"   {name}: {g_:.5f} vs {r_:.5f}")
-        assert abs(g_ - r_) < 1e-2 * abs(r_)
+        assert abs(g_ - r_) < 1.5e-3 * abs(r_)                       # measured 5.2e-4 relative
     params = dict(model.named_parameters())
+    # Whole-network gradients of two forward passes that differ by bf16 rounding: ReLU-mask flips dominate (the backward kernels
+    # themselves are held to 0.999 / 2e-2 with teacher-forced activations in test_gpu_teacher_forced.py).  Floors = measured on
+    # a B200 minus a margin: aggregation 0.998-1.000, mask conv 0.990, encoder lastconv 0.986, normal branch 0.84-0.89 (its
+    # gradients are ill-conditioned in the branch input at random init, see tools/anm_grad_sensitivity.py).
     for k in probe:
         c, r = cos(params[k].grad, ref[k]), rel2(params[k].grad, ref[k])
         print(f"   grad {k}: cosine {c:.4f}, relative L2 error {r:.4f}")
-        assert c > (0.70 if k.startswith("normal_estimator.") else 0.90), (k, c)
+        floor = 0.75 if k.startswith("normal_estimator.") else (0.996 if k.startswith("aggregation.") else 0.975)
+        assert c > floor, (k, c)
 
 
 def test_config4_psmnet_training_step_512x768(fp32_oracle_on_gpu):
@@ -137,20 +142,21 @@ def test_config4_psmnet_training_step_512x768(fp32_oracle_on_gpu):
     print(f"config 4 (PSMNet 2x512x768 train): disparity max err {d_err.max():.4f} px mean {d_err.mean():.5f}; "
           f"loss {float(res['final_loss'].detach()):.5f} vs {float(want['final_loss'].detach()):.5f}")
     assert res["pred_depth"].shape == (2, 3, 512, 768)
-    assert d_err.max().item() < 0.32 and d_err.mean().item() < 0.032
-    assert abs(float(res["final_loss"].detach()) - float(want["final_loss"].detach())) < 1e-2 * float(want["final_loss"].detach())
+    assert d_err.max().item() < 0.18 and d_err.mean().item() < 0.015        # measured 0.087 / 0.0073 px
+    assert abs(float(res["final_loss"].detach()) - float(want["final_loss"].detach())) < 1.2e-3 * float(want["final_loss"].detach())
     params = dict(model.named_parameters())
     for k in probe:
         c, r = cos(params[k].grad, so[k].grad), rel2(params[k].grad, so[k].grad)
         print(f"   grad {k}: cosine {c:.4f}, relative L2 error {r:.4f}")
-        assert c > 0.90, (k, c)
+        assert c > (0.94 if "firstconv" in k else 0.993), (k, c)          # measured: >= 0.9969 (firstconv 0.961: deepest layer)
 
 
 def test_inference_is_run_to_run_deterministic():
     """Two forward passes of the same model on the same input.  Several MMA-issuing warps accumulate into one TMEM tile
-    (conv3d_tc.cu) and the InstanceNorm / BatchNorm statistics use fp32 atomics, so the accumulation ORDER is not fixed by the
-    program: the test records whether the outputs are bit-equal and holds them to the stated bound --
-    disparity within 2e-3 px and an identical ANM level set on all but a vanishing fraction of pixels."""
+    (conv3d_tc.cu) in round 1 and the InstanceNorm statistics used fp32 atomics: run-to-run differences of up to 0.26 px were
+    measured.  Round 2: one MMA-issuing thread per CTA (fixed accumulation order, DPF_CONV_ISSUERS=1 default) and a two-pass
+    statistics reduction without atomics -> the inference path must be BIT-IDENTICAL from run to run (north_star: bit-exact
+    disparity-index selection)."""
     from test_gpu_models import build, calibrated_state
     small = synthetic_batch(2, 128, 160, training=True, seed=0)
     st, _ = calibrated_state("stereodpnet", small)
@@ -167,12 +173,12 @@ def test_inference_is_run_to_run_deterministic():
     dd = max((outs[0][0] - o[0]).abs().max().item() for o in outs[1:])
     dn = max((outs[0][1] - o[1]).abs().max().item() for o in outs[1:])
     print(f"determinism over 3 runs: max |d disparity| {dd:.3e} px, max |d normal| {dn:.3e}; bit-equal: {dd == 0.0 and dn == 0.0}")
-    assert dd <= 2e-3 and dn <= 2e-2
+    assert dd == 0.0 and dn == 0.0
 
 
 @pytest.mark.parametrize("cin,cout,kind", [(32, 32, 0), (64, 32, 0), (32, 64, 1), (64, 32, 2)])
 def test_conv_kernel_run_to_run(cin, cout, kind):
-    """The same convolution launched 4 times: bit-equality is recorded; the bound is one bf16 ulp of the output."""
+    """The same convolution launched 4 times must give bit-identical outputs (single MMA issuer, fixed accumulation order)."""
     from dualpixelface_b200.layers import TCConv3d
     g = torch.Generator(device="cuda").manual_seed(3)
     shape = (2, 4, 70, 105) if kind == 2 else (2, 8, 140, 210)
@@ -184,4 +190,4 @@ def test_conv_kernel_run_to_run(cin, cout, kind):
     diff = max((ys[0] - y).abs().max().item() for y in ys[1:])
     nd = max(int((ys[0] != y).sum()) for y in ys[1:])
     print(f"conv kind {kind} {cin}->{cout}: max run-to-run difference {diff:.3e} ({nd} of {ys[0].numel()} elements differ)")
-    assert diff <= 2.0 ** -7 * ys[0].abs().max().item()
+    assert diff == 0.0 and nd == 0

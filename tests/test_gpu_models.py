@@ -51,14 +51,16 @@ def test_model_eval_parity(name, hw):
     err = (d_got - d_want).abs()
     rng = float(d_want.max() - d_want.min())
     print(f"{name} {hw}: disparity max err {err.max():.4f} mean {err.mean():.5f} (range {rng:.2f})")
-    assert err.max().item() < 2e-2 * 16.0 and err.mean().item() < 2e-3 * 16.0   # 2e-2 (bf16 path) of the 16 px disparity span (mindisp..maxdisp)
+    # north_star tolerance for the bf16 path: 2e-2 relative (= 0.32 px of the 16 px disparity span); held to <= 2x what a B200
+    # measures instead: max 0.073-0.090 px, mean 0.0095-0.0102 px
+    assert err.max().item() < 0.18 and err.mean().item() < 0.02
     assert (got["prob_depth"].float().cpu() - want["prob_depth"]).abs().max().item() < 2e-2
     fe = (got["ref_feature"].cpu() - want["ref_feature"]).abs().max().item()
     assert fe < 2e-2 * want["ref_feature"].abs().max().item()
     if name == "stereodpnet":
         n_err = (got["pred_normal"].float().cpu() - want["pred_normal"]).abs()
         print(f"   normal max err {n_err.max():.4f} mean {n_err.mean():.5f}")
-        assert n_err.mean().item() < 2e-2 and n_err.max().item() < 0.15
+        assert n_err.mean().item() < 7e-3 and n_err.max().item() < 0.125          # measured mean 0.0027-0.0034, max 0.051-0.062
 
 
 def test_cpu_input_fails_loudly():
@@ -81,7 +83,7 @@ def test_model_default_path_bf16_encoder():
     err = (got["pred_depth"].float().cpu() - want["pred_depth"]).abs()
     n_err = (got["pred_normal"].float().cpu() - want["pred_normal"]).abs()
     print(f"bf16 encoder: disparity max err {err.max():.4f} mean {err.mean():.5f}; normal mean {n_err.mean():.5f}")
-    assert err.mean().item() < 2e-2 * 16.0 / 4 and n_err.mean().item() < 2e-2
+    assert err.mean().item() < 0.11 and n_err.mean().item() < 0.02            # measured 0.055 px / 0.0103 (bf16 encoder included)
 
 
 def test_psmnet_gwcnet_style():

@@ -9,7 +9,7 @@ gradient and weight gradient of all kinds, BatchNorm backward, D3D backward) wit
 relative L2 <= 2e-2 (north_star's bf16 tolerance) for every one of the parameters of the 3-D aggregation.
 
 The oracle code runs on the GPU in fp32 (TF32 off); `traced_aggregation` restates O.aggregation_lowres layer by layer only to
-expose each layer's output, and is pinned bit-exactly against O.aggregation_lowres first.
+expose each layer's output, and is pinned against O.aggregation_lowres first (to cuDNN's own run-to-run noise, 1e-4).
 """
 import json
 
@@ -91,7 +91,8 @@ def test_aggregation_gradients_teacher_forced(shape):
     with torch.no_grad():
         ref_costs, ref_outs = O.aggregation_lowres(vol.float(), st, "aggregation", True)
         tr_costs, tr_outs = traced_aggregation(vol.float(), st, "aggregation", {})
-    assert all(torch.equal(a, b_) for a, b_ in zip(ref_costs + ref_outs, tr_costs + tr_outs))
+    # (not torch.equal: cuDNN's fp32 ConvTranspose3d forward is a backward-data algorithm with atomics, two runs differ in the last bits)
+    assert all(torch.allclose(a, b_, rtol=1e-4, atol=1e-5) for a, b_ in zip(ref_costs + ref_outs, tr_costs + tr_outs))
     keys = [k for k in st if k.endswith(".weight") or k.endswith(".bias")]
     so = dict(st)
     for k in keys:

@@ -113,8 +113,8 @@ def test_psmnet_training_step_matches_reference():
     d_err = (res["pred_depth"].detach().float().cpu() - torch.as_tensor(gold["train/pred_depth"])).abs()
     print(f"train pred_depth max err {d_err.max():.4f} mean {d_err.mean():.5f}; loss {float(res['final_loss'].detach()):.5f} vs {float(gold['train/final_loss']):.5f}")
     assert res["pred_depth"].shape[1] == 3
-    assert d_err.max().item() < 2e-2 * 16.0 and d_err.mean().item() < 2e-3 * 16.0
-    assert abs(float(res["final_loss"]) - float(gold["train/final_loss"])) < 2e-2 * float(gold["train/final_loss"])
+    assert d_err.max().item() < 0.17 and d_err.mean().item() < 0.015          # measured on a B200: 0.085 / 0.0073 px
+    assert abs(float(res["final_loss"].detach()) - float(gold["train/final_loss"])) < 1.5e-3 * float(gold["train/final_loss"])   # measured 4.3e-4
     params = dict(model.named_parameters())
     # bf16 activations AND bf16 activation-gradients through 28 conv+BN layers: the error grows with depth from the loss
     # (measured cosine 1.0000 / 0.9999 / 0.994 / 0.958); thresholds are per depth.

@@ -78,7 +78,7 @@ def test_stereodpnet_training_step_depth_only():
     print(f"SDP train pred_depth max err {d_err.max():.4f} mean {d_err.mean():.5f}; loss {float(res['final_loss'].detach()):.5f} "
           f"vs {float(want['final_loss'].detach()):.5f}")
     assert res["pred_depth"].shape[1] == 3 and res["pred_normal"] is None
-    assert d_err.max().item() < 2e-2 * 16.0 and d_err.mean().item() < 2e-3 * 16.0
+    assert d_err.max().item() < 0.15 and d_err.mean().item() < 0.014             # measured on a B200: 0.0745 / 0.0070 px
     assert abs(float(res["final_loss"].detach()) - float(want["final_loss"].detach())) < 2e-2 * float(want["final_loss"].detach())
     params = dict(model.named_parameters())
     for k in probe:
@@ -165,7 +165,7 @@ def test_stereodpnet_training_step_with_normals():
     d_err = (res["pred_depth"].detach().float().cpu() - want["pred_depth"].detach()).abs()
     n_err = (res["pred_normal"].detach().float().cpu() - want["pred_normal"].detach()).abs()
     print(f"SDP train (normals) depth max err {d_err.max():.4f}; normal max err {n_err.max():.4f} mean {n_err.mean():.5f}")
-    assert d_err.max().item() < 2e-2 * 16.0 and n_err.mean().item() < 5e-3
+    assert d_err.max().item() < 0.15 and n_err.mean().item() < 4.5e-3           # measured on a B200: 0.071 px / 0.00215
     # the k sampled levels are a discrete function of the predicted disparity: where the two disparities straddle a
     # selection boundary the branch sees a different level set (inherent to bf16 vs fp32 forward, not to the backward kernels)
     crange = torch.tensor(model.normal_estimator.levels).view(1, -1, 1, 1)
@@ -179,7 +179,7 @@ def test_stereodpnet_training_step_with_normals():
     for name in ("smoothL1_loss", "cosine_loss", "final_loss"):
         got, ref = float(res[name].detach()), float(want[name].detach())
         print(f"   {name}: {got:.5f} vs {ref:.5f}")
-        assert abs(got - ref) < 2e-2 * abs(ref)
+        assert abs(got - ref) < 1.5e-3 * abs(ref)                            # measured <= 5.2e-4 relative
     params = dict(model.named_parameters())
     for k in probe:
         got, ref = params[k].grad.float().cpu(), so[k].grad
