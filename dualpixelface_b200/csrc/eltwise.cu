@@ -8,6 +8,7 @@
 //   y[p, y_coff + c] = act( x[p, c] + bias[c] + res[p, c] ),  act(v) = v > 0 ? v : slope * v   (slope 0 = ReLU, 1 = none)
 #include "../../include/dpf_sm100.h"
 #include "dpf_common.cuh"
+#include <algorithm>
 #include "dpf_ptx.cuh"
 
 namespace {
@@ -109,7 +110,14 @@ extern "C" int dpf_anm_tail_tile(const void* x, float* out, int B, int K, int H4
                                  int Hout, int y_row0, void* stream) {
   DPF_REQUIRE(x && out, "dpf_anm_tail: null pointer");
   DPF_REQUIRE(B > 0 && B <= 65535 && K >= 1 && H4loc >= 1 && W4 > 1 && H4glob > 1 && x_cstride >= 3 && Hout >= 1, "dpf_anm_tail: bad shape");
-  DPF_REQUIRE(q_row0 >= 0 && q_row0 + H4loc <= H4glob && y_row0 >= 0 && y_row0 + Hout <= 4 * H4glob, "dpf_anm_tail: tile outside the image");
+  DPF_REQUIRE(y_row0 >= 0 && y_row0 + Hout <= 4 * H4glob, "dpf_anm_tail: output rows outside the image");
+  {   // every quarter-res row the output rows interpolate from must be inside the local tile (halo rows may lie outside the image)
+    const float sh = static_cast<float>(H4glob - 1) / static_cast<float>(4 * H4glob - 1);
+    const int lo = static_cast<int>(sh * static_cast<float>(y_row0));
+    const int hi = std::min(static_cast<int>(sh * static_cast<float>(y_row0 + Hout - 1)) + 1, H4glob - 1);
+    DPF_REQUIRE(lo >= q_row0 && hi < q_row0 + H4loc, "dpf_anm_tail: the tile (rows %d..%d) does not cover rows %d..%d", q_row0,
+                q_row0 + H4loc - 1, lo, hi);
+  }
   dim3 grid((4 * W4 + 31) / 32, (Hout + 7) / 8, B);
   anm_tail_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, K, H4loc, W4,
                                                                       x_cstride, H4glob, q_row0, Hout, y_row0);

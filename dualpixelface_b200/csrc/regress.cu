@@ -8,6 +8,7 @@
 // Memory-bound: reads D*4 B per quarter-res pixel, writes 4 B per full-res pixel (+ 4*D*4 B if `prob` is requested).
 #include "../../include/dpf_sm100.h"
 #include "dpf_common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -42,20 +43,27 @@ __device__ __forceinline__ void plane_values(const float* __restrict__ cost, siz
   }
 }
 
+// Row tiles (BASELINE config 5): `cost` holds the quarter-resolution rows q_row0 .. q_row0+H4loc-1 of an image that is H4 rows
+// tall, `disp` / `prob` the full-resolution rows y_row0 .. y_row0+Hout-1; the source coordinates use the GLOBAL align_corners
+// scale, so the tiles reproduce the untiled result exactly.  Untiled: H4loc = H4, q_row0 = y_row0 = 0, Hout = 4*H4.
 template <int D>
 __global__ void __launch_bounds__(kTX* kTY) regress_fwd_kernel(const float* __restrict__ cost, float* __restrict__ disp,
                                                                float* __restrict__ prob, int H4, int W4, float mindisp,
-                                                               float step) {
+                                                               float step, int H4loc, int q_row0, int Hout, int y_row0) {
   const int H = 4 * H4, W = 4 * W4;
   const int x = blockIdx.x * kTX + threadIdx.x;
-  const int y = blockIdx.y * kTY + threadIdx.y;
+  const int yl = blockIdx.y * kTY + threadIdx.y;             // local output row
   const int b = blockIdx.z;
-  if (x >= W || y >= H) return;
+  if (x >= W || yl >= Hout) return;
+  const int y = y_row0 + yl;
   const float sh = static_cast<float>(H4 - 1) / static_cast<float>(H - 1);
   const float sw = static_cast<float>(W4 - 1) / static_cast<float>(W - 1);
   const float sd = static_cast<float>(D - 1) / static_cast<float>(4 * D - 1);
-  const Axis ay = src_index(y, sh, H4), ax = src_index(x, sw, W4);
-  const size_t plane = static_cast<size_t>(H4) * W4;
+  Axis ay = src_index(y, sh, H4);
+  const Axis ax = src_index(x, sw, W4);
+  ay.i0 = min(max(ay.i0 - q_row0, 0), H4loc - 1);             // global quarter-res rows -> rows of the local tile
+  ay.i1 = min(max(ay.i1 - q_row0, 0), H4loc - 1);
+  const size_t plane = static_cast<size_t>(H4loc) * W4;
   float c[D];
   plane_values<D>(cost + static_cast<size_t>(b) * D * plane, plane, W4, ay, ax, c);
   float v[4 * D];
@@ -78,11 +86,11 @@ __global__ void __launch_bounds__(kTX* kTY) regress_fwd_kernel(const float* __re
     sed = fmaf(e, mindisp + step * static_cast<float>(k), sed);
   }
   const float inv = 1.0f / se;
-  disp[(static_cast<size_t>(b) * H + y) * W + x] = sed * inv;
+  disp[(static_cast<size_t>(b) * Hout + yl) * W + x] = sed * inv;
   if (prob != nullptr) {
-    float* pp = prob + (static_cast<size_t>(b) * 4 * D * H + y) * W + x;
+    float* pp = prob + (static_cast<size_t>(b) * 4 * D * Hout + yl) * W + x;
 #pragma unroll
-    for (int k = 0; k < 4 * D; ++k) pp[static_cast<size_t>(k) * H * W] = v[k] * inv;
+    for (int k = 0; k < 4 * D; ++k) pp[static_cast<size_t>(k) * Hout * W] = v[k] * inv;
   }
 }
 
@@ -168,17 +176,30 @@ __global__ void __launch_bounds__(kTX* kTY) regress_bwd_kernel(const float* __re
 
 }  // namespace
 
+extern "C" int dpf_regress_fwd_tile(const float* cost, float* disp, float* prob, int B, int D, int H4loc, int W4, int H4glob,
+                                    int q_row0, int Hout, int y_row0, float mindisp, float step, void* stream) {
+  DPF_REQUIRE(cost && disp, "dpf_regress_fwd: null pointer");
+  DPF_REQUIRE(B > 0 && B <= 65535 && H4loc >= 1 && H4glob > 1 && W4 > 1 && Hout >= 1, "dpf_regress_fwd: bad shape B=%d H4=%d W4=%d", B, H4glob, W4);
+  DPF_REQUIRE(D == 8 || D == 4 || D == 16, "dpf_regress_fwd: D=%d not in {4,8,16}", D);
+  DPF_REQUIRE(y_row0 >= 0 && y_row0 + Hout <= 4 * H4glob, "dpf_regress_fwd: output rows outside the image");
+  {   // every quarter-res row the output rows interpolate from must be inside the local tile
+    const float sh = static_cast<float>(H4glob - 1) / static_cast<float>(4 * H4glob - 1);
+    const int lo = static_cast<int>(sh * static_cast<float>(y_row0));
+    const int hi = std::min(static_cast<int>(sh * static_cast<float>(y_row0 + Hout - 1)) + 1, H4glob - 1);
+    DPF_REQUIRE(lo >= q_row0 && hi < q_row0 + H4loc, "dpf_regress_fwd: the cost tile (rows %d..%d) does not cover rows %d..%d",
+                q_row0, q_row0 + H4loc - 1, lo, hi);
+  }
+  dim3 grid((4 * W4 + kTX - 1) / kTX, (Hout + kTY - 1) / kTY, B), block(kTX, kTY);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (D == 8) regress_fwd_kernel<8><<<grid, block, 0, st>>>(cost, disp, prob, H4glob, W4, mindisp, step, H4loc, q_row0, Hout, y_row0);
+  else if (D == 4) regress_fwd_kernel<4><<<grid, block, 0, st>>>(cost, disp, prob, H4glob, W4, mindisp, step, H4loc, q_row0, Hout, y_row0);
+  else regress_fwd_kernel<16><<<grid, block, 0, st>>>(cost, disp, prob, H4glob, W4, mindisp, step, H4loc, q_row0, Hout, y_row0);
+  return dpf::after_launch("dpf_regress_fwd");
+}
+
 extern "C" int dpf_regress_fwd(const float* cost, float* disp, float* prob, int B, int D, int H4, int W4, float mindisp,
                                float step, void* stream) {
-  DPF_REQUIRE(cost && disp, "dpf_regress_fwd: null pointer");
-  DPF_REQUIRE(B > 0 && B <= 65535 && H4 > 1 && W4 > 1, "dpf_regress_fwd: bad shape B=%d H4=%d W4=%d", B, H4, W4);
-  DPF_REQUIRE(D == 8 || D == 4 || D == 16, "dpf_regress_fwd: D=%d not in {4,8,16}", D);
-  dim3 grid((4 * W4 + kTX - 1) / kTX, (4 * H4 + kTY - 1) / kTY, B), block(kTX, kTY);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (D == 8) regress_fwd_kernel<8><<<grid, block, 0, st>>>(cost, disp, prob, H4, W4, mindisp, step);
-  else if (D == 4) regress_fwd_kernel<4><<<grid, block, 0, st>>>(cost, disp, prob, H4, W4, mindisp, step);
-  else regress_fwd_kernel<16><<<grid, block, 0, st>>>(cost, disp, prob, H4, W4, mindisp, step);
-  return dpf::after_launch("dpf_regress_fwd");
+  return dpf_regress_fwd_tile(cost, disp, prob, B, D, H4, W4, H4, 0, 4 * H4, 0, mindisp, step, stream);
 }
 
 extern "C" int dpf_regress_bwd(const float* cost, const float* ddisp, float* dcost, int B, int D, int H4, int W4,

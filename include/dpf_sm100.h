@@ -119,6 +119,12 @@ int dpf_regress_fwd(const float* cost, float* disp, float* prob, int B, int D, i
 /* dcost [B,D,H4,W4] (zeroed by the call) from ddisp [B,H,W]; recomputes the softmax. */
 int dpf_regress_bwd(const float* cost, const float* ddisp, float* dcost, int B, int D, int H4, int W4, float mindisp,
                     float step, void* stream);
+/* dpf_regress_fwd on a ROW TILE (BASELINE config 5): cost [B,D,H4loc,W4] holds the quarter-resolution rows q_row0 ..
+ * q_row0+H4loc-1 of an image H4glob rows tall (q_row0 may be negative / the tile may extend past the image: halo rows), disp
+ * [B,Hout,4*W4] (and prob [B,4D,Hout,4*W4]) the full-resolution rows y_row0 .. y_row0+Hout-1.  Source coordinates use the GLOBAL
+ * align_corners scale, so tiles reproduce the untiled result exactly; the call fails if the tile does not cover the rows it needs. */
+int dpf_regress_fwd_tile(const float* cost, float* disp, float* prob, int B, int D, int H4loc, int W4, int H4glob, int q_row0,
+                         int Hout, int y_row0, float mindisp, float step, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * (5) ANM front end.  Replaces the nearest x0.25 down-sample, sample_with_sort and grid_maker_3d of
