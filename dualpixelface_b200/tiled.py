@@ -252,7 +252,8 @@ class TiledStereoDPNet:
         self.m = model
         self.t = RowTiling(height, rank, world, group)
         dev = next(model.parameters()).device
-        self.enc = TiledSDPEncoder(model.feature_extraction, self.t, dev)
+        # encoder precision follows the model: bf16 (the bench configuration) or fp32 (encoder_autocast off: parity tests)
+        self.enc = TiledSDPEncoder(model.feature_extraction, self.t, dev, torch.bfloat16 if model.encoder_autocast else torch.float32)
         model.aggregation._build()
         model.cost_volume._pack()
         if model.predict_normal:
