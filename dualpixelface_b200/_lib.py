@@ -64,6 +64,8 @@ SIGNATURES = {
     "dpf_conv2d_tc_weight_elems": (c_ll, [c_int, c_int]),
     "dpf_conv2d_tc_fwd": (c_int, [c_void_p] * 6 + [c_int] * 11 + [c_float, c_void_p]),
     "dpf_anm_tail_tile": (c_int, [c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
+    "dpf_fused_losses_ws_floats": (c_ll, [c_ll]),
+    "dpf_fused_losses": (c_int, [c_void_p, c_int] + [c_void_p] * 8 + [c_int] * 3 + [c_void_p]),
     "dpf_channel_max": (c_int, [c_void_p, c_void_p, C.c_longlong, c_int, c_void_p]),
     "dpf_fpn_merge": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "dpf_pyramid_cat": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p]),

@@ -398,7 +398,7 @@ class TiledStereoDPNet:
         assert ref_img.shape[-2] == t.height
         b = ref_img.shape[0]
         x = torch.cat([ref_img[:, :, t.y0:t.y1], tgt_img[:, :, t.y0:t.y1]], 0)
-        f = self.enc(x)
+        f = self.enc(x).to(torch.bfloat16)
         vol = self._volume(f[:b].contiguous(), f[b:].contiguous())
         cost3, out3 = self._aggregate(vol)
         disp = self._regress(cost3)

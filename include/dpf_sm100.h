@@ -270,6 +270,22 @@ int dpf_asm_sample_bwd(const void* dsamples, float* dfeat, int B, int H4, int W4
 int dpf_conv3d_wgrad(int kind, const void* x, const void* dz, float* dw, int B, int D, int H, int W, int Cin, int x_cstride,
                      int x_coff, int Cout, int z_cstride, int z_coff, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * (11) Fused training losses: masked smooth-L1 over the n disparity heads + the element-wise cosine normal
+ *      loss, value and gradient in one pass.  Replaces SMOOTHL1Loss.forward ('given' conversion, disparity target;
+ *      src/loss/depth/smoothL1.py:15-49) and COSINELoss.forward (masked branch; src/loss/normal/cosine.py:35-55).
+ *        pred_depth [B,n,H,W], gt_disp / mask [B,H,W] (mask > 0 selects; NULL = all), pred_normal / gt_normal [B,3,H,W]
+ *        (pred_normal NULL = depth only), all fp32.
+ *        sums [n+2] = { sum_mask sl1(pred_i - gt) (i < n), sum mask, sum_mask sum_c (1 - sim_c) }  (written, deterministic)
+ *        g_depth [B,n,H,W] = mask * d sl1 / d pred_i;   g_normal [B,3,H,W] = mask * d sum_c(1 - sim_c) / d pred_normal
+ *      The caller applies the scalars: smoothL1 = sum_i w_i sums[i] / sums[n]; cosine = sums[n+1] / (3 sums[n]).
+ *      ws: caller-owned scratch of dpf_fused_losses_ws_floats(B*H*W) floats.
+ * ------------------------------------------------------------------------------------------------- */
+long long dpf_fused_losses_ws_floats(long long npix);
+int dpf_fused_losses(const float* pred_depth, int n_heads, const float* gt_disp, const float* mask, const float* pred_normal,
+                     const float* gt_normal, float* g_depth, float* g_normal, float* ws, float* sums, int B, int H, int W,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

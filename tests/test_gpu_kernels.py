@@ -382,3 +382,37 @@ def test_conv2d_rows_channel_windows_chain(ops):
     t = ops.conv2d_rows(xc, wins[2], 32, None, None, t, relu=True, slope=0.05, x_coff=64)
     err = (t.permute(0, 3, 1, 2).float().cpu() - want).abs()
     assert err.max().item() < 1.5e-2 * want.abs().max().item(), err.max().item()      # two extra bf16 roundings of the partial sums
+
+
+@pytest.mark.parametrize("n_heads,with_normal,with_mask", [(3, True, True), (3, False, True), (1, True, True), (3, True, False)])
+def test_fused_losses(ops, n_heads, with_normal, with_mask):
+    """dpf_fused_losses (value + gradient in one pass) == the PyTorch statement of the reference's losses (losses.smooth_l1 / cosine,
+    themselves pinned against the oracle and the reference's golden loss values on CPU) and its autograd gradients; includes
+    |d| > 1 (linear branch), fully masked-out pixels and a zero-length predicted normal (the 1e-6 clamps)."""
+    from dualpixelface_b200 import losses
+    g = torch.Generator().manual_seed(5 + n_heads)
+    b, h, w = 2, 37, 53
+    pred = (torch.randn(b, n_heads, h, w, generator=g) * 3.0).cuda().requires_grad_(True)
+    disp = torch.randn(b, h, w, generator=g).cuda()
+    mask = (torch.rand(b, h, w, generator=g) > 0.3).float().cuda() if with_mask else torch.ones(b, h, w).cuda()
+    pn = torch.randn(b, 1, 3, h, w, generator=g)
+    pn[0, 0, :, 3, 4] = 0.0                                                   # zero-length prediction: clamp path
+    pn = pn.cuda().requires_grad_(True)
+    nrm = torch.randn(b, 3, h, w, generator=g).cuda()
+    batch = {"disp": disp, "mask": mask, "normal": nrm}
+    wts = (1.0, 0.7, 0.5)
+    want_l1 = losses.smooth_l1(pred, batch, wts)
+    want_lc = losses.cosine(pn, batch) if with_normal else None
+    (want_l1 * 1.3 + (want_lc * 0.7 if with_normal else 0.0)).backward()
+    gp, gn = pred.grad.clone(), pn.grad.clone() if with_normal else None
+    p2, n2 = pred.detach().clone().requires_grad_(True), pn.detach().clone().requires_grad_(True)
+    l1, lc = losses.FusedLossFn.apply(p2, n2 if with_normal else None, disp, mask, nrm if with_normal else None, wts)
+    (l1 * 1.3 + (lc * 0.7 if with_normal else 0.0)).backward()
+    assert abs(float(l1) - float(want_l1)) < 1e-5 * max(1.0, abs(float(want_l1)))
+    assert (p2.grad - gp).abs().max().item() < 1e-6 * max(1.0, gp.abs().max().item()) + 1e-9
+    if with_normal:
+        assert abs(float(lc) - float(want_lc)) < 1e-5
+        assert (n2.grad - gn).abs().max().item() < 2e-4 * gn.abs().max().item()
+    # determinism: the partial sums are combined in a fixed order
+    l1b, _ = losses.FusedLossFn.apply(p2.detach(), n2.detach() if with_normal else None, disp, mask, nrm if with_normal else None, wts)
+    assert float(l1b) == float(l1)
