@@ -254,6 +254,7 @@ class TiledStereoDPNet:
         dev = next(model.parameters()).device
         # encoder precision follows the model: bf16 (the bench configuration) or fp32 (encoder_autocast off: parity tests)
         self.enc = TiledSDPEncoder(model.feature_extraction, self.t, dev, torch.bfloat16 if model.encoder_autocast else torch.float32)
+        self.stage_events = None          # set to [] to collect per-stage CUDA events (tools/tiled_check.py, bench.py)
         model.aggregation._build()
         model.cost_volume._pack()
         if model.predict_normal:
@@ -391,18 +392,30 @@ class TiledStereoDPNet:
         fe = t.halo_cat(f, 1, 1, 1)
         return anm_tail(fe, b, anm.k, h4_global=t.height // 4, q_row0=q0 - 1, out_rows=t.y1 - t.y0, y_row0=t.y0)
 
+    def _mark(self, name):
+        if self.stage_events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.stage_events.append((name, e))
+
     @torch.no_grad()
     def __call__(self, batch: dict) -> dict:
         m, t = self.m, self.t
         ref_img, tgt_img = m._select_views(batch)
         assert ref_img.shape[-2] == t.height
         b = ref_img.shape[0]
+        self._mark("start")
         x = torch.cat([ref_img[:, :, t.y0:t.y1], tgt_img[:, :, t.y0:t.y1]], 0)
         f = self.enc(x).to(torch.bfloat16)
+        self._mark("encoder")
         vol = self._volume(f[:b].contiguous(), f[b:].contiguous())
+        self._mark("cost_volume")
         cost3, out3 = self._aggregate(vol)
+        self._mark("aggregation")
         disp = self._regress(cost3)
+        self._mark("regression")
         normal = self._normals(out3, disp, batch) if m.predict_normal else None
+        self._mark("normal_branch")
         return {"pred_depth": disp.unsqueeze(1), "pred_normal": normal.unsqueeze(1) if normal is not None else None,
                 "rows": (t.y0, t.y1)}
 

@@ -7,10 +7,17 @@ from dualpixelface_b200.tiled import HALO, TiledStereoDPNet
 from test_gpu_models import build, calibrated_state
 
 h, w = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (192, 160)
-st, _ = calibrated_state("stereodpnet", synthetic_batch(2, 128, 160, training=True, seed=0))
-model = build("stereodpnet"); model.load_state_dict(st, strict=False); model.cuda().eval(); model.encoder_autocast = False
+if "bench" in sys.argv:                                         # the bench's model (seeded synthetic 'calibrated' weights)
+    from bench import build_model
+    model = build_model(torch.device("cuda"))
+else:
+    st, _ = calibrated_state("stereodpnet", synthetic_batch(2, 128, 160, training=True, seed=0))
+    model = build("stereodpnet"); model.load_state_dict(st, strict=False); model.cuda().eval()
+model.encoder_autocast = "bf16enc" in sys.argv
 batch = {k: v.cuda() for k, v in synthetic_batch(1, h, w, training=True, seed=2).items()}
-def err(a, b): return f"max {float((a.float() - b.float()).abs().max()):.5f} (ref max {float(b.float().abs().max()):.3f})"
+def err(a, b):
+    d = (a.float() - b.float()).abs()
+    return f"max {float(d.max()):.5f} mean {float(d.mean()):.6f} (ref max {float(b.float().abs().max()):.3f}, mean |ref| {float(b.float().abs().mean()):.4f})"
 with torch.no_grad():
     ref_img, tgt_img = model._select_views(batch)
     fr, ft = model._features(ref_img, tgt_img)

@@ -11,6 +11,8 @@ import torch.distributed as dist
 ap = argparse.ArgumentParser()
 ap.add_argument("--height", type=int, default=2240); ap.add_argument("--width", type=int, default=3360)
 ap.add_argument("--iters", type=int, default=5); ap.add_argument("--fp32-encoder", action="store_true")
+ap.add_argument("--weights", default="calibrated", choices=["calibrated", "bench"],
+                help="calibrated: BatchNorm statistics from an oracle pass (numerically sane outputs, for the error check); bench: bench.py's seeded weights")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -23,6 +25,12 @@ from dualpixelface_b200.synthetic import synthetic_batch
 from dualpixelface_b200.tiled import TiledStereoDPNet
 ops.lib()
 model = build_model(dev)
+if a.weights == "calibrated":
+    sys.path.insert(0, "tests")
+    from test_gpu_models import calibrated_state          # test infrastructure (uses the oracle for the calibration pass)
+    st, _ = calibrated_state("stereodpnet", synthetic_batch(2, 128, 160, training=True, seed=0))
+    model.load_state_dict(st, strict=False)
+    model.to(dev).eval()
 if a.fp32_encoder:
     model.encoder_autocast = False
 batch = {k: v.to(dev) for k, v in synthetic_batch(1, a.height, a.width, seed=0).items()}
@@ -42,11 +50,16 @@ def timed(fn, iters):
 
 res = tm.gather(tm(batch))
 tm.t.bytes_exchanged = 0; tm.t.exchanges = 0
+tm.stage_events = []
 one = tm(batch)
+torch.cuda.synchronize()
 halo_bytes, exchanges = tm.t.bytes_exchanged, tm.t.exchanges
+ev = tm.stage_events
+stage_ms = {b_[0]: round(a_[1].elapsed_time(b_[1]), 3) for a_, b_ in zip(ev[:-1], ev[1:])}
+tm.stage_events = None
 ms_tiled = timed(lambda: tm(batch), a.iters)
 out = {"world": world, "height": a.height, "width": a.width, "ms_tiled": round(ms_tiled, 3), "halo_bytes_sent_per_rank": halo_bytes,
-       "exchanges_per_pass": exchanges, "rows": list(tm.t.tiles[rank])}
+       "exchanges_per_pass": exchanges, "rows": list(tm.t.tiles[rank]), "stage_ms_rank0": stage_ms}
 if rank == 0:
     with torch.no_grad():
         ref = model(batch)
