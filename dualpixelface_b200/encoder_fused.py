@@ -16,6 +16,22 @@ from torch.nn.utils.fusion import fuse_conv_bn_weights
 from . import ops
 
 
+# Row tiles (BASELINE config 5, tiled.py): when TILING is a tiled.RowTiling, every convolution of the plan runs on
+# cat(top halo, this rank's rows, bottom halo) with the zero padding along H switched off (tiled.conv_halo); the row-streamed
+# tcgen05 layers fall back to cuDNN + dpf_bias_act there (their kernel pads H itself), and the pyramid upsampling uses the
+# global align_corners coordinates.  None = the untiled plan.
+TILING = None
+
+
+def _halo_input(x, f):
+    """NCHW view of channels-last memory -> (input with halo rows, padding to pass to cuDNN)."""
+    if TILING is None or f["w"].shape[2] == 1:
+        return x, f["pad"]
+    from .tiled import conv_halo
+    top, bottom = conv_halo(f["w"].shape[2], f["stride"][0], f["dil"][0], f["pad"][0])
+    return TILING.halo_cat(x, top, bottom, 2), (0, f["pad"][1])
+
+
 # conv3 of a DPBlock as three chained 32-channel windows works (tests/test_gpu_kernels.py::test_conv2d_rows_channel_windows_chain)
 # but measured slower than cuDNN + one dpf_bias_act pass (encoder 5.37 -> 5.70 ms): off.
 CHAIN_CONV3 = False
@@ -40,13 +56,14 @@ def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d | None):
 
 
 def _conv(x, f):
-    return F.conv2d(x, f["w"], None, f["stride"], f["pad"], f["dil"], f["groups"])
+    x, pad = _halo_input(x, f)
+    return F.conv2d(x, f["w"], None, f["stride"], pad, f["dil"], f["groups"])
 
 
 def _conv_act(x, f, slope, res=None, out=None, y_coff=0):
     """conv + bias (+ res) + activation on an NCHW view of channels-last memory: one dpf_conv2d_fwd launch when the layer is
     eligible, else cuDNN + one dpf_bias_act pass.  `out` (NHWC buffer) / y_coff select a channel window of a wider tensor."""
-    if "wp" in f:
+    if "wp" in f and TILING is None:
         xh = x.permute(0, 2, 3, 1)
         rh = res.permute(0, 2, 3, 1) if res is not None else None
         y = ops.conv2d_rows_multi(xh if xh.is_contiguous() else xh.contiguous(), f["wp"], f["b"],
@@ -60,7 +77,8 @@ def _conv_bias_relu(x, f):
     """conv + bias + ReLU as ONE cuDNN fused op (no separate tail pass); used where the activation is a plain ReLU."""
     if "b16" not in f:
         f["b16"] = f["b"].to(torch.bfloat16)
-    return torch.cudnn_convolution_relu(x, f["w"], f["b16"], f["stride"], f["pad"], f["dil"], f["groups"])
+    x, pad = _halo_input(x, f)
+    return torch.cudnn_convolution_relu(x, f["w"], f["b16"], f["stride"], pad, f["dil"], f["groups"])
 
 
 def pyramid_cat(f1, f2, f3):
@@ -113,7 +131,7 @@ class _Block:
         cat = torch.empty(n, h, w, 3 * c, device=y.device, dtype=torch.bfloat16)
         for i, f in enumerate(self.dil):
             _conv_act(y, f, 1.0, out=cat, y_coff=i * c)
-        if hasattr(self, "c3_windows"):                                                               # prelu(conv3 + a)
+        if hasattr(self, "c3_windows") and TILING is None:                                            # prelu(conv3 + a)
             ah = a.permute(0, 2, 3, 1)
             t = ops.conv2d_rows(cat, self.c3_windows[0], c, None, self.c3["b"], ah if ah.is_contiguous() else ah.contiguous(), x_coff=0)
             t = ops.conv2d_rows(cat, self.c3_windows[1], c, None, None, t, x_coff=c)
@@ -177,7 +195,7 @@ class FusedSDPEncoder:
         if x.shape[1] < self.in_channels:
             x = F.pad(x, (0, 0, 0, 0, 0, self.in_channels - x.shape[1])).contiguous(memory_format=torch.channels_last)
         for f in self.first:
-            x = _conv_act(x, f, 0.0) if "wp" in f else _conv_bias_relu(x, f)
+            x = _conv_act(x, f, 0.0) if ("wp" in f and TILING is None) else _conv_bias_relu(x, f)
         o1 = self.block1(x)
         o2 = o1
         for b in self.inter1:
@@ -188,7 +206,14 @@ class FusedSDPEncoder:
             o3 = b(o3)
         o3 = self.block3(o3)
         f1, f2, f3 = self.fpn([o1, o2, o3])
-        y = pyramid_cat(f1, f2, f3)                                  # upsample x2 / x4 + concat in one pass
+        if TILING is None:
+            y = pyramid_cat(f1, f2, f3)                              # upsample x2 / x4 + concat in one pass
+        else:                                                        # row tile: bilinear rows from the GLOBAL coordinates (1 halo row)
+            from .tiled import tiled_bilinear_rows
+            t = TILING
+            up2 = tiled_bilinear_rows(f2, 2, t.height // 8, t.y0 // 8, t).to(torch.bfloat16)
+            up4 = tiled_bilinear_rows(f3, 4, t.height // 16, t.y0 // 16, t).to(torch.bfloat16)
+            y = torch.cat([f1, up2, up4], 1).contiguous(memory_format=torch.channels_last)
         for fl in self.last:
             y = _conv_bias_relu(y, fl)
         return y

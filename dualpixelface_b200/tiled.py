@@ -96,7 +96,13 @@ class RowTiling:
     def halo_cat(self, x: torch.Tensor, top: int, bottom: int, row_dim: int, wrap: bool = False) -> torch.Tensor:
         up, dn = self.halo(x, top, bottom, row_dim, wrap)
         parts = ([up] if up is not None else []) + [x] + ([dn] if dn is not None else [])
-        return torch.cat(parts, row_dim) if len(parts) > 1 else x
+        if len(parts) == 1:
+            return x
+        if x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
+            # NCHW views of channels-last memory (the 2-D encoder): keep the layout, cuDNN would otherwise transpose every layer
+            parts = [p.contiguous(memory_format=torch.channels_last) for p in parts]
+            return torch.cat(parts, row_dim).contiguous(memory_format=torch.channels_last)
+        return torch.cat(parts, row_dim)
 
     def halo_fill_(self, x_ext: torch.Tensor, h: int, row_dim: int) -> torch.Tensor:
         """Refresh the `h` halo rows on both sides of an extended buffer in place from the neighbours' interior rows."""
@@ -186,8 +192,30 @@ def tiled_bilinear_rows(x: torch.Tensor, factor: int, h_in_global: int, in_row0:
     return F.interpolate(rows, size=(rows.shape[2], win * factor), mode="bilinear", align_corners=True)
 
 
+class TiledFusedSDPEncoder:
+    """The bench configuration's encoder plan (encoder_fused.FusedSDPEncoder: BatchNorm folded, bf16 channels-last cuDNN convs with
+    fused bias / activation tails, FPN merge kernel) on this rank's rows: the plan's convolutions pick up their halo rows through
+    encoder_fused.TILING."""
+
+    def __init__(self, enc: nn.Module, tiling: RowTiling):
+        from .encoder_fused import FusedSDPEncoder
+        self.t = tiling
+        self.plan = FusedSDPEncoder(enc)
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        from . import encoder_fused
+        encoder_fused.TILING = self.t
+        try:
+            y = self.plan(x)                                         # [N,C,Hloc/4,W/4] channels-last
+        finally:
+            encoder_fused.TILING = None
+        return y.permute(0, 2, 3, 1).contiguous()
+
+
 class TiledSDPEncoder:
-    """feature_extraction of StereoDPNet (src/model/stereodpnet/modules.py:58-134) on this rank's rows."""
+    """feature_extraction of StereoDPNet (src/model/stereodpnet/modules.py:58-134) on this rank's rows, plain torch modules (any
+    dtype / device: the fp32 parity tests and the CPU gloo tests use it)."""
 
     def __init__(self, enc: nn.Module, tiling: RowTiling, device, dtype=torch.bfloat16):
         self.t, self.dtype = tiling, dtype
@@ -253,7 +281,8 @@ class TiledStereoDPNet:
         self.t = RowTiling(height, rank, world, group)
         dev = next(model.parameters()).device
         # encoder precision follows the model: bf16 (the bench configuration) or fp32 (encoder_autocast off: parity tests)
-        self.enc = TiledSDPEncoder(model.feature_extraction, self.t, dev, torch.bfloat16 if model.encoder_autocast else torch.float32)
+        self.enc = TiledFusedSDPEncoder(model.feature_extraction, self.t) if model.encoder_autocast else \
+            TiledSDPEncoder(model.feature_extraction, self.t, dev, torch.float32)
         self.stage_events = None          # set to [] to collect per-stage CUDA events (tools/tiled_check.py, bench.py)
         model.aggregation._build()
         model.cost_volume._pack()
