@@ -241,7 +241,9 @@ def anm_select(disp: torch.Tensor, kinv: torch.Tensor, abvalue: torch.Tensor, le
     d = len(levels)
     idx = torch.empty(b, k, h4, w4, device=disp.device, dtype=torch.int32)
     coord = torch.empty(b, k, h4, w4, 3, device=disp.device, dtype=torch.float32)
-    minmax = torch.tensor([[float("inf"), float("-inf")]], device=disp.device).repeat(b, 1).contiguous()
+    minmax = torch.empty(b, 2, device=disp.device, dtype=torch.float32)     # device-side fills: capturable in a CUDA graph
+    minmax[:, 0] = float("inf")
+    minmax[:, 1] = float("-inf")
     lv = (C.c_float * d)(*[float(v) for v in levels])
     check(lib().dpf_anm_select(_p(disp), _p(kinv), _p(abvalue), lv, _p(idx), _p(coord), _p(minmax), b, d, k, h4, w4, _stream()),
           "dpf_anm_select")

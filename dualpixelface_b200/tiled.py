@@ -172,6 +172,9 @@ def tiled_conv2d(conv: nn.Conv2d, x: torch.Tensor, tiling: RowTiling) -> torch.T
     return F.conv2d(xe, conv.weight, conv.bias, conv.stride, (0, conv.padding[1]), conv.dilation, conv.groups)
 
 
+_ROW_TABLES: dict = {}
+
+
 def tiled_bilinear_rows(x: torch.Tensor, factor: int, h_in_global: int, in_row0: int, tiling: RowTiling) -> torch.Tensor:
     """F.interpolate(scale_factor=factor, mode='bilinear', align_corners=True) for this rank's output rows: x [N,C,hin,win] holds
     the input rows in_row0 .. in_row0+hin-1 of an image h_in_global rows tall.  Source index rule of ATen (UpSample.cuh):
@@ -180,13 +183,15 @@ def tiled_bilinear_rows(x: torch.Tensor, factor: int, h_in_global: int, in_row0:
     h_out_global = h_in_global * factor
     o0, o1 = in_row0 * factor, (in_row0 + hin) * factor
     xe = tiling.halo_cat(x, 1, 1, 2).float()                                    # rows in_row0-1 .. in_row0+hin
-    scale = torch.tensor((h_in_global - 1) / (h_out_global - 1), dtype=torch.float32) if h_out_global > 1 else torch.tensor(0.0)
-    src = scale * torch.arange(o0, o1, dtype=torch.float32)
-    i0 = src.to(torch.int64)
-    i1 = torch.clamp(i0 + 1, max=h_in_global - 1)
-    l1 = (src - i0.to(torch.float32)).to(x.device).view(1, 1, -1, 1)
-    li0 = (i0 - (in_row0 - 1)).to(x.device)
-    li1 = (i1 - (in_row0 - 1)).to(x.device)
+    key = (factor, h_in_global, in_row0, hin, str(x.device))
+    if key not in _ROW_TABLES:                                                  # host-built once (no H2D copy in the steady state)
+        scale = torch.tensor((h_in_global - 1) / (h_out_global - 1), dtype=torch.float32) if h_out_global > 1 else torch.tensor(0.0)
+        src = scale * torch.arange(o0, o1, dtype=torch.float32)
+        i0 = src.to(torch.int64)
+        i1 = torch.clamp(i0 + 1, max=h_in_global - 1)
+        _ROW_TABLES[key] = ((src - i0.to(torch.float32)).to(x.device).view(1, 1, -1, 1), (i0 - (in_row0 - 1)).to(x.device),
+                            (i1 - (in_row0 - 1)).to(x.device))
+    l1, li0, li1 = _ROW_TABLES[key]
     rows = (1.0 - l1) * xe.index_select(2, li0) + l1 * xe.index_select(2, li1)   # [N,C,hout_loc,win] fp32
     # columns: the untiled rule (H is already at its final size: identity along H)
     return F.interpolate(rows, size=(rows.shape[2], win * factor), mode="bilinear", align_corners=True)
@@ -284,6 +289,11 @@ class TiledStereoDPNet:
         self.enc = TiledFusedSDPEncoder(model.feature_extraction, self.t) if model.encoder_autocast else \
             TiledSDPEncoder(model.feature_extraction, self.t, dev, torch.float32)
         self.stage_events = None          # set to [] to collect per-stage CUDA events (tools/tiled_check.py, bench.py)
+        # D3D halo rows per layer: measured on the first pass (all-reduced max |row offset|, one host sync each), then FIXED with a
+        # margin so that later passes are sync-free (and capturable in a CUDA graph); check_reach() verifies it after the fact
+        self._hd: List[Optional[int]] = [None, None]
+        self._reach = [None, None]
+        self._kinv_key, self._kinv = None, None
         model.aggregation._build()
         model.cost_volume._pack()
         if model.predict_normal:
@@ -397,11 +407,13 @@ class TiledStereoDPNet:
         p = anm._plan
         b = disp.shape[0]
         q0, q1 = t.rows(4)
-        kq = batch["K"].float().clone()
-        kq[:, :2, :] = kq[:, :2, :] / 4.0
-        kinv = torch.inverse(kq)
-        kinv[:, :, 2] = kinv[:, :, 2] + kinv[:, :, 1] * float(q0)              # the kernel's row index is tile-local: v = h + q0
-        idx, coord, minmax = ops.anm_select(disp.contiguous(), kinv.contiguous(), batch["abvalue"].float().contiguous(), anm.levels, anm.k)
+        if self._kinv_key != batch["K"].data_ptr():                            # torch.inverse synchronises: once per intrinsics tensor
+            kq = batch["K"].float().clone()
+            kq[:, :2, :] = kq[:, :2, :] / 4.0
+            kinv = torch.inverse(kq)
+            kinv[:, :, 2] = kinv[:, :, 2] + kinv[:, :, 1] * float(q0)          # the kernel's row index is tile-local: v = h + q0
+            self._kinv_key, self._kinv = batch["K"].data_ptr(), kinv.contiguous()
+        idx, coord, minmax = ops.anm_select(disp.contiguous(), self._kinv, batch["abvalue"].float().contiguous(), anm.levels, anm.k)
         mn = t.all_reduce(minmax[:, 0].contiguous(), dist.ReduceOp.MIN)        # coordinate normalisation over the WHOLE image
         mx = t.all_reduce(minmax[:, 1].contiguous(), dist.ReduceOp.MAX)
         minmax = torch.stack([mn, mx], 1).contiguous()
@@ -410,7 +422,10 @@ class TiledStereoDPNet:
         for i in (1, 2):
             off = p[f"off{i}"](t.halo_cat(x, 1, 1, 2), shift=p[f"offb{i}"], out_f32=True)[:, :, 1:-1].contiguous()
             reach = t.all_reduce(off[..., 1:81:3].abs().max().reshape(1), dist.ReduceOp.MAX)     # (d, h, w) per tap: rows = 1::3
-            hd = min(int(torch.ceil(reach).item()) + 2, x.shape[2])                         # tap (+-1) + offset + the trilinear corner
+            self._reach[i - 1] = reach
+            if self._hd[i - 1] is None:                                                     # first pass: one host sync per layer
+                self._hd[i - 1] = min(int(torch.ceil(reach).item()) + 3, x.shape[2])        # tap (+-1) + offset + trilinear corner + margin
+            hd = self._hd[i - 1]
             y = ops.dcn3d(t.halo_cat(x, hd, hd, 2), t.halo_cat(off, hd, hd, 2), p[f"w{i}"], p[f"cpad{i}"], p[f"aff{i}"][0],
                           p[f"aff{i}"][1], relu=True)
             x = y[:, :, hd:-hd].contiguous()
@@ -447,6 +462,25 @@ class TiledStereoDPNet:
         self._mark("normal_branch")
         return {"pred_depth": disp.unsqueeze(1), "pred_normal": normal.unsqueeze(1) if normal is not None else None,
                 "rows": (t.y0, t.y1)}
+
+    def check_reach(self) -> bool:
+        """True if the D3D row offsets of the LAST pass stayed inside the halo fixed on the first pass (one host sync)."""
+        return all(r is None or float(r) <= h - 2 for r, h in zip(self._reach, self._hd))
+
+    def capture(self, batch: dict):
+        """Capture one tiled forward -- kernels AND the NCCL halo exchanges -- in a CUDA graph.  The tiled path is launch-bound
+        (~85 exchanges + ~500 kernels for a few ms of GPU work per rank); replaying a graph removes the host from the loop.
+        Returns (replay, static_batch, static_out): copy new images into static_batch['left'/'right'], call replay(), read static_out."""
+        static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+        for _ in range(2):                                     # eager warm-up: communicators, plans, tables, the D3D halo
+            self(static)
+        torch.cuda.synchronize()
+        if self.t.world > 1:
+            dist.barrier(group=self.t.group)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self(static)
+        return g.replay, static, out
 
     def gather(self, res: dict) -> dict:
         """Assemble the full image on every rank (all_gather of the row tiles; tiles differ by at most 16 rows, padded)."""

@@ -11,6 +11,7 @@ import torch.distributed as dist
 ap = argparse.ArgumentParser()
 ap.add_argument("--height", type=int, default=2240); ap.add_argument("--width", type=int, default=3360)
 ap.add_argument("--iters", type=int, default=5); ap.add_argument("--fp32-encoder", action="store_true")
+ap.add_argument("--graph", action="store_true", help="also capture the tiled forward (incl. NCCL halo exchanges) in a CUDA graph")
 ap.add_argument("--weights", default="calibrated", choices=["calibrated", "bench"],
                 help="calibrated: BatchNorm statistics from an oracle pass (numerically sane outputs, for the error check); bench: bench.py's seeded weights")
 a = ap.parse_args()
@@ -58,8 +59,18 @@ ev = tm.stage_events
 stage_ms = {b_[0]: round(a_[1].elapsed_time(b_[1]), 3) for a_, b_ in zip(ev[:-1], ev[1:])}
 tm.stage_events = None
 ms_tiled = timed(lambda: tm(batch), a.iters)
+ms_graph, graph_err = None, None
+if a.graph:
+    try:
+        replay, sbatch, sout = tm.capture(batch)
+        replay(); torch.cuda.synchronize()
+        graph_err = float((sout["pred_depth"] - one["pred_depth"]).abs().max())
+        ms_graph = timed(replay, a.iters)
+    except Exception as e:  # noqa: BLE001
+        graph_err = f"{type(e).__name__}: {str(e)[:200]}"
 out = {"world": world, "height": a.height, "width": a.width, "ms_tiled": round(ms_tiled, 3), "halo_bytes_sent_per_rank": halo_bytes,
-       "exchanges_per_pass": exchanges, "rows": list(tm.t.tiles[rank]), "stage_ms_rank0": stage_ms}
+       "exchanges_per_pass": exchanges, "rows": list(tm.t.tiles[rank]), "stage_ms_rank0": stage_ms, "ms_tiled_cuda_graph": ms_graph,
+       "graph_vs_eager_max_diff": graph_err, "d3d_halo_rows": tm._hd, "reach_ok": tm.check_reach()}
 if rank == 0:
     with torch.no_grad():
         ref = model(batch)
