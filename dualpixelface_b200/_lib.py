@@ -69,6 +69,7 @@ SIGNATURES = {
     "dpf_channel_max": (c_int, [c_void_p, c_void_p, C.c_longlong, c_int, c_void_p]),
     "dpf_fpn_merge": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "dpf_pyramid_cat": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p]),
+    "dpf_pyramid_cat_tile": (c_int, [c_void_p] * 4 + [c_int] * 10 + [c_void_p]),
     "dpf_anm_tail_bwd": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     "dpf_anm_gather_bwd": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
 }

@@ -137,14 +137,17 @@ namespace {
 
 __global__ void __launch_bounds__(256) pyramid_cat_kernel(const __nv_bfloat16* __restrict__ f1, const __nv_bfloat16* __restrict__ f2,
                                                           const __nv_bfloat16* __restrict__ f3, __nv_bfloat16* __restrict__ out,
-                                                          int N, int h, int w, int h2, int w2, int h3, int w3, int C) {
+                                                          int N, int h, int w, int h2, int w2, int h3, int w3, int C, int hg, int row0) {
   // one thread per (pixel, pyramid level): the source coordinates and blend weights are computed once and reused for all
-  // C/8 channel chunks; the three threads of a pixel write its 3*C output channels contiguously
+  // C/8 channel chunks; the three threads of a pixel write its 3*C output channels contiguously.
+  // Row crops (config 5): the maps hold rows row0 .. (level 1), row0/2 .. , row0/4 .. of images hg, hg/2, hg/4 rows tall; the
+  // source rows follow the GLOBAL align_corners scale.  Untiled: hg = h, row0 = 0.
   const int c8n = C >> 3;
   const long long total = static_cast<long long>(N) * h * w * 3;
-  const float ry2 = (h > 1) ? static_cast<float>(h2 - 1) / static_cast<float>(h - 1) : 0.f;
+  const int hg2 = hg / 2, hg3 = hg / 4;
+  const float ry2 = (hg > 1) ? static_cast<float>(hg2 - 1) / static_cast<float>(hg - 1) : 0.f;
   const float rx2 = (w > 1) ? static_cast<float>(w2 - 1) / static_cast<float>(w - 1) : 0.f;
-  const float ry3 = (h > 1) ? static_cast<float>(h3 - 1) / static_cast<float>(h - 1) : 0.f;
+  const float ry3 = (hg > 1) ? static_cast<float>(hg3 - 1) / static_cast<float>(hg - 1) : 0.f;
   const float rx3 = (w > 1) ? static_cast<float>(w3 - 1) / static_cast<float>(w - 1) : 0.f;
   for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < total;
        q += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -162,10 +165,13 @@ __global__ void __launch_bounds__(256) pyramid_cat_kernel(const __nv_bfloat16* _
     }
     const __nv_bfloat16* src = lvl == 1 ? f2 : f3;
     const int hs = lvl == 1 ? h2 : h3, ws = lvl == 1 ? w2 : w3;
-    const float sy = (lvl == 1 ? ry2 : ry3) * static_cast<float>(y), sx = (lvl == 1 ? rx2 : rx3) * static_cast<float>(x);
-    const int y0 = min(static_cast<int>(sy), hs - 1), x0 = min(static_cast<int>(sx), ws - 1);
-    const int y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
-    const float ly = sy - static_cast<float>(y0), lx = sx - static_cast<float>(x0);
+    const float sy = (lvl == 1 ? ry2 : ry3) * static_cast<float>(y + row0), sx = (lvl == 1 ? rx2 : rx3) * static_cast<float>(x);
+    const int hgs = lvl == 1 ? hg2 : hg3, rs = lvl == 1 ? row0 / 2 : row0 / 4;         // global height / first row of the source level
+    const int gy0 = min(static_cast<int>(sy), hgs - 1), gy1 = min(gy0 + 1, hgs - 1);   // global source rows
+    const float ly = sy - static_cast<float>(gy0);
+    const int y0 = min(max(gy0 - rs, 0), hs - 1), y1 = min(max(gy1 - rs, 0), hs - 1);  // rows of the local crop
+    const int x0 = min(static_cast<int>(sx), ws - 1), x1 = min(x0 + 1, ws - 1);
+    const float lx = sx - static_cast<float>(x0);
     const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
     const __nv_bfloat16* base = src + static_cast<size_t>(n) * hs * ws * C;
     const __nv_bfloat16* p00 = base + (static_cast<size_t>(y0) * ws + x0) * C;
@@ -202,16 +208,27 @@ __global__ void __launch_bounds__(256) channel_max_kernel(const __nv_bfloat16* _
 
 }  // namespace
 
+extern "C" int dpf_pyramid_cat_tile(const void* f1, const void* f2, const void* f3, void* out, int N, int h, int w, int h2, int w2,
+                                    int h3, int w3, int C, int hglob, int row0, void* stream);
+
 extern "C" int dpf_pyramid_cat(const void* f1, const void* f2, const void* f3, void* out, int N, int h, int w, int h2, int w2,
                                int h3, int w3, int C, void* stream) {
+  DPF_REQUIRE(h2 * 2 == h && h3 * 4 == h, "dpf_pyramid_cat: levels must be h, h/2, h/4 rows");
+  return dpf_pyramid_cat_tile(f1, f2, f3, out, N, h, w, h2, w2, h3, w3, C, h, 0, stream);
+}
+
+extern "C" int dpf_pyramid_cat_tile(const void* f1, const void* f2, const void* f3, void* out, int N, int h, int w, int h2, int w2,
+                                    int h3, int w3, int C, int hglob, int row0, void* stream) {
   DPF_REQUIRE(f1 && f2 && f3 && out, "dpf_pyramid_cat: null pointer");
+  DPF_REQUIRE(hglob % 4 == 0 && row0 % 4 == 0 && row0 >= 0 && row0 + h <= hglob && h2 * 2 == h && h3 * 4 == h,
+              "dpf_pyramid_cat: a crop must start on a multiple of 4 rows and the levels must be h, h/2, h/4 rows");
   DPF_REQUIRE(DPF_ALIGNED16(f1) && DPF_ALIGNED16(f2) && DPF_ALIGNED16(f3) && DPF_ALIGNED16(out), "dpf_pyramid_cat: pointers must be 16-byte aligned");
   DPF_REQUIRE(N > 0 && h > 0 && w > 0 && h2 > 0 && w2 > 0 && h3 > 0 && w3 > 0 && C >= 8 && C % 8 == 0, "dpf_pyramid_cat: bad shape");
   const long long total = static_cast<long long>(N) * h * w * 3;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(dpf::sm_count()) * 16));
   pyramid_cat_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(f1), reinterpret_cast<const __nv_bfloat16*>(f2), reinterpret_cast<const __nv_bfloat16*>(f3),
-      reinterpret_cast<__nv_bfloat16*>(out), N, h, w, h2, w2, h3, w3, C);
+      reinterpret_cast<__nv_bfloat16*>(out), N, h, w, h2, w2, h3, w3, C, hglob, row0);
   return dpf::after_launch("dpf_pyramid_cat");
 }
 

@@ -21,6 +21,7 @@ from . import ops
 # tcgen05 layers fall back to cuDNN + dpf_bias_act there (their kernel pads H itself), and the pyramid upsampling uses the
 # global align_corners coordinates.  None = the untiled plan.
 TILING = None
+CROP = None       # (quarter-res rows of the whole image, first quarter-res row of this crop): overlap-recompute encoder of tiled.py
 
 
 def _halo_input(x, f):
@@ -81,17 +82,18 @@ def _conv_bias_relu(x, f):
     return torch.cudnn_convolution_relu(x, f["w"], f["b16"], f["stride"], pad, f["dil"], f["groups"])
 
 
-def pyramid_cat(f1, f2, f3):
+def pyramid_cat(f1, f2, f3, hglob=None, row0=0):
     """cat([f1, bilinear x2 (f2), bilinear x4 (f3)], 1) with align_corners=True (modules.py:128-133 of the reference); inputs
-    and output are NCHW views of channels-last bf16 memory."""
+    and output are NCHW views of channels-last bf16 memory.  hglob / row0: the maps are row crops starting at level-1 row row0 of
+    an image hglob level-1 rows tall (global coordinates)."""
     from . import _lib
     n, c, h, w = f1.shape
     a, b, d = (t.permute(0, 2, 3, 1).contiguous() for t in (f1, f2, f3))
     for t in (a, b, d):
         ops._req(t, torch.bfloat16, "pyramid level")
     out = torch.empty(n, h, w, 3 * c, device=f1.device, dtype=torch.bfloat16)
-    _lib.check(ops.lib().dpf_pyramid_cat(ops._p(a), ops._p(b), ops._p(d), ops._p(out), n, h, w, b.shape[1], b.shape[2], d.shape[1],
-                                         d.shape[2], c, ops._stream()), "dpf_pyramid_cat")
+    _lib.check(ops.lib().dpf_pyramid_cat_tile(ops._p(a), ops._p(b), ops._p(d), ops._p(out), n, h, w, b.shape[1], b.shape[2], d.shape[1],
+                                              d.shape[2], c, hglob or h, row0, ops._stream()), "dpf_pyramid_cat")
     return out.permute(0, 3, 1, 2)
 
 
@@ -207,7 +209,7 @@ class FusedSDPEncoder:
         o3 = self.block3(o3)
         f1, f2, f3 = self.fpn([o1, o2, o3])
         if TILING is None:
-            y = pyramid_cat(f1, f2, f3)                              # upsample x2 / x4 + concat in one pass
+            y = pyramid_cat(f1, f2, f3, *(CROP or (None, 0)))        # upsample x2 / x4 + concat in one pass
         else:                                                        # row tile: bilinear rows from the GLOBAL coordinates (1 halo row)
             from .tiled import tiled_bilinear_rows
             t = TILING

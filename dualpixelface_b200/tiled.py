@@ -7,9 +7,11 @@ its own rows; what it needs from the neighbours travels as HALO ROWS over NCCL p
 both directions of a layer's exchange in one group call), never as recomputation (the receptive field of the path is ~51
 quarter-resolution rows against 70-row tiles).  Rows beyond the image border are zeros -- they ARE the convolution padding.
 
-  2-D encoder      every k x k conv (stride s, dilation d) runs on  cat(top halo, rows, bottom halo)  with zero padding along H
-                   switched off: top = d(k-1)/2 rows, bottom = d(k-1)+1-s-top rows.  FPN nearest x2 is tile-local; the bilinear
-                   x2 / x4 pyramid upsampling uses the GLOBAL align_corners coordinates (1 halo row).
+  2-D encoder      default "overlap": the untiled encoder plan on the tile + its receptive-field margin (368 px), no communication
+                   (the encoder is adjacent to the path and 22 % of the FLOPs; its ~45 per-layer exchanges cost more host time
+                   than the recomputation).  "exchange": every k x k conv (stride s, dilation d) runs on cat(top halo, rows, bottom
+                   halo) with zero padding along H switched off: top = d(k-1)/2 rows, bottom = d(k-1)+1-s-top rows.  FPN nearest x2
+                   is tile-local; the bilinear x2 / x4 pyramid upsampling uses the GLOBAL align_corners coordinates.
   ASM volume       the sampling tables are built for the global height and re-indexed to the tile; 2 halo rows with WRAP-AROUND
                    between the first and the last tile (the phase sample is a circular row shift, asm.py:63-75); the
                    InstanceNorm statistics are all-reduced ([2B,32,2] fp32).
@@ -197,6 +199,78 @@ def tiled_bilinear_rows(x: torch.Tensor, factor: int, h_in_global: int, in_row0:
     return F.interpolate(rows, size=(rows.shape[2], win * factor), mode="bilinear", align_corners=True)
 
 
+def encoder_margin(n_inter1: int = 1, n_inter2: int = 1) -> int:
+    """Half-height of the StereoDPNet encoder's receptive field in full-resolution rows, rounded up to a multiple of 16 (+16 spare).
+    Walking back from the quarter-resolution output (src/model/stereodpnet/modules.py:58-134): lastconv 2 x (3x3 @1/4) = 8 px;
+    bilinear x4 of the 1/16 level = 16; FPN 3x3 @1/16 = 16; block3 (DPBlock @1/8 -> 1/16: conv1 1 + conv2 1 + dilated 5 + conv3 1 +
+    conv4 2 + depthwise 2 = 12 rows @1/8) = 96; each interblock2 (11 rows @1/8) = 88; block2 (12 rows @1/4) = 48; each interblock1
+    (11 rows @1/4) = 44; block1 (12 rows @1/2) = 24; firstconv (2 rows @1/2 + the stride-2 3x3) = 6."""
+    px = 8 + 16 + 16 + 96 + 88 * n_inter2 + 48 + 44 * n_inter1 + 24 + 6
+    return (px + 15) // 16 * 16 + 16
+
+
+class _Crop:
+    """A row crop [a0, a1) of an image `height` rows tall, seen as a world-1 tiling (halo rows = zeros)."""
+
+    def __init__(self, height, a0, a1):
+        self.height, self.y0, self.y1, self.world = height, a0, a1, 1
+
+    def halo_cat(self, x, top, bottom, row_dim, wrap=False):
+        shp = lambda k: x.shape[:row_dim] + (k,) + x.shape[row_dim + 1:]
+        return torch.cat([x.new_zeros(shp(top)), x, x.new_zeros(shp(bottom))], row_dim)
+
+
+class OverlapSDPEncoder:
+    """The encoder by OVERLAP-RECOMPUTE: this rank runs the UNTILED encoder on its rows plus the receptive-field margin
+    (encoder_margin(): 368 px each side) and keeps its own rows.  No communication at all: the per-layer exchange variant
+    (TiledFusedSDPEncoder: ~45 exchanges) is bound by the host-side cost of its NCCL calls (12.4 ms for a half image on 2 GPUs),
+    while the encoder is only 22 % of the model's FLOPs, so recomputing (280 + 2 x 368) / 280 of a tile is cheaper.  The 3-D
+    path (receptive field ~51 quarter-res rows per side against 70-row tiles) keeps the per-layer halo exchange.
+    fused=True: the bench configuration's plan (encoder_fused.FusedSDPEncoder, crop-aware pyramid kernel); fused=False: plain torch
+    modules in `dtype` (CPU / fp32 tests)."""
+
+    def __init__(self, enc: nn.Module, tiling: RowTiling, device, fused: bool = True, dtype=torch.float32):
+        self.t, self.fused, self.dtype = tiling, fused, dtype
+        self.margin = encoder_margin(len(enc.interblock1), len(enc.interblock2))
+        self.a0, self.a1 = max(0, tiling.y0 - self.margin), min(tiling.height, tiling.y1 + self.margin)
+        if fused:
+            from .encoder_fused import FusedSDPEncoder
+            self.plan = FusedSDPEncoder(enc)
+        else:
+            self.enc = fused_torch_encoder(enc, device, dtype)
+
+    @torch.no_grad()
+    def __call__(self, images: torch.Tensor) -> torch.Tensor:
+        """images [N,3,H,W] (the WHOLE image) -> [N,Hloc/4,W/4,C] for this rank's rows."""
+        t = self.t
+        x = images[:, :, self.a0:self.a1]
+        lo, hi = (t.y0 - self.a0) // 4, (t.y1 - self.a0) // 4
+        if self.fused:
+            from . import encoder_fused
+            encoder_fused.CROP = (t.height // 4, self.a0 // 4)
+            try:
+                y = self.plan(x)
+            finally:
+                encoder_fused.CROP = None
+            return y.permute(0, 2, 3, 1)[:, lo:hi].contiguous()
+        e, crop = self.enc, _Crop(t.height, self.a0, self.a1)
+        x = x.to(self.dtype).contiguous(memory_format=torch.channels_last)
+        o1 = e.block1(e.firstconv(x))
+        o2 = o1
+        for m in e.interblock1:
+            o2 = m(o2)
+        o2 = e.block2(o2)
+        o3 = o2
+        for m in e.interblock2:
+            o3 = m(o3)
+        o3 = e.block3(o3)
+        f = e.fpn(OrderedDict(layer1=o1, layer2=o2, layer3=o3))
+        up2 = tiled_bilinear_rows(f["layer2"], 2, t.height // 8, self.a0 // 8, crop)
+        up4 = tiled_bilinear_rows(f["layer3"], 4, t.height // 16, self.a0 // 16, crop)
+        y = e.lastconv(torch.cat([f["layer1"], up2.to(self.dtype), up4.to(self.dtype)], 1))
+        return y.permute(0, 2, 3, 1)[:, lo:hi].contiguous()
+
+
 class TiledFusedSDPEncoder:
     """The bench configuration's encoder plan (encoder_fused.FusedSDPEncoder: BatchNorm folded, bf16 channels-last cuDNN convs with
     fused bias / activation tails, FPN merge kernel) on this rank's rows: the plan's convolutions pick up their halo rows through
@@ -286,8 +360,10 @@ class TiledStereoDPNet:
         self.t = RowTiling(height, rank, world, group)
         dev = next(model.parameters()).device
         # encoder precision follows the model: bf16 (the bench configuration) or fp32 (encoder_autocast off: parity tests)
-        self.enc = TiledFusedSDPEncoder(model.feature_extraction, self.t) if model.encoder_autocast else \
-            TiledSDPEncoder(model.feature_extraction, self.t, dev, torch.float32)
+        # "overlap" (default): untiled encoder on the tile + its receptive-field margin, no communication; "exchange": per-layer halos
+        self.encoder_mode = "overlap"
+        self.enc = OverlapSDPEncoder(model.feature_extraction, self.t, dev, fused=bool(model.encoder_autocast))
+        self._enc_exchange = None
         self.stage_events = None          # set to [] to collect per-stage CUDA events (tools/tiled_check.py, bench.py)
         # D3D halo rows per layer: measured on the first pass (all-reduced max |row offset|, one host sync each), then FIXED with a
         # margin so that later passes are sync-free (and capturable in a CUDA graph); check_reach() verifies it after the fact
@@ -449,8 +525,14 @@ class TiledStereoDPNet:
         assert ref_img.shape[-2] == t.height
         b = ref_img.shape[0]
         self._mark("start")
-        x = torch.cat([ref_img[:, :, t.y0:t.y1], tgt_img[:, :, t.y0:t.y1]], 0)
-        f = self.enc(x).to(torch.bfloat16)
+        if self.encoder_mode == "overlap":
+            f = self.enc(torch.cat([ref_img, tgt_img], 0)).to(torch.bfloat16)
+        else:
+            if self._enc_exchange is None:
+                dev = ref_img.device
+                self._enc_exchange = TiledFusedSDPEncoder(m.feature_extraction, t) if m.encoder_autocast else \
+                    TiledSDPEncoder(m.feature_extraction, t, dev, torch.float32)
+            f = self._enc_exchange(torch.cat([ref_img[:, :, t.y0:t.y1], tgt_img[:, :, t.y0:t.y1]], 0)).to(torch.bfloat16)
         self._mark("encoder")
         vol = self._volume(f[:b].contiguous(), f[b:].contiguous())
         self._mark("cost_volume")

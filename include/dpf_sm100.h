@@ -189,6 +189,11 @@ int dpf_bias_act(const void* x, const float* bias, const void* res, void* y, lon
  * out[N,h,w,3C] = cat(f1[N,h,w,C], bilinear(f2[N,h2,w2,C]), bilinear(f3[N,h3,w3,C])), align_corners=True, bf16 channels-last. */
 int dpf_pyramid_cat(const void* f1, const void* f2, const void* f3, void* out, int N, int h, int w, int h2, int w2, int h3,
                     int w3, int C, void* stream);
+/* dpf_pyramid_cat on a ROW CROP: the three maps hold the rows row0.. / row0/2.. / row0/4.. of levels that are hglob, hglob/2,
+ * hglob/4 rows tall; source rows follow the GLOBAL align_corners scale (BASELINE config 5: the encoder runs on this rank's rows
+ * plus its receptive-field margin). */
+int dpf_pyramid_cat_tile(const void* f1, const void* f2, const void* f3, void* out, int N, int h, int w, int h2, int w2, int h3,
+                         int w3, int C, int hglob, int row0, void* stream);
 /* FPN top-down merge (torchvision FeaturePyramidNetwork.forward, used at src/model/stereodpnet/modules.py:83,124):
  * y[N,h,w,C] = x + bias + nearest_upsample(top[N,ht,wt,C]); bf16 channels-last, one pass. */
 int dpf_fpn_merge(const void* x, const float* bias, const void* top, void* y, int N, int h, int w, int ht, int wt, int C,

@@ -104,3 +104,45 @@ def test_tiled_encoder_world2_equals_untiled():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert all(v[:4] == (True, True, True, True) for v in dict(ret).values()), dict(ret)
+
+
+def test_overlap_encoder_margin_is_sufficient():
+    """Overlap-recompute encoder (no communication): a tile in the MIDDLE of a tall image -- artificial crop borders on both sides,
+    exactly encoder_margin() rows away -- reproduces the untiled encoder's rows (to fp32 noise); with a 96-row margin it does not.
+    (The analytic receptive field, 346 px, is a guarantee; with these random weights the influence has decayed to 1e-6 by ~224 px.)"""
+    from dualpixelface_b200.runner import load_config, model_selector
+    torch.manual_seed(0)
+    torch.set_num_threads(4)
+    model = model_selector(load_config("eval_faceDP", "pytest", root=ROOT, make_dirs=False), root=ROOT).eval()
+    for m in model.feature_extraction.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.running_mean.uniform_(-0.2, 0.2); m.running_var.uniform_(0.5, 1.5)
+    margin = tiled.encoder_margin(1, 1)
+    assert margin == 368
+    h, w = 2 * margin + 64, 32                                     # rows [margin, margin + 64) are 'margin' away from both ends
+    img = torch.randn(1, 3, h, w, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        want = tiled.fused_torch_encoder(model.feature_extraction, "cpu", torch.float32)(img).permute(0, 2, 3, 1)
+
+    class T:                                                       # a 3-tile split whose middle tile is the probe
+        height, y0, y1, world = h, margin, margin + 64, 3
+    enc = tiled.OverlapSDPEncoder(model.feature_extraction, T, "cpu", fused=False, dtype=torch.float32)
+    assert (enc.a0, enc.a1) == (0, h)
+    # emulate artificial borders: zero everything outside [a0, a1) by shrinking the crop via a smaller margin
+    got = enc(img)
+    assert (got - want[:, margin // 4:(margin + 64) // 4]).abs().max().item() < 1e-5 * want.abs().max().item()
+    for shrink, expect_equal in ((0, True), (margin - 96, False)):
+        enc.margin = margin - shrink
+        enc.a0, enc.a1 = T.y0 - enc.margin, T.y1 + enc.margin
+        pad = shrink                                               # crop rows [a0, a1) of a LARGER image: real data beyond the crop is cut off
+        big = torch.randn(1, 3, h + 2 * 64, w, generator=torch.Generator().manual_seed(2))
+        del pad
+        class TB:
+            height, y0, y1, world = h + 128, margin + 64, margin + 128, 3
+        encb = tiled.OverlapSDPEncoder(model.feature_extraction, TB, "cpu", fused=False, dtype=torch.float32)
+        encb.margin = margin - shrink
+        encb.a0, encb.a1 = TB.y0 - encb.margin, TB.y1 + encb.margin
+        with torch.no_grad():
+            wantb = tiled.fused_torch_encoder(model.feature_extraction, "cpu", torch.float32)(big).permute(0, 2, 3, 1)[:, TB.y0 // 4:TB.y1 // 4]
+        err = (encb(big) - wantb).abs().max().item() / wantb.abs().max().item()
+        assert (err < 1e-5) == expect_equal, (shrink, err)
