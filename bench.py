@@ -17,6 +17,8 @@ Extra blocks on the same JSON line (each guarded: a failure is reported inside i
              all-reduce (parallel.GradSync), so the 1 -> 8 GPU curve of the driver contains the collective
   "psmnet"   BASELINE config 1 (1 x 448x448 eval) and config 4 (512x768 crops: eval and fwd+bwd+optimizer, also under torchrun)
   "costvol"  north_star kernel (1): dpf_costvol_fwd (concat / diff / gwc) alone, CUDA events, GB/s against the HBM roofline
+  "config5"  BASELINE config 5: one 2240x3360 pair -- at N = 1 the untiled forward, under torchrun row tiles over the N GPUs with
+             halo exchange (dualpixelface_b200/tiled.py); ms per pair (max over ranks), halo bytes and exchanges per pair
   "gpu_eager_oracle"  the oracle's own PyTorch code on the SAME B200 (fp32 eager, cuDNN), as context for the speed-up
 """
 from __future__ import annotations
@@ -263,6 +265,47 @@ def gpu_eager_oracle_block(dev):
         torch.cuda.empty_cache()
 
 
+def config5_block(dev, rank, world, steps):
+    """BASELINE config 5: ONE 2240x3360 pair; under torchrun split into row tiles over the N GPUs with halo exchange
+    (dualpixelface_b200/tiled.py), else the untiled single-GPU forward.  Device time of one pair (max over ranks)."""
+    from dualpixelface_b200.synthetic import synthetic_batch
+    h, w = 2240, 3360
+    try:
+        model = build_model(dev)
+        batch = {k: v.to(dev) for k, v in synthetic_batch(1, h, w, seed=0).items()}
+        out = {"workload": f"stereodpnet_infer_{h}x{w}_b1", "n_gpus": world}
+        with torch.no_grad():
+            if world == 1:
+                ms = _time_ms(lambda: model(batch), max(steps, 3), 2)
+                out.update(ms_per_pair=round(ms, 3), mode="untiled, one GPU")
+            else:
+                from dualpixelface_b200.tiled import TiledStereoDPNet
+                tm = TiledStereoDPNet(model, h, rank, world)
+                tm(batch); tm(batch)
+                tm.t.bytes_exchanged = tm.t.exchanges = 0
+                tm(batch)
+                torch.cuda.synchronize()
+                sent, nex = tm.t.bytes_exchanged, tm.t.exchanges
+                torch.distributed.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n = max(steps, 3)
+                e0.record()
+                for _ in range(n):
+                    tm(batch)
+                e1.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1) / n], device=dev, dtype=torch.float64)
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+                out.update(ms_per_pair=round(t.item(), 3), mode=f"row tiles over {world} GPUs, per-layer halo exchange (NCCL p2p) in the 3-D path, "
+                           "overlap-recompute encoder", rows_rank0=list(tm.t.tiles[0]), halo_bytes_sent_rank0=int(sent), exchanges_per_pair=int(nex),
+                           d3d_halo_rows=tm._hd, d3d_reach_ok=bool(tm.check_reach()))
+        del model, batch
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
+
 def measured_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from this round's `ncu --set full` captures, by kernel key
     (profiles/r02_traffic.json, written by tools/summarize_ncu.py --traffic)."""
@@ -439,6 +482,7 @@ def run_ours(args):
         tsteps = max(3, min(args.steps, 5))
         extras["train"] = guarded_train_block("stereodpnet", (8, 4, 2), H, W, tsteps, 3, dev, rank, world)
         extras["psmnet"] = psmnet_block(dev, rank, world, tsteps)
+        extras["config5"] = config5_block(dev, rank, world, tsteps)
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
