@@ -60,6 +60,7 @@ SIGNATURES = {
     "dpf_dcn3d_bwd_data": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),
     "dpf_dcn3d_bwd_weight": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "dpf_conv2d_fwd": (c_int, [c_void_p] * 6 + [c_int] * 11 + [c_float, c_void_p]),
+    "dpf_conv3d_s2_fwd": (c_int, [c_void_p] * 5 + [c_int] * 11 + [c_void_p]),
     "dpf_conv2d_tc_npad": (c_int, [c_int]),
     "dpf_conv2d_tc_weight_elems": (c_ll, [c_int, c_int]),
     "dpf_conv2d_tc_fwd": (c_int, [c_void_p] * 6 + [c_int] * 11 + [c_float, c_void_p]),

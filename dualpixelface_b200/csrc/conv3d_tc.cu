@@ -466,8 +466,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
 // ============================================================================================================
 constexpr int kFEpiWarps = 8;                                       // fused kernel: 8 epilogue warps, MMA warps 8-9, 4 producers
 constexpr int kFMmaWarp = kFEpiWarps;
-// MMA issue (template parameter NISS, see the generic kernel): 1 = one thread, program order, deterministic (default);
-// 4 = the (128-row block, K-step) pairs of a plane are dealt round-robin to four issuing warps -- K-steps of one block then race
+// MMA issue (template parameter NISS, see the generic kernel): 1 = one thread, program order, deterministic;
+// NISS == NBLK (default where a tile has 2 or 3 blocks): one issuing warp per 128-row block, each accumulator owned by ONE thread --
+// as deterministic as a single issuer, with 2-3 warps sharing the descriptor arithmetic;
+// 4 (DPF_CONV_ISSUERS=4) = the (128-row block, K-step) pairs of a plane are dealt round-robin to four issuing warps -- K-steps of one block then race
 // into one accumulator (every MMA accumulates into a pre-zeroed stage, so any order is CORRECT, but the fp32 rounding differs from
 // run to run).  Round 1 used 4 because the single issuer was the critical path (~10 uniform-datapath instructions of descriptor
 // arithmetic per tcgen05.mma behind a per-MMA branch); the single-issuer loop now has no branch and no address masking, so the
@@ -650,7 +652,9 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
                 const uint64_t bd2 = bdesc_hi | static_cast<uint64_t>(b0 + ks * 2 * C::W_ROWS + run1 * NPAD);
 #pragma unroll
                 for (int blk = 0; blk < C::NBLK; ++blk) {
-                  if (NISS > 1 && (blk * C::KSTEPS + ks) % NISS != mw) continue;     // this warp's share of the plane
+                  // NISS == NBLK: warp mw OWNS 128-row block mw (all of its K-steps and taps) -- every accumulator is written by one
+                  // thread in program order: parallel issue AND deterministic.  Otherwise (NISS = 4, opt-in) round-robin shares.
+                  if (NISS > 1 && (NISS == C::NBLK ? (blk != mw) : ((blk * C::KSTEPS + ks) % NISS != mw))) continue;
                   if (blk == 0 || blk < nblk) {                   // a tile always has its first block (no runtime test)
                     const uint64_t adesc = adesc_hi | static_cast<uint64_t>(a0 + ks * 2 * (C::CH_STRIDE >> 4) + blk * 8);
                     const uint32_t col = tmem_base + blk * (R * NPAD);
@@ -850,7 +854,9 @@ int launch_fused_n(ConvKParams kp, cudaStream_t st) {
 
 template <int CIN, int NPAD, int WT, int NS, int R, int DILW = 1>
 int launch_fused(const ConvKParams& kp, cudaStream_t st) {
-  return conv_issuers() == 4 ? launch_fused_n<CIN, NPAD, WT, NS, R, DILW, 4>(kp, st) : launch_fused_n<CIN, NPAD, WT, NS, R, DILW, 1>(kp, st);
+  constexpr int NBLK = WT / 8;
+  constexpr int OWN = (NBLK >= 2 && NBLK <= 4) ? NBLK : 1;          // one issuing warp per block when a tile has several blocks
+  return conv_issuers() == 4 ? launch_fused_n<CIN, NPAD, WT, NS, R, DILW, 4>(kp, st) : launch_fused_n<CIN, NPAD, WT, NS, R, DILW, OWN>(kp, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1002,6 +1008,11 @@ extern "C" int dpf_conv3d_fwd(const dpf_conv3d_args* a, void* stream) {
       if (a->Cin == 32 && npad == 32) return launch_fused<32, 32, 16, 4, 8>(kp, st);
       if (a->Cin == 32 && npad == 16 && wide24) return launch_fused<32, 16, 24, 4, 8>(kp, st);
       if (a->Cin == 32 && npad == 16) return launch_fused<32, 16, 16, 4, 8>(kp, st);
+      {
+        static int wide64 = -1;                                      // DPF_CONV_64W16=1: 16-wide tiles (2 blocks, 2-slot ring) for 64 -> 32
+        if (wide64 < 0) { const char* e = getenv("DPF_CONV_64W16"); wide64 = e ? atoi(e) : 0; }
+        if (a->Cin == 64 && npad == 32 && wide64) return launch_fused<64, 32, 16, 2, 8>(kp, st);
+      }
       if (a->Cin == 64 && npad == 32) return launch_fused<64, 32, 8, 4, 16>(kp, st);
       if (a->Cin == 64 && npad == 16) return launch_fused<64, 16, 8, 4, 16>(kp, st);
     }

@@ -72,6 +72,12 @@ class TCConv3d:
             w = w.transpose(0, 1)
         self.cout, cin = int(w.shape[0]), int(w.shape[1])
         self.cin = cin_pad or cin
+        # stride 2: the plane-streamed kernel (dpf_conv3d_s2_fwd) takes all input channels and up to 64 (Cin 32) / 32 (Cin 64) output
+        # channels per launch -- 1 launch for conv1 (32 -> 64), 2 for conv3 (64 -> 64), no fp32 partial-sum chain
+        self.s2 = None
+        if kind == KIND_S2 and self.cin in (32, 64) and cin == self.cin and self.cout % 8 == 0:
+            step = 64 if self.cin == 32 else 32
+            self.s2 = [(ops.pack_conv_weight(w[co:co + step].float()), co, min(step, self.cout - co)) for co in range(0, self.cout, step)]
         self.plan = plan_launches(kind, self.cin, self.cout)
         self.packed = []
         for ln in self.plan:
@@ -97,6 +103,11 @@ class TCConv3d:
         if out is None:
             out = torch.empty(*self.out_shape(x), self.cout, device=x.device,
                               dtype=torch.float32 if out_f32 else torch.bfloat16)
+        if self.s2 is not None and residual is None and out.dtype == torch.bfloat16:
+            for wp, co, n in self.s2:
+                ops.conv3d_s2(x, wp, n, scale[co:co + n].contiguous() if scale is not None else None,
+                              shift[co:co + n].contiguous() if shift is not None else None, relu, out=out, y_coff=y_coff + co)
+            return out
         partial = None
         for ln, wp in zip(self.plan, self.packed):
             sc = scale[ln.y_coff: ln.y_coff + ln.cout] if scale is not None else None

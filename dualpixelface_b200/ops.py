@@ -405,3 +405,22 @@ def conv2d_tc(x: torch.Tensor, w_packed: torch.Tensor, cout: int, dil: int = 1, 
                                   out.shape[-1], y_coff, int(dil), int(relu), float(slope), _stream()), "dpf_conv2d_tc_fwd")
     _timing_end(tm, f"conv2d_tc {cin}->{cout} d{dil}", 2.0 * 9 * cin * cout * n * h * w, "flop")
     return out
+
+
+def conv3d_s2(x: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+              relu: bool = False, out: Optional[torch.Tensor] = None, y_coff: int = 0) -> torch.Tensor:
+    """Stride-2 3x3x3 conv (+ affine + ReLU) in ONE launch of the plane-streamed kernel (dpf_conv3d_s2_fwd): x [B,D,H,W,Cin] bf16
+    with Cin = 8 * w_packed.shape[1] in {32, 64} -> [B,ceil(D/2),ceil(H/2),ceil(W/2),Cy] (cout channels at y_coff)."""
+    _req(x, torch.bfloat16, "x"); _req(w_packed, torch.bfloat16, "w_packed")
+    b, d, h, w, cx = x.shape
+    cin = w_packed.shape[1] * 8
+    do, ho, wo = (d + 1) // 2, (h + 1) // 2, (w + 1) // 2
+    if out is None:
+        out = torch.empty(b, do, ho, wo, cout, device=x.device, dtype=torch.bfloat16)
+    _req(out, torch.bfloat16, "out")
+    assert out.shape[:4] == (b, do, ho, wo) and w_packed.shape[0] == 27
+    tm = _timing_begin()
+    check(lib().dpf_conv3d_s2_fwd(_p(x), _p(w_packed), _p(out), _p(scale), _p(shift), b, d, h, w, cin, cout, cx, 0, out.shape[-1], y_coff,
+                                  int(relu), _stream()), "dpf_conv3d_s2_fwd")
+    _timing_end(tm, f"conv3d_s2 {cin}->{cout}", 2.0 * 27 * cin * cout * b * do * ho * wo, "flop")
+    return out

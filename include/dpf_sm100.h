@@ -213,6 +213,14 @@ int dpf_conv2d_fwd(const void* x, const void* w, void* y, const float* scale, co
                    int N, int H, int W, int Cin, int Cout, int x_cstride, int x_coff, int y_cstride, int y_coff,
                    int dil, int relu, float slope, void* stream);
 
+/* Stride-2 3x3x3 convolution (pad 1) + per-channel affine + ReLU, plane-streamed on tcgen05 (conv3d_s2.cu): every input plane is
+ * staged once per tile, N = all output channels (<= 64 for Cin = 32, <= 32 for Cin = 64), input channels in 32-channel windows that
+ * accumulate in TMEM.  Replaces dresK.conv1 / conv3 (nn.Conv3d k3 s2 p1 + BatchNorm3d + ReLU, src/model/stereodpnet/modules.py:
+ * 208,213) in ONE launch where dpf_conv3d_fwd kind 1 needed 2 / 4.  x [B,D,H,W,x_cstride] -> y [B,ceil(D/2),ceil(H/2),ceil(W/2),
+ * y_cstride] bf16; w = dpf_conv3d_fwd's packing of the [Cout,Cin,3,3,3] tensor ([27][Cin/8][Npad][8]).  Deterministic. */
+int dpf_conv3d_s2_fwd(const void* x, const void* w, void* y, const float* scale, const float* shift, int B, int D, int H, int W,
+                      int Cin, int Cout, int x_cstride, int x_coff, int y_cstride, int y_coff, int relu, void* stream);
+
 /* 2-D 3x3 convolution, stride 1, ANY dilation (pad = dil), Cin in {32, 64, 96}, Cout <= 96 in ONE launch, on a dedicated tcgen05
  * implicit-GEMM kernel (conv2d_tc.cu: dilation by residue-class sub-images, input channels consumed in 32 / 48-channel windows
  * that accumulate in TMEM, N = Cout).  Replaces the six bias-free Conv2d + LeakyReLU(0.1) `convtext` layers of ANM

@@ -245,8 +245,11 @@ def strided_case(ops, cin, cout, shape, seed, transposed, residual=False):
 
 
 @pytest.mark.parametrize("cin,cout,shape", [(32, 64, (1, 8, 32, 16)), (32, 64, (2, 8, 36, 52)), (64, 64, (1, 4, 18, 26)),
-                                            (32, 32, (1, 2, 70, 106))])
+                                            (32, 32, (1, 2, 70, 106)), (32, 64, (1, 5, 35, 53)), (64, 64, (2, 7, 21, 19)),
+                                            (64, 32, (1, 1, 17, 9)), (32, 16, (1, 3, 16, 16))])
 def test_conv_stride2(ops, cin, cout, shape):
+    """plane-streamed stride-2 kernel (dpf_conv3d_s2_fwd): even and ODD depths / heights / widths (the last output plane then has
+    no kd = 2 plane), one and two 32-channel k-parts, 16 / 32 / 64 output channels."""
     assert strided_case(ops, cin, cout, shape, 11, transposed=False) < 1e-2
 
 
