@@ -318,6 +318,8 @@ extern "C" int dpf_conv3d_s2_fwd(const void* x, const void* w, void* y, const fl
   const int npad = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : 64);           // = the packing of dpf_conv3d_fwd (pack_conv_weight)
   if (Cin == 32 && npad == 64) return launch_s2<32, 64, 3, 4>(kp, st);
   if (Cin == 32 && npad == 32) return launch_s2<32, 32, 4, 4>(kp, st);
+  if (Cin == 32 && npad == 16) return launch_s2<32, 16, 4, 4>(kp, st);
+  if (Cin == 64 && npad == 16) return launch_s2<64, 16, 4, 4>(kp, st);
   if (Cin == 64 && npad == 32) return launch_s2<64, 32, 3, 4>(kp, st);
-  return dpf::fail("dpf_conv3d_s2_fwd: no kernel for Cin=%d Cout=%d (built: 32 -> <= 64, 64 -> <= 32 per launch)", Cin, Cout);
+  return dpf::fail("dpf_conv3d_s2_fwd: no kernel for Cin=%d Cout=%d (built: Cin 32 -> Cout <= 64, Cin 64 -> Cout <= 32 per launch)", Cin, Cout);
 }

@@ -49,7 +49,12 @@ constexpr int kMmaWarp = kEpiWarps;                                   // warp 4
 //            on a B200 (tests/test_gpu_configs.py), ~1e-4 of the outputs differ by one bf16 ulp between two launches.
 // In both modes no MMA overwrites: the epilogue leaves every accumulator zeroed after reading it (tcgen05.st).
 constexpr int kGMmaWarps = 4;                                         // warps reserved for the role (NISS of them issue)
-constexpr int kThreads = (kEpiWarps + kGMmaWarps + kProdWarps) * 32;  // 384
+// Transposed kind: the epilogue was the bottleneck (ncu r01: LSU 64 %, tensor 13.6 % -- each of the 128 epilogue threads drains 4
+// parity classes x 32 channels + 8 residual chunks per work item), so a SECOND set of four epilogue warps (warps 12-15, same TMEM
+// lane quarters) takes the rh = 1 classes; the other geometries leave those warps idle.
+constexpr int kEpi2Warps = 4;
+constexpr int kEpi2First = kEpiWarps + kGMmaWarps + kProdWarps;      // warp 12
+constexpr int kThreads = (kEpiWarps + kGMmaWarps + kProdWarps + kEpi2Warps) * 32;  // 512
 constexpr int kMaxTaps = 27;
 
 enum { GEO_S1 = 0, GEO_S2 = 1, GEO_T2 = 2 };
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_tfull[i], NISS);
-      mbar_init(&bar_tempty[i], kEpiWarps);
+      mbar_init(&bar_tempty[i], GEO == GEO_T2 ? kEpiWarps + kEpi2Warps : kEpiWarps);
     }
     mbar_fence_init();
   }
@@ -185,7 +190,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
 
   const int D = p.D, H = p.H, W = p.W;
 
-  if (warp >= kMmaWarp + kGMmaWarps) {
+  if (warp >= kEpi2First && GEO != GEO_T2) {
+    // second epilogue set: only the transposed kind uses it
+  } else if (warp >= kMmaWarp + kGMmaWarps && warp < kEpi2First) {
     // =================================== producers: global -> shared ring ===================================
     const int pwarp = warp - (kMmaWarp + kGMmaWarps);            // 0..kProdWarps-1
     constexpr int PIECES_PER_ROW = C::CWIN * C::NCH;
@@ -238,9 +245,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[prev_slot]);
     }
-  } else if (warp >= kMmaWarp + NISS) {
+  } else if (warp >= kMmaWarp + NISS && warp < kMmaWarp + kGMmaWarps) {
     // reserved MMA-role warps that do not issue in this instantiation: nothing to do until the teardown barrier
-  } else if (warp >= kMmaWarp) {
+  } else if (warp >= kMmaWarp && warp < kMmaWarp + kGMmaWarps) {
     // ============ MMA issuers: each warp runs the (warp-uniform) control flow of its taps, one elected lane issues =====
     const int mw = warp - kMmaWarp;
     constexpr uint32_t idesc = umma_idesc_bf16_f32(128, NPAD);
@@ -309,8 +316,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
     }
   } else {
     // =================================== epilogue: TMEM -> registers -> global ============================
+    // warps 0-3: all classes (transposed kind: the rh = 0 classes); warps 12-15 (transposed kind only): the rh = 1 classes
     uint32_t it = 0;
-    const int m = warp * 32 + lane;
+    const int ew = warp & 3;                                     // TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31)
+    const int cls_lo = (GEO == GEO_T2 && warp >= kEpi2First) ? 2 : 0;
+    const int cls_hi = (GEO == GEO_T2 && warp < kEpi2First) ? 2 : C::NCLS;
+    const int m = ew * 32 + lane;
     const int hrow = m >> 3, wcol = m & 7;
     constexpr int OS = (GEO == GEO_T2) ? 2 : 1;                  // output stride of the GEMM-row grid
     constexpr bool kPrefetch = (GEO == GEO_T2) && (C::NBLK == 1) && (NPAD == 32);
@@ -330,6 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         if (kPrefetch && use_pref) {
 #pragma unroll
           for (int cls = 0; cls < C::NCLS; ++cls) {
+            if (cls < cls_lo || cls >= cls_hi) continue;
             const int oh = mh * OS + (cls >> 1), mw = tw * WT + wcol, ow = mw * OS + (cls & 1);
             const bool ok = (mh < p.Mh) && (mw < p.Mw) && (oh < p.Ho) && (ow < p.Wo);
             const size_t vox = ((static_cast<size_t>(b) * p.Do + item) * p.Ho + oh) * static_cast<size_t>(p.Wo) + ow;
@@ -346,6 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
         tc_fence_after_sync();
 #pragma unroll(kPrefetch ? 4 : 1)
         for (int cls = 0; cls < C::NCLS; ++cls) {
+          if (cls < cls_lo || cls >= cls_hi) continue;
           const int oh = mh * OS + (cls >> 1);
 #pragma unroll 1
           for (int blk = 0; blk < nblk; ++blk) {
@@ -353,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
             const int ow = mw * OS + (cls & 1);
             const bool ok = (mh < p.Mh) && (mw < p.Mw) && (oh < p.Ho) && (ow < p.Wo);
             const size_t vox = ((static_cast<size_t>(b) * p.Do + item) * p.Ho + oh) * static_cast<size_t>(p.Wo) + ow;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + ((as * C::NCLS + cls) * C::NBLK + blk) * NPAD;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + ((as * C::NCLS + cls) * C::NBLK + blk) * NPAD;
 #pragma unroll
             for (int c0 = 0; c0 < NPAD; c0 += 16) {
               uint32_t v[16];
@@ -477,7 +490,7 @@ constexpr int kFMmaWarp = kFEpiWarps;
 constexpr int kFMmaWarps = 4;                                       // warps reserved for the role (NISS of them issue)
 constexpr int kFThreads = (kFEpiWarps + kFMmaWarps + kProdWarps) * 32;   // 512
 
-template <int CIN, int NPAD, int WT, int NS, int R, int DILW = 1>
+template <int CIN, int NPAD, int WT, int NS, int R, int DILW = 1, int KS = 1>
 struct FCfg {
   static constexpr int NCH = CIN / 8;
   static constexpr int WP = WT + 2 * DILW;                       // window columns: DILW = column dilation (2-D mode only)
@@ -489,7 +502,8 @@ struct FCfg {
   static constexpr int W_GROUP_BYTES = NCH * W_ROWS * 16;        // one (kh,kw): [c8][kd*NPAD+co][8]
   static constexpr int W_BYTES = 9 * W_GROUP_BYTES;
   static constexpr int NBLK = WT / 8;
-  static constexpr int COLS = R * NBLK * NPAD;
+  static constexpr int SET_COLS = R * NBLK * NPAD;               // one accumulator ring
+  static constexpr int COLS = KS * SET_COLS;                     // KS = 2: split-K, one ring per issuing warp (summed in the epilogue)
   static constexpr int TMEM_COLS = COLS <= 32 ? 32 : COLS <= 64 ? 64 : COLS <= 128 ? 128 : COLS <= 256 ? 256 : 512;
   static constexpr int KSTEPS = CIN / 16;
   static constexpr int SMEM_BYTES = W_BYTES + NS * SLOT_BYTES + 2 * NPAD * 4 + (2 * NS + 2 * R) * 8 + 16 + 128;
@@ -501,7 +515,12 @@ struct FCfg {
 
 template <int CIN, int NPAD, int WT, int NS, int R, int DILW, int NISS>
 __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __grid_constant__ ConvKParams p) {
-  using C = FCfg<CIN, NPAD, WT, NS, R, DILW>;
+  // One-block tiles (WT = 8) with two issuing warps: SPLIT-K -- warp 0 issues the first half of the K-steps into accumulator ring 0,
+  // warp 1 the second half into ring 1, the epilogue adds the two rings in a fixed order.  Every accumulator is still written by
+  // exactly one thread in program order (deterministic), and two warps share the descriptor arithmetic.
+  constexpr int KS = (NISS == 2 && WT == 8) ? 2 : 1;
+  using C = FCfg<CIN, NPAD, WT, NS, R, DILW, KS>;
+  static_assert(KS == 1 || C::KSTEPS % 2 == 0, "split-K needs an even number of K-steps");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
   uint8_t* s_w = smem;
@@ -654,10 +673,11 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
                 for (int blk = 0; blk < C::NBLK; ++blk) {
                   // NISS == NBLK: warp mw OWNS 128-row block mw (all of its K-steps and taps) -- every accumulator is written by one
                   // thread in program order: parallel issue AND deterministic.  Otherwise (NISS = 4, opt-in) round-robin shares.
-                  if (NISS > 1 && (NISS == C::NBLK ? (blk != mw) : ((blk * C::KSTEPS + ks) % NISS != mw))) continue;
+                  if (KS == 2 ? (ks / (C::KSTEPS / 2) != mw)
+                              : (NISS > 1 && (NISS == C::NBLK ? (blk != mw) : ((blk * C::KSTEPS + ks) % NISS != mw)))) continue;
                   if (blk == 0 || blk < nblk) {                   // a tile always has its first block (no runtime test)
                     const uint64_t adesc = adesc_hi | static_cast<uint64_t>(a0 + ks * 2 * (C::CH_STRIDE >> 4) + blk * 8);
-                    const uint32_t col = tmem_base + blk * (R * NPAD);
+                    const uint32_t col = tmem_base + (KS == 2 ? mw * C::SET_COLS : 0) + blk * (R * NPAD);
                     umma_bf16(col + s_first * NPAD, adesc, bd1, idesc1, true);
                     if (run2 > 0) umma_bf16(col, adesc, bd2, idesc2, true);
                   }
@@ -712,19 +732,33 @@ __global__ void __launch_bounds__(kFThreads, 1) conv3d_kdfused_kernel(const __gr
         mbar_wait(&bar_tfull[st], (Q / R) & 1u);
         tc_fence_after_sync();
         uint32_t v[PER][16];
+        uint32_t v2[KS == 2 ? PER : 1][16];                          // split-K: the second accumulator ring
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
           const int item = i * 2 + half;
           const int blk = item / CHUNKS, c0 = (item % CHUNKS) * 16;
-          if (item < ITEMS && blk < nblk) tmem_ld16(lane_base + blk * (R * NPAD) + st * NPAD + c0, v[i]);
+          if (item < ITEMS && blk < nblk) {
+            tmem_ld16(lane_base + blk * (R * NPAD) + st * NPAD + c0, v[i]);
+            if (KS == 2) tmem_ld16(lane_base + C::SET_COLS + blk * (R * NPAD) + st * NPAD + c0, v2[i % (KS == 2 ? PER : 1)]);
+          }
         }
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < PER; ++i) {                              // leave the stage zeroed for its next output plane
           const int item = i * 2 + half;
           const int blk = item / CHUNKS, c0 = (item % CHUNKS) * 16;
-          if (item < ITEMS && blk < nblk) tmem_zero16(lane_base + blk * (R * NPAD) + st * NPAD + c0);
+          if (item < ITEMS && blk < nblk) {
+            tmem_zero16(lane_base + blk * (R * NPAD) + st * NPAD + c0);
+            if (KS == 2) tmem_zero16(lane_base + C::SET_COLS + blk * (R * NPAD) + st * NPAD + c0);
+          }
+        }
+        if (KS == 2) {                                               // ring 0 + ring 1, always in this order
+#pragma unroll
+          for (int i = 0; i < PER; ++i)
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              v[i][j] = __float_as_uint(__uint_as_float(v[i][j]) + __uint_as_float(v2[i % (KS == 2 ? PER : 1)][j]));
         }
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
@@ -836,7 +870,7 @@ int conv_issuers() {
 
 template <int CIN, int NPAD, int WT, int NS, int R, int DILW, int NISS>
 int launch_fused_n(ConvKParams kp, cudaStream_t st) {
-  using C = FCfg<CIN, NPAD, WT, NS, R, DILW>;
+  using C = FCfg<CIN, NPAD, WT, NS, R, DILW, (NISS == 2 && WT == 8) ? 2 : 1>;
   kp.tiles_h = (kp.Mh + 15) / 16;
   kp.tiles_w = (kp.Mw + WT - 1) / WT;
   kp.ntiles = kp.B * kp.tiles_h * kp.tiles_w;
@@ -855,7 +889,8 @@ int launch_fused_n(ConvKParams kp, cudaStream_t st) {
 template <int CIN, int NPAD, int WT, int NS, int R, int DILW = 1>
 int launch_fused(const ConvKParams& kp, cudaStream_t st) {
   constexpr int NBLK = WT / 8;
-  constexpr int OWN = (NBLK >= 2 && NBLK <= 4) ? NBLK : 1;          // one issuing warp per block when a tile has several blocks
+  // one issuing warp per block when a tile has several blocks; one-block tiles with >= 4 K-steps (Cin = 64): two warps, split-K
+  constexpr int OWN = (NBLK >= 2 && NBLK <= 4) ? NBLK : ((CIN == 64 && 2 * R * NPAD <= 512) ? 2 : 1);
   return conv_issuers() == 4 ? launch_fused_n<CIN, NPAD, WT, NS, R, DILW, 4>(kp, st) : launch_fused_n<CIN, NPAD, WT, NS, R, DILW, OWN>(kp, st);
 }
 
@@ -1008,12 +1043,9 @@ extern "C" int dpf_conv3d_fwd(const dpf_conv3d_args* a, void* stream) {
       if (a->Cin == 32 && npad == 32) return launch_fused<32, 32, 16, 4, 8>(kp, st);
       if (a->Cin == 32 && npad == 16 && wide24) return launch_fused<32, 16, 24, 4, 8>(kp, st);
       if (a->Cin == 32 && npad == 16) return launch_fused<32, 16, 16, 4, 8>(kp, st);
-      {
-        static int wide64 = -1;                                      // DPF_CONV_64W16=1: 16-wide tiles (2 blocks, 2-slot ring) for 64 -> 32
-        if (wide64 < 0) { const char* e = getenv("DPF_CONV_64W16"); wide64 = e ? atoi(e) : 0; }
-        if (a->Cin == 64 && npad == 32 && wide64) return launch_fused<64, 32, 16, 2, 8>(kp, st);
-      }
-      if (a->Cin == 64 && npad == 32) return launch_fused<64, 32, 8, 4, 16>(kp, st);
+      // (64 -> 32 with 16-wide tiles -- 2 blocks, one issuing warp each -- only fits a 2-slot ring next to the 110 KB of weights:
+      //  measured 714 vs 949 TFLOP/s for the 8-wide tile with a 4-slot ring, so it stays 8-wide / single issuer)
+      if (a->Cin == 64 && npad == 32) return launch_fused<64, 32, 8, 4, 8>(kp, st);
       if (a->Cin == 64 && npad == 16) return launch_fused<64, 16, 8, 4, 16>(kp, st);
     }
     if (a->Cin == 32 && npad == 32) return launch<GEO_S1, 32, 32, 24, 5>(kp, st);
@@ -1074,7 +1106,7 @@ extern "C" int dpf_conv2d_fwd(const void* x, const void* w, void* y, const float
     int rc;
     if (dil == 3) rc = npad == 32 ? launch_fused<32, 32, 24, 4, 5, 3>(kp, st) : launch_fused<32, 16, 24, 4, 8, 3>(kp, st);
     else if (dil == 5) rc = npad == 32 ? launch_fused<32, 32, 24, 4, 5, 5>(kp, st) : launch_fused<32, 16, 24, 4, 8, 5>(kp, st);
-    else if (Cin == 64) rc = npad == 32 ? launch_fused<64, 32, 8, 4, 16>(kp, st) : launch_fused<64, 16, 8, 4, 16>(kp, st);
+    else if (Cin == 64) rc = npad == 32 ? launch_fused<64, 32, 8, 4, 8>(kp, st) : launch_fused<64, 16, 8, 4, 16>(kp, st);
     else if (npad == 32) rc = wide24 ? launch_fused<32, 32, 24, 4, 5>(kp, st) : launch_fused<32, 32, 16, 4, 8>(kp, st);
     else rc = wide24 ? launch_fused<32, 16, 24, 4, 8>(kp, st) : launch_fused<32, 16, 16, 4, 8>(kp, st);
     if (rc) return rc;
