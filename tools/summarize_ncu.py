@@ -39,8 +39,35 @@ def full(rep, tag):
                 f.write(f"{h} [{u}] = {v}\n")
     print(open(OUT / f"{tag}.txt").read())
 
+def traffic(rep):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first captured launch, in bytes."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    tot = 0.0
+    for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        j = hdr.index(k)
+        v = float(vals[j].replace(",", ""))
+        tot += v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[j]]
+    return tot, vals[hdr.index("Kernel Name")]
+
+
 if __name__ == "__main__":
-    # bench.py --steps 2 --warmup 1 runs 3 warm-up + 2 timed + 2 stage + 2 per-kernel + 2+2 e2e passes = 13 model passes
-    launch_list("gpurun_out/r01_launches_bench.csv", 13, "r01_bench")
-    for t in ("r01_conv_kdfused_32x32", "r01_conv_kdfused_64x32", "r01_dcn3d", "r01_dcn3d_bwd_data", "r01_wgrad_32x32"):
-        full(f"gpurun_out/{t}.ncu-rep", t)
+    import json
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02l"      # file prefix under gpurun_out/
+    # bench.py --steps 2 --warmup 1 --no-extras --no-cpu runs 3 warm-up + 2 timed + 2 stage + 2 per-kernel + 2+2 e2e passes = 13
+    launch_list(f"gpurun_out/{tag}_launches.csv", 13, "r02_bench")
+    import shutil
+    shutil.copy(f"gpurun_out/{tag}_launches.csv", OUT / "r02_launches_bench.csv")
+    # bench-line kernel key -> capture (the capture tools run the same instantiation at the same shape as the bench step)
+    caps = {"dcn3d_kernel<64>": "dcn3d", "costvol_fwd": "costvol", "regress_fwd": "regress", "conv3d_s2 32->64": "conv_s2",
+            "conv3d kind0 64->32": "conv_kdfused_64x32", "conv3d kind0 32->32": "conv_kdfused_32x32", "conv2d_tc 64->96 d1": "conv2d"}
+    tr = {}
+    for key, name in caps.items():
+        rep = Path(f"gpurun_out/{tag}_{name}.ncu-rep")
+        if not rep.is_file():
+            continue
+        full(str(rep), f"r02_{name}")
+        b, kname = traffic(str(rep))
+        tr[key] = {"bytes_per_launch": b, "kernel": kname, "source": f"profiles/r02_{name}.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)"}
+    (OUT / "r02_traffic.json").write_text(json.dumps(tr, indent=1))
