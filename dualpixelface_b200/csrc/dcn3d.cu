@@ -36,7 +36,12 @@ constexpr int kProdWarps = 16;
 constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;   // 672
 constexpr int kVoxPerPass = kProdWarps * 32 / 4;              // 4 threads (32 bytes = two channel chunks each) per voxel
 constexpr int kNOut = 64;
-constexpr int kBlocks = 2;                                    // GEMM blocks (128 voxels each) per work unit
+#ifndef DPF_DCN_BLOCKS
+#define DPF_DCN_BLOCKS 1
+#endif
+constexpr int kBlocks = DPF_DCN_BLOCKS;                       // GEMM blocks (128 voxels = 8 rows x 16 columns each) per work unit
+constexpr int kUnitH = 8 * kBlocks;                           // rows of a work unit (its width is 16)
+constexpr int kUnitVox = 128 * kBlocks;
 #ifndef DPF_DCN_STAGES
 #define DPF_DCN_STAGES 3
 #endif
@@ -46,7 +51,7 @@ constexpr int kTaps = 27;
 constexpr int kSplitTap = 12;
 constexpr int kOffPitchA = 36, kOffPitchB = 52;              // words; 36 mod 32 = 4, 52 mod 32 = 20: 8 consecutive voxels -> 8 banks
 constexpr int kOffPiecesA = 9, kOffPiecesB = 12;             // 16-byte pieces per voxel
-constexpr int kOffBytes = 256 * (kOffPitchA + kOffPitchB) * 4;
+constexpr int kOffBytes = kUnitVox * (kOffPitchA + kOffPitchB) * 4;
 
 struct DcnParams {
   const __nv_bfloat16* x;
@@ -60,8 +65,9 @@ struct DcnParams {
   int nunits, tiles_h, tiles_w;
 };
 
-template <int CINP, bool STAGED = false>
+template <int CINP, int OMODE = 0>
 struct DCfg {
+  static constexpr bool STAGED = OMODE == 1;
   static constexpr int NCH = CINP / 8;
   static constexpr int KSTEPS = CINP / 16;
   static constexpr int A_CHUNK_BYTES = 128 * 16 + 16;                // chunk pitch (= LBO), +16 B: conflict-free st.shared
@@ -69,7 +75,7 @@ struct DCfg {
   static constexpr int A_STAGE_BYTES = kBlocks * A_BLOCK_BYTES;
   static constexpr int W_TAP_BYTES = NCH * kNOut * 16;               // [chunk][64 rows][16 B]
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + W_TAP_BYTES;
-  static constexpr int TMEM_COLS = 256;                              // 2 stages x 2 blocks x 64 columns
+  static constexpr int TMEM_COLS = 2 * kBlocks * kNOut;                // 2 stages x kBlocks blocks x 64 columns (128 or 256)
   static constexpr int BASE_BYTES = kStages * STAGE_BYTES + 2 * kNOut * 4 + (2 * kStages + 4) * 8 + 16;
   static constexpr int OFF_AT = (BASE_BYTES + 15) & ~15;             // staged offsets (16-byte aligned)
   static constexpr int SMEM_BYTES = (STAGED ? OFF_AT + kOffBytes : BASE_BYTES) + 128;
@@ -83,7 +89,7 @@ __device__ __forceinline__ void unit_coords(int unit, const DcnParams& p, int& d
   int t = unit / p.D;
   w0 = (t % p.tiles_w) * 16;
   t /= p.tiles_w;
-  h0 = (t % p.tiles_h) * 16;
+  h0 = (t % p.tiles_h) * kUnitH;
   b = t / p.tiles_h;
 }
 
@@ -105,12 +111,12 @@ __device__ __forceinline__ void stage_offsets(const DcnParams& p, int unit, int 
     int t = unit / p.D;
     uw0 = (t % p.tiles_w) * 16;
     t /= p.tiles_w;
-    uh0 = (t % p.tiles_h) * 16;
+    uh0 = (t % p.tiles_h) * kUnitH;
     ub = t / p.tiles_h;
   }
   const long long plane = (static_cast<long long>(ub) * p.D + ud) * p.H;
   const uint32_t dst0 = smem_u32(s_dst);
-  for (int i = ptid; i < 256 * NP; i += kProdWarps * 32) {
+  for (int i = ptid; i < kUnitVox * NP; i += kProdWarps * 32) {
     const int r = i / NP, q = i - r * NP;
     const int hh = uh0 + (r >> 4), ww = uw0 + (r & 15);
     const bool ok = (hh < p.H) && (ww < p.W);
@@ -120,9 +126,11 @@ __device__ __forceinline__ void stage_offsets(const DcnParams& p, int unit, int 
   cp_async_commit();
 }
 
-template <int CINP, bool STAGED>
+template <int CINP, int OMODE>
 __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constant__ DcnParams p) {
-  using C = DCfg<CINP, STAGED>;
+  using C = DCfg<CINP, OMODE>;
+  constexpr bool STAGED = OMODE == 1;
+  constexpr bool VECOFF = OMODE == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
   uint8_t* s_stage = smem;
@@ -134,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
   uint64_t* bar_tempty = bar_tfull + 2;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + 2);
   float* s_offA = reinterpret_cast<float*>(smem + C::OFF_AT);            // [256][kOffPitchA]   (STAGED only)
-  float* s_offB = s_offA + 256 * kOffPitchA;                             // [256][kOffPitchB]
+  float* s_offB = s_offA + kUnitVox * kOffPitchA;                             // [256][kOffPitchB]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -209,18 +217,54 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
       // otherwise be two dependent memory round trips per (voxel, tap)
       const float* obase[PASSES];
       float onext[PASSES][3];
+      // VECOFF: the 81 offsets of a voxel are read as 16-byte pieces, 3 pieces (= 4 taps x 3 floats) at a time: lane cq < 3 of the
+      // voxel's 4-lane group loads piece cq of the block (ONE load instruction = 8 lines per warp for 4 taps, instead of 3 scalar
+      // loads = 24 lines per tap); the three floats of a tap are then fetched from the owning lane with warp shuffles.
+      float4 oblk[PASSES], onxt[PASSES];
+      const float4* ob4[PASSES];
       if (!STAGED) {
 #pragma unroll
         for (int ps = 0; ps < PASSES; ++ps) {
-          obase[ps] = p.offset + static_cast<size_t>(vbase + (ud * H + vh[ps]) * W + vw[ps]) * p.off_cstride;
-          onext[ps][0] = __ldg(obase[ps] + 0); onext[ps][1] = __ldg(obase[ps] + 1); onext[ps][2] = __ldg(obase[ps] + 2);
+          const int r = ps * kVoxPerPass + vsub;
+          const int hh = uh0 + (r >> 4), ww = uw0 + (r & 15);
+          const bool vin = (hh < H) && (ww < W);                          // independent of lane_live (the lane may serve offsets only)
+          obase[ps] = p.offset + static_cast<size_t>(vbase + (ud * H + (vin ? hh : 0)) * W + (vin ? ww : 0)) * p.off_cstride;
+          if (VECOFF) {
+            ob4[ps] = reinterpret_cast<const float4*>(obase[ps]) + min(cq, 2);
+            oblk[ps] = __ldg(ob4[ps]);
+          } else {
+            onext[ps][0] = __ldg(obase[ps] + 0); onext[ps][1] = __ldg(obase[ps] + 1); onext[ps][2] = __ldg(obase[ps] + 2);
+          }
         }
       }
       for (int tap = 0; tap < kTaps; ++tap, ++g) {
         const int stage = g % kStages;
         const uint32_t ph = (g / kStages) & 1u;
         float ocur[PASSES][3];
-        if (STAGED) {
+        if (VECOFF) {
+          const int j = tap & 3;
+          if (j == 0 && tap + 4 < kTaps) {                             // next block (taps tap+4 .. tap+7) while this one is used
+#pragma unroll
+            for (int ps = 0; ps < PASSES; ++ps) onxt[ps] = __ldg(ob4[ps] + 3 * ((tap >> 2) + 1));
+          }
+          const int gl = lane & ~3;
+          // word 3*j + a of the 12-word block lives in lane (3*j + a) / 4, component (3*j + a) % 4: warp-uniform switch on j
+#define DPF_OFF_PICK(A, LANE, COMP) ocur[ps][A] = __shfl_sync(0xffffffffu, oblk[ps].COMP, gl | LANE)
+#pragma unroll
+          for (int ps = 0; ps < PASSES; ++ps) {
+            switch (j) {
+              case 0: DPF_OFF_PICK(0, 0, x); DPF_OFF_PICK(1, 0, y); DPF_OFF_PICK(2, 0, z); break;
+              case 1: DPF_OFF_PICK(0, 0, w); DPF_OFF_PICK(1, 1, x); DPF_OFF_PICK(2, 1, y); break;
+              case 2: DPF_OFF_PICK(0, 1, z); DPF_OFF_PICK(1, 1, w); DPF_OFF_PICK(2, 2, x); break;
+              default: DPF_OFF_PICK(0, 2, y); DPF_OFF_PICK(1, 2, z); DPF_OFF_PICK(2, 2, w); break;
+            }
+          }
+#undef DPF_OFF_PICK
+          if (j == 3) {
+#pragma unroll
+            for (int ps = 0; ps < PASSES; ++ps) oblk[ps] = onxt[ps];
+          }
+        } else if (STAGED) {
           if (tap == kSplitTap) {
             // half B of this unit has landed and every producer is past its last read of half A: refill A for the next unit
             cp_async_wait<0>();
@@ -419,14 +463,16 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
   }
 }
 
-template <int CINP, bool STAGED>
+template <int CINP, int OMODE>
 int launch_dcn(const DcnParams& p, cudaStream_t st) {
-  using C = DCfg<CINP, STAGED>;
-  auto kern = dcn3d_kernel<CINP, STAGED>;
+  using C = DCfg<CINP, OMODE>;
+  auto kern = dcn3d_kernel<CINP, OMODE>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return dpf::fail("dpf_dcn3d_fwd: cannot opt in to %d B shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e));
+    // the gather lives on the L1 cache: ask for the smallest shared-memory carve-out that holds this kernel's buffers
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (C::SMEM_BYTES + 1024) * 100 / (228 * 1024) + 1);
     attr_done = true;
   }
   const int grid = std::min(p.nunits, dpf::sm_count());
@@ -457,14 +503,16 @@ extern "C" int dpf_dcn3d_fwd(const void* x, const float* offset, const void* w, 
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.B = B; p.D = D; p.H = H; p.W = W; p.relu = relu; p.x_cstride = x_cstride;
   p.nvox = static_cast<long long>(B) * D * H * W;
-  p.tiles_h = (H + 15) / 16;
+  p.tiles_h = (H + kUnitH - 1) / kUnitH;
   p.tiles_w = (W + 15) / 16;
   p.nunits = B * D * p.tiles_h * p.tiles_w;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // staged offsets need 16-byte aligned voxel rows that hold floats 0..83 (the 81 real offsets + padding)
-  static int staged_env = -1;
-  if (staged_env < 0) { const char* e = getenv("DPF_DCN_STAGED"); staged_env = e ? atoi(e) : 0; }
-  const bool staged = staged_env && off_cstride % 4 == 0 && off_cstride >= 84 && (reinterpret_cast<uintptr_t>(offset) & 15u) == 0;
-  if (Cin_pad == 32) return staged ? launch_dcn<32, true>(p, st) : launch_dcn<32, false>(p, st);
-  return staged ? launch_dcn<64, true>(p, st) : launch_dcn<64, false>(p, st);
+  // offset path: 2 (default) = 16-byte loads + shuffles, 1 = staged in shared memory, 0 = scalar loads.  Modes 1 and 2 need
+  // 16-byte aligned voxel rows that hold floats 0..83 (the 81 real offsets + padding); anything else takes mode 0.
+  static int omode_env = -1;
+  if (omode_env < 0) { const char* e = getenv("DPF_DCN_OMODE"); omode_env = e ? atoi(e) : 2; }
+  const bool vec_ok = off_cstride % 4 == 0 && off_cstride >= 84 && (reinterpret_cast<uintptr_t>(offset) & 15u) == 0;
+  const int omode = vec_ok ? omode_env : 0;
+  if (Cin_pad == 32) return omode == 2 ? launch_dcn<32, 2>(p, st) : omode == 1 ? launch_dcn<32, 1>(p, st) : launch_dcn<32, 0>(p, st);
+  return omode == 2 ? launch_dcn<64, 2>(p, st) : omode == 1 ? launch_dcn<64, 1>(p, st) : launch_dcn<64, 0>(p, st);
 }
