@@ -304,57 +304,66 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
           const float pw = static_cast<float>(vw[ps] + tk) + ocur[ps][2];
           const bool inside = vlive[ps] && pd > -1.f && phh > -1.f && pw > -1.f && pd < static_cast<float>(D) &&
                               phh < static_cast<float>(H) && pw < static_cast<float>(W);
-          const float fd = floorf(pd), fh = floorf(phh), fw = floorf(pw);
-          const int d0 = static_cast<int>(fd), h0 = static_cast<int>(fh), w0 = static_cast<int>(fw);
-          const float ld = pd - fd, lh = phh - fh, lw = pw - fw;
-          // branch-free corners: clamp the index, zero the weight when the corner (or the whole sample) is outside,
-          // so that all 8 loads are issued back to back
-          const float wd0 = (inside && d0 >= 0) ? 1.f - ld : 0.f, wd1 = (inside && d0 + 1 <= D - 1) ? ld : 0.f;
-          const float wh0 = (h0 >= 0) ? 1.f - lh : 0.f, wh1 = (h0 + 1 <= H - 1) ? lh : 0.f;
-          const float ww0 = (w0 >= 0) ? 1.f - lw : 0.f, ww1 = (w0 + 1 <= W - 1) ? lw : 0.f;
-          const int dc0 = min(max(d0, 0), D - 1), dc1 = min(max(d0 + 1, 0), D - 1);
-          const int hc0 = min(max(h0, 0), H - 1), hc1 = min(max(h0 + 1, 0), H - 1);
-          const int wc0 = min(max(w0, 0), W - 1), wc1 = min(max(w0 + 1, 0), W - 1);
-          const uint32_t b00 = static_cast<uint32_t>(vbase + dc0 * HW + hc0 * W) * cs2 + lane_off;
-          const uint32_t b01 = static_cast<uint32_t>(vbase + dc0 * HW + hc1 * W) * cs2 + lane_off;
-          const uint32_t b10 = static_cast<uint32_t>(vbase + dc1 * HW + hc0 * W) * cs2 + lane_off;
-          const uint32_t b11 = static_cast<uint32_t>(vbase + dc1 * HW + hc1 * W) * cs2 + lane_off;
-          const uint32_t o0 = static_cast<uint32_t>(wc0) * cs2, o1 = static_cast<uint32_t>(wc1) * cs2;
-          uint4 ua[8], ub2[8];
-          ld_global_v8(xbytes + (b00 + o0), ua[0], ub2[0]);
-          ld_global_v8(xbytes + (b00 + o1), ua[1], ub2[1]);
-          ld_global_v8(xbytes + (b01 + o0), ua[2], ub2[2]);
-          ld_global_v8(xbytes + (b01 + o1), ua[3], ub2[3]);
-          ld_global_v8(xbytes + (b10 + o0), ua[4], ub2[4]);
-          ld_global_v8(xbytes + (b10 + o1), ua[5], ub2[5]);
-          ld_global_v8(xbytes + (b11 + o0), ua[6], ub2[6]);
-          ld_global_v8(xbytes + (b11 + o1), ua[7], ub2[7]);
-          const float a00 = wd0 * wh0, a01 = wd0 * wh1, a10 = wd1 * wh0, a11 = wd1 * wh1;
-          const float cw[8] = {a00 * ww0, a00 * ww1, a01 * ww0, a01 * ww1, a10 * ww0, a10 * ww1, a11 * ww0, a11 * ww1};
-          // packed bf16 blend (HFMA2.BF16): the blended A tile is rounded to bf16 for the MMA anyway
+          // warp-uniform skip: when none of the warp's 8 voxels samples inside the volume for this tap, the A rows are zero and
+          // neither the address arithmetic nor the loads are issued
           __nv_bfloat162 acc[8];
-          {
-            const __nv_bfloat162 w2 = __float2bfloat162_rn(cw[0]);
-            acc[0] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[0].x));
-            acc[1] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[0].y));
-            acc[2] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[0].z));
-            acc[3] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[0].w));
-            acc[4] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[0].x));
-            acc[5] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[0].y));
-            acc[6] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[0].z));
-            acc[7] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[0].w));
-          }
+          if (__any_sync(0xffffffffu, inside)) {
+            const float fd = floorf(pd), fh = floorf(phh), fw = floorf(pw);
+            const int d0 = static_cast<int>(fd), h0 = static_cast<int>(fh), w0 = static_cast<int>(fw);
+            const float ld = pd - fd, lh = phh - fh, lw = pw - fw;
+            // branch-free corners: clamp the index, zero the weight when the corner (or the whole sample) is outside,
+            // so that all 8 loads are issued back to back
+            const float wd0 = (inside && d0 >= 0) ? 1.f - ld : 0.f, wd1 = (inside && d0 + 1 <= D - 1) ? ld : 0.f;
+            const float wh0 = (h0 >= 0) ? 1.f - lh : 0.f, wh1 = (h0 + 1 <= H - 1) ? lh : 0.f;
+            const float ww0 = (w0 >= 0) ? 1.f - lw : 0.f, ww1 = (w0 + 1 <= W - 1) ? lw : 0.f;
+            const int dc0 = min(max(d0, 0), D - 1), dc1 = min(max(d0 + 1, 0), D - 1);
+            const int hc0 = min(max(h0, 0), H - 1), hc1 = min(max(h0 + 1, 0), H - 1);
+            const int wc0 = min(max(w0, 0), W - 1), wc1 = min(max(w0 + 1, 0), W - 1);
+            const uint32_t b00 = !inside ? lane_off : static_cast<uint32_t>(vbase + dc0 * HW + hc0 * W) * cs2 + lane_off;
+            const uint32_t b01 = !inside ? lane_off : static_cast<uint32_t>(vbase + dc0 * HW + hc1 * W) * cs2 + lane_off;
+            const uint32_t b10 = !inside ? lane_off : static_cast<uint32_t>(vbase + dc1 * HW + hc0 * W) * cs2 + lane_off;
+            const uint32_t b11 = !inside ? lane_off : static_cast<uint32_t>(vbase + dc1 * HW + hc1 * W) * cs2 + lane_off;
+            // a sample outside the volume contributes zero and is not read (deform_im2col_cuda.cuh:248): its lanes point all eight
+            // loads at ONE dummy line (voxel 0), so they add a single wavefront to the instruction instead of eight
+            const uint32_t o0 = inside ? static_cast<uint32_t>(wc0) * cs2 : 0u, o1 = inside ? static_cast<uint32_t>(wc1) * cs2 : 0u;
+            uint4 ua[8], ub2[8];
+            ld_global_v8(xbytes + (b00 + o0), ua[0], ub2[0]);
+            ld_global_v8(xbytes + (b00 + o1), ua[1], ub2[1]);
+            ld_global_v8(xbytes + (b01 + o0), ua[2], ub2[2]);
+            ld_global_v8(xbytes + (b01 + o1), ua[3], ub2[3]);
+            ld_global_v8(xbytes + (b10 + o0), ua[4], ub2[4]);
+            ld_global_v8(xbytes + (b10 + o1), ua[5], ub2[5]);
+            ld_global_v8(xbytes + (b11 + o0), ua[6], ub2[6]);
+            ld_global_v8(xbytes + (b11 + o1), ua[7], ub2[7]);
+            const float a00 = wd0 * wh0, a01 = wd0 * wh1, a10 = wd1 * wh0, a11 = wd1 * wh1;
+            const float cw[8] = {a00 * ww0, a00 * ww1, a01 * ww0, a01 * ww1, a10 * ww0, a10 * ww1, a11 * ww0, a11 * ww1};
+            // packed bf16 blend (HFMA2.BF16): the blended A tile is rounded to bf16 for the MMA anyway
+            {
+              const __nv_bfloat162 w2 = __float2bfloat162_rn(cw[0]);
+              acc[0] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[0].x));
+              acc[1] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[0].y));
+              acc[2] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[0].z));
+              acc[3] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[0].w));
+              acc[4] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[0].x));
+              acc[5] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[0].y));
+              acc[6] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[0].z));
+              acc[7] = __hmul2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[0].w));
+            }
+  #pragma unroll
+            for (int c = 1; c < 8; ++c) {
+              const __nv_bfloat162 w2 = __float2bfloat162_rn(cw[c]);
+              acc[0] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[c].x), acc[0]);
+              acc[1] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[c].y), acc[1]);
+              acc[2] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[c].z), acc[2]);
+              acc[3] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[c].w), acc[3]);
+              acc[4] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[c].x), acc[4]);
+              acc[5] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[c].y), acc[5]);
+              acc[6] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[c].z), acc[6]);
+              acc[7] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[c].w), acc[7]);
+            }
+          } else {
 #pragma unroll
-          for (int c = 1; c < 8; ++c) {
-            const __nv_bfloat162 w2 = __float2bfloat162_rn(cw[c]);
-            acc[0] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[c].x), acc[0]);
-            acc[1] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[c].y), acc[1]);
-            acc[2] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[c].z), acc[2]);
-            acc[3] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ua[c].w), acc[3]);
-            acc[4] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[c].x), acc[4]);
-            acc[5] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[c].y), acc[5]);
-            acc[6] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[c].z), acc[6]);
-            acc[7] = __hfma2(w2, *reinterpret_cast<const __nv_bfloat162*>(&ub2[c].w), acc[7]);
+            for (int c = 0; c < 8; ++c) acc[c] = __float2bfloat162_rn(0.f);
           }
           if (lane_live) {
             uint4 oa, ob;

@@ -23,6 +23,16 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _strict_fp32_reference():
+    """The parity tests compare the bf16 sm_100a hot path with fp32 oracle code and, where `encoder_autocast = False`, run the
+    cuDNN encoder in fp32 to isolate the hot path: TF32 must be off for both, independent of which test module runs first."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
 @pytest.fixture(scope="session")
 def golden_stages():
     import numpy as np
