@@ -36,6 +36,9 @@ def _halo_input(x, f):
 # conv3 of a DPBlock as three chained 32-channel windows works (tests/test_gpu_kernels.py::test_conv2d_rows_channel_windows_chain)
 # but measured slower than cuDNN + one dpf_bias_act pass (encoder 5.37 -> 5.70 ms): off.
 CHAIN_CONV3 = False
+import os
+TC_CONV3 = os.environ.get("DPF_ENC_TC_CONV3", "1") != "0"
+TC_MODE = os.environ.get("DPF_ENC_TC", "all")          # none | dil (dilated layers only) | all
 
 
 def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d | None):
@@ -53,6 +56,13 @@ def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d | None):
             tuple(conv.padding) == tuple(conv.dilation) and conv.groups == 1 and conv.in_channels == 32 and conv.out_channels in (16, 32)):
         # (64-channel layers and multi-chunk outputs are supported by the kernel but measured slower than cuDNN here)
         f["wp"] = ops.conv2d_rows_plan(wf)
+    # other 3x3 / stride 1 layers with 32, 64 or 96 input channels (any dilation: the dilation-2 conv4 of the inter-blocks, for which
+    # cuDNN falls back to sm80-class kernels; the 64-channel blocks): the dedicated 2-D tcgen05 kernel, bias + activation (+ skip) fused
+    elif (TC_MODE != "none" and tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 1) and conv.dilation[0] == conv.dilation[1]
+          and tuple(conv.padding) == tuple(conv.dilation) and conv.groups == 1 and conv.in_channels in (32, 64, 96)
+          and conv.out_channels % 8 == 0 and conv.out_channels <= 96 and (TC_MODE == "all" or conv.dilation[0] > 1)):
+        f["tc"] = ops.pack_conv2d_tc_weight(wf)
+        f["cout"] = conv.out_channels
     return f
 
 
@@ -70,6 +80,12 @@ def _conv_act(x, f, slope, res=None, out=None, y_coff=0):
         y = ops.conv2d_rows_multi(xh if xh.is_contiguous() else xh.contiguous(), f["wp"], f["b"],
                                   rh if rh is None or rh.is_contiguous() else rh.contiguous(), relu=slope != 1.0, slope=slope,
                                   out=out, y_coff=y_coff, dil=f["dil"][0])
+        return y.permute(0, 3, 1, 2)
+    if "tc" in f and TILING is None:
+        xh = x.permute(0, 2, 3, 1)
+        rh = res.permute(0, 2, 3, 1) if res is not None else None
+        y = ops.conv2d_tc(xh if xh.is_contiguous() else xh.contiguous(), f["tc"], f["cout"], f["dil"][0], None, f["b"],
+                          rh if rh is None or rh.is_contiguous() else rh.contiguous(), relu=slope != 1.0, slope=slope, out=out, y_coff=y_coff)
         return y.permute(0, 3, 1, 2)
     return ops.bias_act(_conv(x, f), f["b"], slope, res=res, out=out, y_coff=y_coff)
 
@@ -121,6 +137,14 @@ class _Block:
             bn = blk.conv3[1]
             wf, _ = _fuse(c3.weight, c3.bias, bn.running_mean, bn.running_var, bn.eps, bn.weight, bn.bias)
             self.c3_windows = [ops.pack_conv2d_weight(wf.detach().float()[:, k:k + 32]) for k in (0, 32, 64)]
+        # conv3 on the dedicated 2-D tcgen05 kernel (dpf_conv2d_tc_fwd: all 96 input channels in one launch, bias + skip + PReLU fused)
+        if (TC_CONV3 and not hasattr(self, "c3_windows") and tuple(c3.kernel_size) == (3, 3) and tuple(c3.stride) == (1, 1) and
+                tuple(c3.dilation) == (1, 1) and tuple(c3.padding) == (1, 1) and c3.groups == 1 and c3.in_channels in (32, 64, 96)
+                and c3.out_channels % 8 == 0 and c3.out_channels <= 96 and self.s3 != 1.0):
+            from torch.nn.utils.fusion import fuse_conv_bn_weights as _fuse
+            bn = blk.conv3[1]
+            wf, _ = _fuse(c3.weight, c3.bias, bn.running_mean, bn.running_var, bn.eps, bn.weight, bn.bias)
+            self.c3_tc = ops.pack_conv2d_tc_weight(wf.detach().float())
         self.c4, self.s4 = _fold(blk.conv4[0][0], blk.conv4[0][1]), _slope(blk.conv4[1])
         self.dw = _fold(blk.conv5.depthwise, None)
         self.pw, self.s5 = _fold(blk.conv5.pointwise, blk.conv5.bn), _slope(blk.conv5.prelu)
@@ -139,9 +163,13 @@ class _Block:
             t = ops.conv2d_rows(cat, self.c3_windows[1], c, None, None, t, x_coff=c)
             t = ops.conv2d_rows(cat, self.c3_windows[2], c, None, None, t, relu=self.s3 != 1.0, slope=self.s3, x_coff=2 * c)
             t = t.permute(0, 3, 1, 2)
+        elif hasattr(self, "c3_tc") and TILING is None:
+            ah = a.permute(0, 2, 3, 1)
+            t = ops.conv2d_tc(cat, self.c3_tc, c, 1, None, self.c3["b"], ah if ah.is_contiguous() else ah.contiguous(), relu=True,
+                              slope=self.s3).permute(0, 3, 1, 2)
         else:
             t = ops.bias_act(_conv(cat.permute(0, 3, 1, 2), self.c3), self.c3["b"], self.s3, res=a)
-        u = ops.bias_act(_conv(t, self.c4), self.c4["b"], self.s4)
+        u = _conv_act(t, self.c4, self.s4)
         v = ops.bias_act(_conv(_conv(u, self.dw), self.pw), self.pw["b"], self.s5)
         return ops.bias_act(_conv(x, self.skip), self.skip["b"], 1.0, res=v)                         # + weighted skip
 
