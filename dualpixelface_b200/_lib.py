@@ -25,7 +25,7 @@ class ConvArgs(C.Structure):
         ("y_f32", c_int), ("y_cstride", c_int), ("y_coff", c_int),
         ("scale", c_void_p), ("shift", c_void_p), ("residual", c_void_p),
         ("relu", c_int), ("stats", c_void_p),
-        ("x_cstride", c_int), ("x_coff", c_int), ("res_pre", c_int),
+        ("x_cstride", c_int), ("x_coff", c_int), ("res_pre", c_int), ("slope", c_float),
     ]
 
 
@@ -73,6 +73,7 @@ SIGNATURES = {
     "dpf_pyramid_cat_tile": (c_int, [c_void_p] * 4 + [c_int] * 10 + [c_void_p]),
     "dpf_anm_tail_bwd": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     "dpf_anm_gather_bwd": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
+    "dpf_softargmin_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_float, c_float, c_void_p]),
 }
 
 _lib = None

@@ -264,6 +264,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * s_scale[c0 + j] + s_shift[c0 + j];
           __nv_bfloat16* yo = p.y + pix * p.y_cstride + p.y_coff + c0;
+          const bool res_post = (p.relu & 2) != 0;             // y = act(v) + residual instead of act(v + residual)
+          if (res_post && (p.relu & 1)) {
+            const float sl = p.slope;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f) + sl * fminf(f[j], 0.f);
+          }
           if (p.residual != nullptr) {
             const __nv_bfloat16* ro = p.residual + pix * p.y_cstride + p.y_coff + c0;
             uint4 r0 = *reinterpret_cast<const uint4*>(ro), r1 = make_uint4(0u, 0u, 0u, 0u);
@@ -273,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
             f[8] += bf16_lo(r1.x); f[9] += bf16_hi(r1.x); f[10] += bf16_lo(r1.y); f[11] += bf16_hi(r1.y);
             f[12] += bf16_lo(r1.z); f[13] += bf16_hi(r1.z); f[14] += bf16_lo(r1.w); f[15] += bf16_hi(r1.w);
           }
-          if (p.relu) {
+          if ((p.relu & 1) && !res_post) {
             const float sl = p.slope;                           // 0 = ReLU, else LeakyReLU / single-parameter PReLU
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f) + sl * fminf(f[j], 0.f);

@@ -1028,9 +1028,11 @@ extern "C" int dpf_conv3d_fwd(const dpf_conv3d_args* a, void* stream) {
   }
   kp.xs_h = a->W; kp.xs_d = static_cast<long long>(a->H) * a->W; kp.xs_b = kp.xs_d * a->D;   // dense [B,D,H,W] views
   kp.ys_h = kp.xs_h; kp.ys_d = kp.xs_d; kp.ys_b = kp.xs_b;
-  kp.halo = 0; kp.center_row_only = 0; kp.lin_d = kp.lin_h = kp.lin_max = 0; kp.slope = 0.f;
+  kp.halo = 0; kp.center_row_only = 0; kp.lin_d = kp.lin_h = kp.lin_max = 0; kp.slope = a->slope;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int npad = npad_for(a->Cout);
+  DPF_REQUIRE(a->slope == 0.f || (a->kind == 0 && npad <= 32 && a->relu),
+              "dpf_conv3d_fwd: a LeakyReLU slope is built for the kd-fused 3x3x3 stride-1 layers (Cout <= 32) only");
   if (geo == GEO_S1) {
     DPF_REQUIRE(a->Cin == 32 || a->Cout <= 32, "dpf_conv3d_fwd: Cin=64 supports Cout<=32 per launch (split on the host)");
     static int fused = -1;

@@ -174,6 +174,29 @@ __global__ void __launch_bounds__(kTX* kTY) regress_bwd_kernel(const float* __re
   }
 }
 
+
+// Soft-argmin over D levels at the resolution of the cost (no up-sampling): one thread per position, coalesced plane reads.
+__global__ void __launch_bounds__(256) softargmin_kernel(const float* __restrict__ cost, float* __restrict__ disp, float* __restrict__ prob,
+                                                         int D, long long P, float mindisp, float step) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= P) return;
+  const float* c = cost + static_cast<long long>(blockIdx.y) * D * P + i;
+  float m = -INFINITY;
+  for (int d = 0; d < D; ++d) m = fmaxf(m, __ldg(c + d * P));
+  float se = 0.f, sed = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float e = __expf(__ldg(c + d * P) - m);
+    se += e;
+    sed = fmaf(e, mindisp + step * static_cast<float>(d), sed);
+  }
+  const float inv = 1.0f / se;
+  disp[static_cast<long long>(blockIdx.y) * P + i] = sed * inv;
+  if (prob != nullptr) {
+    float* pp = prob + static_cast<long long>(blockIdx.y) * D * P + i;
+    for (int d = 0; d < D; ++d) pp[d * P] = __expf(__ldg(c + d * P) - m) * inv;
+  }
+}
+
 }  // namespace
 
 extern "C" int dpf_regress_fwd_tile(const float* cost, float* disp, float* prob, int B, int D, int H4loc, int W4, int H4glob,
@@ -215,4 +238,13 @@ extern "C" int dpf_regress_bwd(const float* cost, const float* ddisp, float* dco
   else if (D == 4) regress_bwd_kernel<4><<<grid, block, 0, st>>>(cost, ddisp, dcost, H4, W4, mindisp, step);
   else regress_bwd_kernel<16><<<grid, block, 0, st>>>(cost, ddisp, dcost, H4, W4, mindisp, step);
   return dpf::after_launch("dpf_regress_bwd");
+}
+
+extern "C" int dpf_softargmin_fwd(const float* cost, float* disp, float* prob, int B, int D, long long P, float mindisp, float step,
+                                  void* stream) {
+  DPF_REQUIRE(cost && disp, "dpf_softargmin_fwd: null pointer");
+  DPF_REQUIRE(B > 0 && B <= 65535 && D >= 1 && D <= 64 && P > 0 && (P + 255) / 256 < (1LL << 31), "dpf_softargmin_fwd: bad shape");
+  dim3 grid(static_cast<unsigned>((P + 255) / 256), B);
+  softargmin_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(cost, disp, prob, D, P, mindisp, step);
+  return dpf::after_launch("dpf_softargmin_fwd");
 }

@@ -97,12 +97,14 @@ class TCConv3d:
 
     def __call__(self, x: torch.Tensor, scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
                  residual: Optional[torch.Tensor] = None, relu: bool = False, out_f32: bool = False,
-                 out: Optional[torch.Tensor] = None, y_coff: int = 0) -> torch.Tensor:
+                 out: Optional[torch.Tensor] = None, y_coff: int = 0, slope: float = 0.0) -> torch.Tensor:
         from . import ops
         assert x.shape[-1] == self.cin, (x.shape, self.cin)
         if out is None:
             out = torch.empty(*self.out_shape(x), self.cout, device=x.device,
                               dtype=torch.float32 if out_f32 else torch.bfloat16)
+        if slope != 0.0 and not (self.kind == KIND_3x3x3 and all(ln.first_k and ln.last_k for ln in self.plan)):
+            raise NotImplementedError("a LeakyReLU slope is built for single-window 3x3x3 stride-1 layers only")
         if self.s2 is not None and residual is None and out.dtype == torch.bfloat16:
             for wp, co, n in self.s2:
                 ops.conv3d_s2(x, wp, n, scale[co:co + n].contiguous() if scale is not None else None,
@@ -114,7 +116,7 @@ class TCConv3d:
             sh = shift[ln.y_coff: ln.y_coff + ln.cout] if shift is not None else None
             if ln.first_k and ln.last_k:
                 ops.conv3d(x, wp, self.kind, ln.cout, sc, sh, residual, relu, out=out, y_coff=y_coff + ln.y_coff,
-                           cin=ln.cin, x_coff=ln.x_coff)
+                           cin=ln.cin, x_coff=ln.x_coff, slope=slope)
                 continue
             # input-channel split: chain fp32 partial sums, finish with the affine
             if residual is not None:

@@ -131,8 +131,9 @@ def _timing_end(e0, key, work, unit):
 def conv3d(x: torch.Tensor, w_packed: torch.Tensor, kind: int, cout: int, scale: Optional[torch.Tensor] = None,
            shift: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, relu: bool = False,
            out: Optional[torch.Tensor] = None, out_f32: bool = False, y_coff: int = 0, cin: Optional[int] = None,
-           x_coff: int = 0, res_pre: bool = False) -> torch.Tensor:
+           x_coff: int = 0, res_pre: bool = False, slope: float = 0.0) -> torch.Tensor:
     """One launch: y = relu?(conv(x) * scale + shift + residual); x [B,D,H,W,Cx] bf16 -> y [B,Do,Ho,Wo,Cstride].
+    slope: negative-side slope of the activation (LeakyReLU; kd-fused 3x3x3 stride-1 layers with Cout <= 32 only).
 
     `cin`/`x_coff` select a channel window of x; `y_coff` a channel offset of the output tensor `out`.
     """
@@ -160,7 +161,7 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, kind: int, cout: int, scale:
                  scale=scale.data_ptr() if scale is not None else None,
                  shift=shift.data_ptr() if shift is not None else None,
                  residual=residual.data_ptr() if residual is not None else None, relu=int(relu), stats=None,
-                 x_cstride=cx, x_coff=x_coff, res_pre=int(res_pre))
+                 x_cstride=cx, x_coff=x_coff, res_pre=int(res_pre), slope=float(slope))
     tm = _timing_begin()
     check(lib().dpf_conv3d_fwd(C.byref(a), _stream()), "dpf_conv3d_fwd")
     vox = b * (d * h * w if kind == KIND_T2 else do * ho * wo)       # transposed: every input voxel meets all 27 taps
@@ -381,10 +382,11 @@ def pack_conv2d_tc_weight(w: torch.Tensor, cin_pad: Optional[int] = None) -> tor
 
 def conv2d_tc(x: torch.Tensor, w_packed: torch.Tensor, cout: int, dil: int = 1, scale: Optional[torch.Tensor] = None,
               shift: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, relu: bool = False, slope: float = 0.0,
-              out: Optional[torch.Tensor] = None, y_coff: int = 0, x_coff: int = 0) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, y_coff: int = 0, x_coff: int = 0, res_post: bool = False) -> torch.Tensor:
     """3x3 / stride 1 / dilation dil / padding dil conv on channels-last images in ONE launch (dpf_conv2d_tc_fwd):
     x [N,H,W,Cx] bf16 (Cin = 8 * w_packed.shape[1] channels from x_coff) -> y [N,H,W,Cy] (ceil8(cout) channels at y_coff; the ones
-    beyond cout are exact zeros), y = act(conv * scale + shift + residual), act = LeakyReLU(slope) when relu (slope 0 = ReLU)."""
+    beyond cout are exact zeros), y = act(conv * scale + shift + residual), act = LeakyReLU(slope) when relu (slope 0 = ReLU);
+    res_post: y = act(conv * scale + shift) + residual."""
     _req(x, torch.bfloat16, "x"); _req(w_packed, torch.bfloat16, "w_packed")
     n, h, w, cx = x.shape
     cin = w_packed.shape[1] * 8
@@ -402,7 +404,7 @@ def conv2d_tc(x: torch.Tensor, w_packed: torch.Tensor, cout: int, dil: int = 1, 
             assert t.numel() == cout
     tm = _timing_begin()
     check(lib().dpf_conv2d_tc_fwd(_p(x), _p(w_packed), _p(out), _p(scale), _p(shift), _p(residual), n, h, w, cin, cout, cx, x_coff,
-                                  out.shape[-1], y_coff, int(dil), int(relu), float(slope), _stream()), "dpf_conv2d_tc_fwd")
+                                  out.shape[-1], y_coff, int(dil), int(relu) | (2 if res_post else 0), float(slope), _stream()), "dpf_conv2d_tc_fwd")
     _timing_end(tm, f"conv2d_tc {cin}->{cout} d{dil}", 2.0 * 9 * cin * cout * n * h * w, "flop")
     return out
 
@@ -424,3 +426,14 @@ def conv3d_s2(x: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optiona
                                   int(relu), _stream()), "dpf_conv3d_s2_fwd")
     _timing_end(tm, f"conv3d_s2 {cin}->{cout}", 2.0 * 27 * cin * cout * b * do * ho * wo, "flop")
     return out
+
+
+def softargmin(cost: torch.Tensor, mindisp: float, step: float, want_prob: bool = False):
+    """Soft-argmin over dim 1 without up-sampling (dpf_softargmin_fwd): cost [B,D,*] fp32 -> (disp [B,*], prob [B,D,*] | None)."""
+    _req(cost, torch.float32, "cost")
+    b, d = cost.shape[:2]
+    p = cost[0, 0].numel()
+    disp = torch.empty(b, *cost.shape[2:], device=cost.device, dtype=torch.float32)
+    prob = torch.empty_like(cost) if want_prob else None
+    check(lib().dpf_softargmin_fwd(_p(cost), _p(disp), _p(prob), b, d, p, float(mindisp), float(step), _stream()), "dpf_softargmin_fwd")
+    return disp, prob

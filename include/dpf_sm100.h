@@ -102,6 +102,8 @@ typedef struct dpf_conv3d_args {
   float* stats;
   int x_cstride, x_coff;   /* channel stride / offset of x (0,0 = dense Cin); lets a launch read a channel window */
   int res_pre;             /* 1: y = relu?((conv + residual) * scale + shift)  (K-split partial sums) */
+  float slope;             /* relu != 0: v > 0 ? v : slope * v (0 = ReLU; LeakyReLU(0.2) of StereoNet's filter, src/model/stereonet/
+                              mainmodel.py:43-49); non-zero only for kind 0 with Cout <= 32 */
 } dpf_conv3d_args;
 int dpf_conv3d_fwd(const dpf_conv3d_args* args, void* stream);
 /* number of bf16 elements of the packed weight buffer for (kind, Cin, Cout) */
@@ -116,6 +118,9 @@ long long dpf_conv3d_weight_elems(int kind, int Cin, int Cout);
  * ------------------------------------------------------------------------------------------------- */
 int dpf_regress_fwd(const float* cost, float* disp, float* prob, int B, int D, int H4, int W4, float mindisp, float step,
                     void* stream);
+/* Soft-argmin WITHOUT up-sampling (StereoNet's disp_regression, src/model/stereonet/modules.py:99-120): cost [B,D,P] fp32 ->
+ * disp [B,P] = sum_d softmax_d(cost) * (mindisp + d*step); prob (optional, may be NULL) [B,D,P] = the softmax.  D <= 64. */
+int dpf_softargmin_fwd(const float* cost, float* disp, float* prob, int B, int D, long long P, float mindisp, float step, void* stream);
 /* dcost [B,D,H4,W4] (zeroed by the call) from ddisp [B,H,W]; recomputes the softmax. */
 int dpf_regress_bwd(const float* cost, const float* ddisp, float* dcost, int B, int D, int H4, int W4, float mindisp,
                     float step, void* stream);
@@ -228,7 +233,9 @@ int dpf_conv3d_s2_fwd(const void* x, const void* w, void* y, const float* scale,
  *   y[n,h,w, y_coff+co] = act( conv(x[..., x_coff:x_coff+Cin]; w)[co] * scale[co] + shift[co] + residual[n,h,w, y_coff+co] )
  * x [N,H,W,x_cstride], y / residual [N,H,W,y_cstride] bf16 channels-last; w bf16 [9 taps (kh,kw)][Cin/8][Npad][8] with
  * Npad = dpf_conv2d_tc_npad(Cout) (output channels zero-padded); ceil8(Cout) channels are written (the extra ones are 0).
- * scale / shift fp32 [Cout] or NULL; act(v) = relu ? (v > 0 ? v : slope*v) : v.  Deterministic (single MMA issuer). */
+ * scale / shift fp32 [Cout] or NULL; act(v) = (relu & 1) ? (v > 0 ? v : slope*v) : v.  relu & 2: the residual is added AFTER the
+ * activation, y = act(conv * scale + shift) + residual (BasicBlock of StereoNet, src/model/stereonet/modules.py:19-29).
+ * Deterministic (single MMA issuer). */
 int dpf_conv2d_tc_npad(int Cout);
 long long dpf_conv2d_tc_weight_elems(int Cin, int Cout);
 int dpf_conv2d_tc_fwd(const void* x, const void* w, void* y, const float* scale, const float* shift, const void* residual,

@@ -699,6 +699,72 @@ def psmnet_forward(batch: dict, st: State, training: bool, cfg: dict = PSM_CFG, 
     return res
 
 
+STN_CFG = dict(mindisp=-4, maxdisp=12, k=3, loss_weight=(1.0, 1.0), lambdas=(1.0,))
+
+
+def _stn_block(x, st: State, p: str, dil: int, training: bool, stats=None):
+    """BasicBlock.forward of StereoNet, src/model/stereonet/modules.py:10-29: ``x + LeakyReLU_0.2(convbn(x))`` -- the block's
+    conv2 is constructed (its weights are in the state dict) but never applied (:23, the reference's own "bug?" note :27)."""
+    return x + F.leaky_relu(_convbn2(x, st, p + ".conv1.0", 1, 1, dil, training, stats), 0.2)
+
+
+def stn_encoder(img: torch.Tensor, st: State, p: str, training: bool, k: int = 3, stats=None):
+    """FeatureExtraction.forward, src/model/stereonet/modules.py:32-61: k 5x5 stride-2 convs (bias, no activation), six
+    BasicBlocks, one 3x3 conv with bias -> [B,32,H/2^k,W/2^k]."""
+    x = img
+    for i in range(k):
+        x = _conv2(x, st, f"{p}.downsample.{i}", stride=2, pad=2, bias=True)
+    for i in range(6):
+        x = _stn_block(x, st, f"{p}.residual_blocks.{i}", 1, training, stats)
+    return _conv2(x, st, p + ".conv_alone", bias=True)
+
+
+def stn_refine(low_disp: torch.Tensor, rgb: torch.Tensor, st: State, p: str, training: bool, stats=None):
+    """EdgeAwareRefinement.forward, src/model/stereonet/modules.py:64-96: bilinear (align_corners=False) upsample of the
+    low-resolution disparity to the image size, x8 when the size ratio is >= 1.5, 4 -> 32 convbn + LeakyReLU(0.2), six dilated
+    BasicBlocks (1, 2, 4, 8, 1, 1), 32 -> 1 conv with bias, ReLU(upsampled + residual)."""
+    up = F.interpolate(low_disp.unsqueeze(1), size=rgb.shape[-2:], mode="bilinear", align_corners=False)
+    if rgb.shape[-1] / low_disp.shape[-1] >= 1.5:
+        up = up * 8
+    x = F.leaky_relu(_convbn2(torch.cat([up, rgb], 1), st, p + ".conv2d_feature.0", 1, 1, 1, training, stats), 0.2)
+    for i, dil in enumerate((1, 2, 4, 8, 1, 1)):
+        x = _stn_block(x, st, f"{p}.residual_astrous_blocks.{i}", dil, training, stats)
+    return F.relu((up + _conv2(x, st, p + ".conv2d_out", bias=True)).squeeze(1))
+
+
+def stereonet_forward(batch: dict, st: State, training: bool, cfg: dict = STN_CFG, flip_lr: bool = True,
+                      stages: Optional[dict] = None, stats: Optional[dict] = None):
+    """STEREONET.forward, src/model/stereonet/mainmodel.py:80-152: features at 1/2^k, DIFFERENCE volume over int(costrange)
+    row shifts (:100-114; costrange keeps the /4 of the other models, :37-40), four convbn_3d + LeakyReLU(0.2) and a 32 -> 1
+    conv with bias (:43-51,117-120), softmax regression over the 2^k levels WITHOUT up-sampling (modules.py:99-120; bins
+    arange(level) * (maxdisp-mindisp)/level + mindisp), edge-aware refinement on batch['right'] (:125-126; always the right
+    image, whatever flip_lr says), level 0 scaled by W / w and bilinearly up-sampled (:128-137)."""
+    level = int(math.pow(2, cfg["k"]))
+    crange = cost_range(cfg["mindisp"], cfg["maxdisp"], level)
+    bins = np.arange(level, dtype=np.float64) * ((cfg["maxdisp"] - cfg["mindisp"]) / float(level)) + cfg["mindisp"]
+    ref_img, tgt_img = _pick_ref_target(batch, flip_lr, training)
+    ref = stn_encoder(ref_img, st, "feature_extraction", training, cfg["k"], stats)
+    tgt = stn_encoder(tgt_img, st, "feature_extraction", training, cfg["k"], stats)
+    vol = diff_volume(ref, tgt, crange)
+    x = vol
+    for i in range(4):
+        x = F.leaky_relu(_convbn3(x, st, f"filter.{i}.0", 1, training, stats), 0.2)
+    cost = _conv3(x, st, "conv3d_alone", bias=True).squeeze(1)
+    disp, prob = regression(cost, bins)
+    right = batch["right"]
+    refined = stn_refine(disp, right, st, "edge_aware_refinements.0", training, stats)
+    coarse = F.interpolate((disp * (right.shape[-1] / disp.shape[-1])).unsqueeze(1), size=right.shape[-2:], mode="bilinear",
+                           align_corners=False).squeeze(1)
+    res = {"pred_depth": torch.stack([coarse, refined], 1), "prob_depth": prob.unsqueeze(1), "ref_feature": ref.max(1)[0]}
+    if stages is not None:
+        stages.update(ref=ref, tgt=tgt, volume=vol, cost=cost, disp_low=disp)
+    if training and "disp" in batch:
+        l1 = smooth_l1_multi(res["pred_depth"], batch["disp"], batch.get("mask"), cfg["loss_weight"])
+        res["smoothL1_loss"] = l1
+        res["final_loss"] = cfg["lambdas"][0] * l1
+    return res
+
+
 def calibrate_running_stats(st: State, stats: dict) -> State:
     """Copy of ``st`` whose BatchNorm running statistics are the batch statistics collected in ``stats``.
 

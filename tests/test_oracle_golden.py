@@ -186,3 +186,36 @@ def test_oracle_gwcnet_style():
     gold, res, shapes = _variant_case("psm_gwcnet8", "psmnet", dict(O.PSM_CFG, cost_volume="gwcnet", group_num=8))
     assert shapes["aggregation.dres0.0.0.weight"] == (32, 72, 3, 3, 3)
     close(gold["psm_gwcnet8/pred_depth"], res["pred_depth"], 1e-5)
+
+
+# ---- StereoNet, fixtures from tests/golden/make_golden_stereonet.py (the unmodified reference) ----
+def _stereonet_shapes():
+    import json
+    return {k: tuple(v) for k, v in json.loads((GOLDEN / "state_keys_stereonet.json").read_text()).items()}
+
+
+def test_oracle_stereonet_forward():
+    """Oracle == the reference's STEREONET in train mode (batch statistics, loss) and in eval mode with calibrated statistics."""
+    gold = np.load(GOLDEN / "model_stereonet.npz")
+    st = synth_state(_stereonet_shapes(), seed=1)
+    batch = synthetic_batch(2, 64, 96, training=True, seed=0)
+    stats = {}
+    with torch.no_grad():
+        res_t = O.stereonet_forward(dict(batch), st, True, stats=stats)
+        res_e = O.stereonet_forward(dict(batch), O.calibrate_running_stats(st, stats), False)
+    close(gold["train/pred_depth"], res_t["pred_depth"], 2e-5)
+    close(gold["train/final_loss"], res_t["final_loss"], 2e-5)
+    for key in ("pred_depth", "prob_depth", "ref_feature"):
+        close(gold[f"eval/{key}"], res_e[key], 2e-5)
+    assert res_e["pred_depth"].shape == (2, 2, 64, 96) and res_e["prob_depth"].shape == (2, 1, 8, 8, 12)
+
+
+def test_oracle_stereonet_grads():
+    gold = np.load(GOLDEN / "model_stereonet.npz")
+    st = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v)
+          for k, v in synth_state(_stereonet_shapes(), seed=1).items()}
+    res = O.stereonet_forward(dict(synthetic_batch(2, 64, 96, training=True, seed=0)), st, True)
+    res["final_loss"].backward()
+    for key in [k[len("train/grad/"):] for k in gold.files if k.startswith("train/grad/")]:
+        close(gold[f"train/grad/{key}"], st[key].grad, 1e-4)
+    assert st["feature_extraction.residual_blocks.0.conv2.0.weight"].grad is None      # constructed but never applied (modules.py:23)
