@@ -40,7 +40,7 @@ def test_abi_version_and_cpu_refusal():
 def test_conv_struct_layout_matches_header():
     text = HEADER.read_text()
     body = text[text.index("typedef struct dpf_conv3d_args"):text.index("} dpf_conv3d_args;")]
-    names = re.findall(r"\b(?:int|const void\*|void\*|const float\*|float\*)\s+([^;]+);", body)
+    names = re.findall(r"\b(?:int|const void\*|void\*|const float\*|float\*|float)\s+([^;]+);", body)
     fields = [n.strip() for grp in names for n in grp.split(",")]
     fields = [re.sub(r"\s*/\*.*", "", f).strip() for f in fields]
     assert fields == [f[0] for f in _lib.ConvArgs._fields_], (fields, [f[0] for f in _lib.ConvArgs._fields_])
