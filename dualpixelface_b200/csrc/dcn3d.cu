@@ -53,6 +53,11 @@ constexpr int kOffPitchA = 36, kOffPitchB = 52;              // words; 36 mod 32
 constexpr int kOffPiecesA = 9, kOffPiecesB = 12;             // 16-byte pieces per voxel
 constexpr int kOffBytes = kUnitVox * (kOffPitchA + kOffPitchB) * 4;
 
+// (kd, kh, kw) - 1 of tap t = (kd*3 + kh)*3 + kw
+__constant__ signed char kTapD[27] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+__constant__ signed char kTapH[27] = {-1, -1, -1, 0, 0, 0, 1, 1, 1, -1, -1, -1, 0, 0, 0, 1, 1, 1, -1, -1, -1, 0, 0, 0, 1, 1, 1};
+__constant__ signed char kTapW[27] = {-1, 0, 1, -1, 0, 1, -1, 0, 1, -1, 0, 1, -1, 0, 1, -1, 0, 1, -1, 0, 1, -1, 0, 1, -1, 0, 1};
+
 struct DcnParams {
   const __nv_bfloat16* x;
   const float* offset;
@@ -63,6 +68,7 @@ struct DcnParams {
   int B, D, H, W, relu, x_cstride, off_cstride;
   long long nvox;
   int nunits, tiles_h, tiles_w;
+  int skip_oob;
 };
 
 template <int CINP, int OMODE = 0>
@@ -97,6 +103,13 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
+}
+
+// base + 32-bit byte offset as one IMAD.WIDE.U32 (the compiler's 64-bit add is two instructions per gathered corner)
+__device__ __forceinline__ const char* ptr_add_u32(const char* base, uint32_t off) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(off), "l"(reinterpret_cast<unsigned long long>(base)));
+  return reinterpret_cast<const char*>(r);
 }
 
 // producers only (16 warps): named barrier 1
@@ -294,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
           mbar_arrive_expect_tx(&bar_full[stage], C::W_TAP_BYTES);
           bulk_g2s(smem_u32(sa + C::A_STAGE_BYTES), p.w + static_cast<size_t>(tap) * (C::W_TAP_BYTES / 2), C::W_TAP_BYTES, &bar_full[stage]);
         }
-        const int ti = tap / 9 - 1, tj = (tap / 3) % 3 - 1, tk = tap % 3 - 1;
+        const int ti = static_cast<int>(kTapD[tap]), tj = static_cast<int>(kTapH[tap]), tk = static_cast<int>(kTapW[tap]);
         const float fdz = static_cast<float>(ud + ti);
 #pragma unroll
         for (int ps = 0; ps < PASSES; ++ps) {
@@ -307,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
           // warp-uniform skip: when none of the warp's 8 voxels samples inside the volume for this tap, the A rows are zero and
           // neither the address arithmetic nor the loads are issued
           __nv_bfloat162 acc[8];
-          if (__any_sync(0xffffffffu, inside)) {
+          if (!p.skip_oob || __any_sync(0xffffffffu, inside)) {
             const float fd = floorf(pd), fh = floorf(phh), fw = floorf(pw);
             const int d0 = static_cast<int>(fd), h0 = static_cast<int>(fh), w0 = static_cast<int>(fw);
             const float ld = pd - fd, lh = phh - fh, lw = pw - fw;
@@ -319,22 +332,22 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
             const int dc0 = min(max(d0, 0), D - 1), dc1 = min(max(d0 + 1, 0), D - 1);
             const int hc0 = min(max(h0, 0), H - 1), hc1 = min(max(h0 + 1, 0), H - 1);
             const int wc0 = min(max(w0, 0), W - 1), wc1 = min(max(w0 + 1, 0), W - 1);
-            const uint32_t b00 = !inside ? lane_off : static_cast<uint32_t>(vbase + dc0 * HW + hc0 * W) * cs2 + lane_off;
-            const uint32_t b01 = !inside ? lane_off : static_cast<uint32_t>(vbase + dc0 * HW + hc1 * W) * cs2 + lane_off;
-            const uint32_t b10 = !inside ? lane_off : static_cast<uint32_t>(vbase + dc1 * HW + hc0 * W) * cs2 + lane_off;
-            const uint32_t b11 = !inside ? lane_off : static_cast<uint32_t>(vbase + dc1 * HW + hc1 * W) * cs2 + lane_off;
+            const uint32_t b00 = (p.skip_oob && !inside) ? lane_off : static_cast<uint32_t>(vbase + dc0 * HW + hc0 * W) * cs2 + lane_off;
+            const uint32_t b01 = (p.skip_oob && !inside) ? lane_off : static_cast<uint32_t>(vbase + dc0 * HW + hc1 * W) * cs2 + lane_off;
+            const uint32_t b10 = (p.skip_oob && !inside) ? lane_off : static_cast<uint32_t>(vbase + dc1 * HW + hc0 * W) * cs2 + lane_off;
+            const uint32_t b11 = (p.skip_oob && !inside) ? lane_off : static_cast<uint32_t>(vbase + dc1 * HW + hc1 * W) * cs2 + lane_off;
             // a sample outside the volume contributes zero and is not read (deform_im2col_cuda.cuh:248): its lanes point all eight
             // loads at ONE dummy line (voxel 0), so they add a single wavefront to the instruction instead of eight
-            const uint32_t o0 = inside ? static_cast<uint32_t>(wc0) * cs2 : 0u, o1 = inside ? static_cast<uint32_t>(wc1) * cs2 : 0u;
+            const uint32_t o0 = (inside || !p.skip_oob) ? static_cast<uint32_t>(wc0) * cs2 : 0u, o1 = (inside || !p.skip_oob) ? static_cast<uint32_t>(wc1) * cs2 : 0u;
             uint4 ua[8], ub2[8];
-            ld_global_v8(xbytes + (b00 + o0), ua[0], ub2[0]);
-            ld_global_v8(xbytes + (b00 + o1), ua[1], ub2[1]);
-            ld_global_v8(xbytes + (b01 + o0), ua[2], ub2[2]);
-            ld_global_v8(xbytes + (b01 + o1), ua[3], ub2[3]);
-            ld_global_v8(xbytes + (b10 + o0), ua[4], ub2[4]);
-            ld_global_v8(xbytes + (b10 + o1), ua[5], ub2[5]);
-            ld_global_v8(xbytes + (b11 + o0), ua[6], ub2[6]);
-            ld_global_v8(xbytes + (b11 + o1), ua[7], ub2[7]);
+            ld_global_v8(ptr_add_u32(xbytes, b00 + o0), ua[0], ub2[0]);
+            ld_global_v8(ptr_add_u32(xbytes, b00 + o1), ua[1], ub2[1]);
+            ld_global_v8(ptr_add_u32(xbytes, b01 + o0), ua[2], ub2[2]);
+            ld_global_v8(ptr_add_u32(xbytes, b01 + o1), ua[3], ub2[3]);
+            ld_global_v8(ptr_add_u32(xbytes, b10 + o0), ua[4], ub2[4]);
+            ld_global_v8(ptr_add_u32(xbytes, b10 + o1), ua[5], ub2[5]);
+            ld_global_v8(ptr_add_u32(xbytes, b11 + o0), ua[6], ub2[6]);
+            ld_global_v8(ptr_add_u32(xbytes, b11 + o1), ua[7], ub2[7]);
             const float a00 = wd0 * wh0, a01 = wd0 * wh1, a10 = wd1 * wh0, a11 = wd1 * wh1;
             const float cw[8] = {a00 * ww0, a00 * ww1, a01 * ww0, a01 * ww1, a10 * ww0, a10 * ww1, a11 * ww0, a11 * ww1};
             // packed bf16 blend (HFMA2.BF16): the blended A tile is rounded to bf16 for the MMA anyway
@@ -427,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
     uint32_t it = 0;
     for (int unit = unit_lo; unit < unit_hi; ++unit, ++it) {
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
-      mbar_wait(&bar_tfull[as], aph);
+      mbar_wait(&bar_tfull[as], aph);      // (a nanosleep back-off here was measured 2 % slower: it delays the accumulator hand-back)
       tc_fence_after_sync();
       int ud, uh0, uw0, ub;
       unit_coords(unit, p, ud, uh0, uw0, ub);
@@ -518,6 +531,11 @@ extern "C" int dpf_dcn3d_fwd(const void* x, const float* offset, const void* w, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // offset path: 2 (default) = 16-byte loads + shuffles, 1 = staged in shared memory, 0 = scalar loads.  Modes 1 and 2 need
   // 16-byte aligned voxel rows that hold floats 0..83 (the 81 real offsets + padding); anything else takes mode 0.
+  {
+    static int skip_env = -1;
+    if (skip_env < 0) { const char* e = getenv("DPF_DCN_SKIP"); skip_env = e ? atoi(e) : 1; }
+    p.skip_oob = skip_env;
+  }
   static int omode_env = -1;
   if (omode_env < 0) { const char* e = getenv("DPF_DCN_OMODE"); omode_env = e ? atoi(e) : 2; }
   const bool vec_ok = off_cstride % 4 == 0 && off_cstride >= 84 && (reinterpret_cast<uintptr_t>(offset) & 15u) == 0;
