@@ -78,6 +78,8 @@ class TCConv3d:
         if kind == KIND_S2 and self.cin in (32, 64) and cin == self.cin and self.cout % 8 == 0:
             step = 64 if self.cin == 32 else 32
             self.s2 = [(ops.pack_conv_weight(w[co:co + step].float()), co, min(step, self.cout - co)) for co in range(0, self.cout, step)]
+        # 32 -> 1 heads: the bandwidth-bound kernel with the taps as the GEMM's N dimension (dpf_conv3d_head_fwd)
+        self.head = ops.pack_head_weight(w) if (kind == KIND_3x3x3 and self.cout == 1 and cin == 32 and self.cin == 32) else None
         self.plan = plan_launches(kind, self.cin, self.cout)
         self.packed = []
         for ln in self.plan:
@@ -103,6 +105,9 @@ class TCConv3d:
         if out is None:
             out = torch.empty(*self.out_shape(x), self.cout, device=x.device,
                               dtype=torch.float32 if out_f32 else torch.bfloat16)
+        if (self.head is not None and out.dtype == torch.float32 and out.shape[-1] == 1 and y_coff == 0 and scale is None and not relu
+                and (shift is None or shift.numel() == 1)):
+            return ops.conv3d_head(x, self.head, residual, float(shift) if shift is not None else 0.0, out=out)
         if slope != 0.0 and not (self.kind == KIND_3x3x3 and all(ln.first_k and ln.last_k for ln in self.plan)):
             raise NotImplementedError("a LeakyReLU slope is built for single-window 3x3x3 stride-1 layers only")
         if self.s2 is not None and residual is None and out.dtype == torch.bfloat16:

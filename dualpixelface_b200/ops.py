@@ -437,3 +437,29 @@ def softargmin(cost: torch.Tensor, mindisp: float, step: float, want_prob: bool 
     prob = torch.empty_like(cost) if want_prob else None
     check(lib().dpf_softargmin_fwd(_p(cost), _p(disp), _p(prob), b, d, p, float(mindisp), float(step), _stream()), "dpf_softargmin_fwd")
     return disp, prob
+
+
+def pack_head_weight(w: torch.Tensor) -> torch.Tensor:
+    """nn.Conv3d(32, 1, 3) weight [1,32,3,3,3] -> bf16 [4 (c/8)][32 (tap; 27 real + 5 zero)][8 (c%8)] for dpf_conv3d_head_fwd."""
+    assert tuple(w.shape) == (1, 32, 3, 3, 3), w.shape
+    buf = torch.zeros(4, 32, 8, device=w.device, dtype=torch.float32)
+    buf[:, :27] = w.detach().float().reshape(4, 8, 27).permute(0, 2, 1)
+    return buf.to(torch.bfloat16).contiguous()
+
+
+def conv3d_head(x: torch.Tensor, w_packed: torch.Tensor, residual: Optional[torch.Tensor] = None, shift: float = 0.0,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """32 -> 1 channel 3x3x3 conv on the bandwidth-bound head kernel: x [B,D,H,W,Cx>=32] bf16 -> [B,D,H,W,1] fp32 (+ shift + residual)."""
+    _req(x, torch.bfloat16, "x"); _req(w_packed, torch.bfloat16, "w_packed")
+    b, d, h, w, cx = x.shape
+    if out is None:
+        out = torch.empty(b, d, h, w, 1, device=x.device, dtype=torch.float32)
+    _req(out, torch.float32, "out")
+    assert out.numel() == b * d * h * w
+    if residual is not None:
+        _req(residual, torch.float32, "residual")
+        assert residual.numel() == out.numel()
+    tm = _timing_begin()
+    check(lib().dpf_conv3d_head_fwd(_p(x), _p(w_packed), _p(out), _p(residual), float(shift), b, d, h, w, cx, _stream()), "dpf_conv3d_head_fwd")
+    _timing_end(tm, "conv3d_head 32->1", float(b * d * h * w * (32 * 2 + 4 + (4 if residual is not None else 0))), "byte")
+    return out

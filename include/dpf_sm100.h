@@ -226,6 +226,16 @@ int dpf_conv2d_fwd(const void* x, const void* w, void* y, const float* scale, co
 int dpf_conv3d_s2_fwd(const void* x, const void* w, void* y, const float* scale, const float* shift, int B, int D, int H, int W,
                       int Cin, int Cout, int x_cstride, int x_coff, int y_cstride, int y_coff, int relu, void* stream);
 
+/* 32 -> 1 channel 3x3x3 convolution (stride 1, pad 1), fp32 output: the `nn.Conv3d(32, 1, 3, 1, 1)` closing each classifK of the
+ * hourglass (src/model/stereodpnet/modules.py:288-296, cumulative adds :323-325) and StereoNet's conv3d_alone
+ * (src/model/stereonet/mainmodel.py:50-51).  Bandwidth-bound formulation (conv3d_head.cu): the 27 taps are the N dimension of ONE
+ * MMA pair per 128 positions, the partial planes are combined with their shifts on the CUDA cores.
+ *   y[b,d,h,w] = sum_{c,kd,kh,kw} w[c,kd,kh,kw] * x[b,d+kd-1,h+kh-1,w+kw-1,c] + shift + residual[b,d,h,w]
+ * x [B,D,H,W,x_cstride] bf16 (channels 0..31 are used); w bf16 [4 (c/8)][32 (tap, 27 real + 5 zero rows)][8 (c%8)];
+ * y / residual [B,D,H,W] fp32 (residual may be NULL, may alias y).  Deterministic. */
+int dpf_conv3d_head_fwd(const void* x, const void* w, float* y, const float* residual, float shift, int B, int D, int H, int W,
+                        int x_cstride, void* stream);
+
 /* 2-D 3x3 convolution, stride 1, ANY dilation (pad = dil), Cin in {32, 64, 96}, Cout <= 96 in ONE launch, on a dedicated tcgen05
  * implicit-GEMM kernel (conv2d_tc.cu: dilation by residue-class sub-images, input channels consumed in 32 / 48-channel windows
  * that accumulate in TMEM, N = Cout).  Replaces the six bias-free Conv2d + LeakyReLU(0.1) `convtext` layers of ANM

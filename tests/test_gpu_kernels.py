@@ -419,3 +419,27 @@ def test_fused_losses(ops, n_heads, with_normal, with_mask):
     # determinism: the partial sums are combined in a fixed order
     l1b, _ = losses.FusedLossFn.apply(p2.detach(), n2.detach() if with_normal else None, disp, mask, nrm if with_normal else None, wts)
     assert float(l1b) == float(l1)
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 37, 50), (1, 8, 28, 60), (1, 1, 14, 30), (2, 3, 16, 33)])
+def test_conv3d_head_vs_torch(shape):
+    """dpf_conv3d_head_fwd (taps as the GEMM N dimension + shifted sums) == F.conv3d in fp32 on the same bf16 operands; ragged
+    sizes, tiles that end exactly at / one past the image border, shift and fp32 residual."""
+    import torch.nn.functional as F
+    from dualpixelface_b200.layers import KIND_3x3x3, TCConv3d
+    b, d, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(b, d, h, w, 32, device="cuda", generator=g).to(torch.bfloat16)
+    wt = (torch.randn(1, 32, 3, 3, 3, device="cuda", generator=g) * 0.1).to(torch.bfloat16).float()
+    res = torch.randn(b, d, h, w, 1, device="cuda", generator=g)
+    layer = TCConv3d(wt, KIND_3x3x3)
+    assert layer.head is not None
+    want = F.conv3d(x.float().permute(0, 4, 1, 2, 3), wt, padding=1).permute(0, 2, 3, 4, 1)
+    got = layer(x, out_f32=True)
+    assert got.shape == want.shape
+    err = (got - want).abs().max().item()
+    print(f"head {shape}: max abs err {err:.2e} (output max {want.abs().max():.2f})")
+    assert err < 2e-4 * max(1.0, want.abs().max().item())
+    got2 = layer(x, shift=torch.tensor([0.25], device="cuda"), residual=res, out_f32=True)
+    assert (got2 - (want + 0.25 + res)).abs().max().item() < 2e-4 * max(1.0, want.abs().max().item())
+    assert torch.equal(layer(x, out_f32=True), got)                       # deterministic
