@@ -30,14 +30,15 @@ constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;     // 544
 constexpr int RH = 16, RW = 32;                                  // input region of a tile (rows x columns)
 constexpr int OH = RH - 2, OW = RW - 2;                          // output tile
 constexpr int NBLK = RW / 8;                                     // GEMM blocks (16 rows x 8 columns = 128 positions)
-constexpr int NS = 2;                                            // input slots
+constexpr int NS = 4;                                            // input slots
+constexpr int NP = 1;                                            // P buffers
 constexpr int CH_STRIDE = RH * RW * 16 + 32;                     // bytes between 8-channel chunk planes (+32: conflict-free cp.async)
 constexpr int SLOT_BYTES = 4 * CH_STRIDE;
 constexpr int W_BYTES = 4 * 32 * 16;                             // [c8][32 taps][8] bf16
 constexpr int PP = 40;                                           // row pitch of a P plane in floats (rows 4q..4q+3 -> distinct banks)
 constexpr int P_TAP = RH * PP;                                   // floats per tap plane
 constexpr int P_BYTES = 27 * P_TAP * 4;
-constexpr int SMEM_BYTES = W_BYTES + NS * SLOT_BYTES + 2 * P_BYTES + (2 * NS + 8) * 8 + 16 + 128;
+constexpr int SMEM_BYTES = W_BYTES + NS * SLOT_BYTES + NP * P_BYTES + (2 * NS + 8) * 8 + 16 + 128;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 
 struct HeadParams {
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_head_kernel(const __grid_c
   uint8_t* s_w = smem;
   uint8_t* s_slots = smem + W_BYTES;
   float* s_p = reinterpret_cast<float*>(s_slots + NS * SLOT_BYTES);
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_p) + 2 * P_BYTES);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_p) + NP * P_BYTES);
   uint64_t* bar_empty = bar_full + NS;
   uint64_t* bar_tfull = bar_empty + NS;
   uint64_t* bar_tempty = bar_tfull + 2;
@@ -101,7 +102,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_head_kernel(const __grid_c
     // =================================== producers: (tile, plane) -> slot ring ======================================
     const int ptid = threadIdx.x - (kMmaWarp + 1) * 32;          // 0..127
     uint32_t g = 0;
-    int prev_slot = -1;
+    auto land = [&](int slot) {                                   // this thread's copies into `slot` have landed: publish them
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[slot]);
+    };
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int tw = tile % p.tiles_w;
       const int th = (tile / p.tiles_w) % p.tiles_h;
@@ -122,20 +127,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_head_kernel(const __grid_c
           cp_async16_zfill(sbase + c8 * CH_STRIDE + pos * 16, src, ok);
         }
         cp_async_commit();
-        if (prev_slot >= 0) {
-          cp_async_wait<1>();
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_full[prev_slot]);
+        if (g >= 2) {                                             // three planes in flight: plane g-2 is published now
+          cp_async_wait<2>();
+          land((g - 2) % NS);
         }
-        prev_slot = slot;
       }
     }
-    if (prev_slot >= 0) {
+    if (g >= 2) {
+      cp_async_wait<1>();
+      land((g - 2) % NS);
+    }
+    if (g >= 1) {
       cp_async_wait<0>();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_full[prev_slot]);
+      land((g - 1) % NS);
     }
   } else if (warp == kMmaWarp) {
     // =================================== MMA issuer: 4 blocks x 2 k-steps per plane ================================
@@ -178,9 +182,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_head_kernel(const __grid_c
       for (int z = 0; z < D; ++z, ++g) {
         const uint32_t as = g & 1u;
         mbar_wait(&bar_tfull[as], (g >> 1) & 1u);
-        mbar_wait(&bar_pempty[as], ((g >> 1) & 1u) ^ 1u);
+        const uint32_t ps = g % NP;
+        mbar_wait(&bar_pempty[ps], ((g / NP) & 1u) ^ 1u);
         tc_fence_after_sync();
-        float* pbuf = s_p + as * (P_BYTES / 4);
+        float* pbuf = s_p + ps * (P_BYTES / 4);
         const int m = q * 32 + lane;
 #pragma unroll
         for (int blk = 0; blk < NBLK; ++blk) {
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_head_kernel(const __grid_c
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&bar_tempty[as]);                           // accumulator stage free for the MMA of plane z + 2
-          mbar_arrive(&bar_pfull[as]);                            // (release: the st.shared above are ordered before the arrive)
+          mbar_arrive(&bar_pfull[ps]);                            // (release: the st.shared above are ordered before the arrive)
         }
       }
     }
@@ -231,8 +236,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_head_kernel(const __grid_c
           if (p.residual != nullptr && z >= 1 && col_ok && orow <= OH && h < H && w < W)
             rsd[i] = __ldg(p.residual + ((static_cast<size_t>(b) * D + (z - 1)) * H + h) * W + w);
         }
-        mbar_wait(&bar_pfull[as], (g >> 1) & 1u);
-        const float* pbuf = s_p + as * (P_BYTES / 4);
+        const uint32_t ps = g % NP;
+        mbar_wait(&bar_pfull[ps], (g / NP) & 1u);
+        const float* pbuf = s_p + ps * (P_BYTES / 4);
         // ---- input plane z feeds output planes z+1 (kd 0), z (kd 1), z-1 (kd 2)
         if (col_ok) {
 #pragma unroll
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_head_kernel(const __grid_c
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_pempty[as]);              // this warp has read everything it needs from the buffer
+        if (lane == 0) mbar_arrive(&bar_pempty[ps]);              // this warp has read everything it needs from the buffer
         // ---- output plane z-1 is complete (and plane D-1 after the last input plane)
 #pragma unroll
         for (int fin = 0; fin < 2; ++fin) {
