@@ -53,5 +53,5 @@ def test_tiled_world2_matches_untiled():
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     out = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
     print(out)
-    assert out["world"] == 2 and out["exchanges_per_pass"] > 50
+    assert out["world"] == 2 and out["exchanges_per_pass"] > 20          # 35 with the overlap-recompute encoder (3-D path + ANM only)
     assert out["disp_max_err"] < 0.25 and out["disp_mean_err"] < 0.03 and out["normal_mean_err"] < 0.012   # as in the world-1 test
