@@ -576,6 +576,19 @@ class ANM(nn.Module):
             self._plan = p
         return self._plan
 
+    def _kinv(self, K: torch.Tensor) -> torch.Tensor:
+        """inverse of the quarter-resolution intrinsics (normal_module.py:100-103).  torch.inverse synchronises the host (its error
+        check reads back a status); linalg.inv_ex(check_errors=False) is the same factorisation without the read-back, and the result
+        is cached per intrinsics tensor (storage, version, shape): steady-state inference is sync-free and CUDA-graph capturable."""
+        key = (K.data_ptr(), K._version, tuple(K.shape), K.device)
+        c = self.__dict__.get("_kinv_cache")
+        if c is None or c[0] != key:
+            kq = K.float().clone()
+            kq[:, :2, :] = kq[:, :2, :] / 4.0
+            c = (key, torch.linalg.inv_ex(kq, check_errors=False)[0].contiguous())
+            self.__dict__["_kinv_cache"] = c
+        return c[1]
+
     def forward(self, costs: Sequence[torch.Tensor], disp_maps: Sequence[torch.Tensor], batch: dict):
         """costs: [out3] as [B,D,H4,W4,C] bf16; disp_maps: [disparity [B,H,W] fp32] -> ([normal [B,3,H,W]], offsets, offsets)."""
         if self.training:                      # forward + backward through the autograd Functions of train_anm.py
@@ -586,9 +599,7 @@ class ANM(nn.Module):
         normals, off1s, off2s = [], [], []
         for out3, disp in zip(costs, disp_maps):
             b = out3.shape[0]
-            kq = batch["K"].float().clone()
-            kq[:, :2, :] = kq[:, :2, :] / 4.0
-            kinv = torch.inverse(kq).contiguous()
+            kinv = self._kinv(batch["K"])
             idx, coord, minmax = ops.anm_select(disp.contiguous(), kinv, batch["abvalue"].float().contiguous(), self.levels, self.k)
             fv = ops.anm_gather(out3, idx, coord, minmax, 64)                          # [B,K,H4,W4,64]
             if self.use_deform:
