@@ -43,9 +43,27 @@ class _DenseGrad(torch.autograd.Function):
         return g.contiguous(memory_format=torch.channels_last) if ctx.cl else g.contiguous()
 
 
+class EncoderBatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d of the 2-D encoders (same parameters / buffers / state-dict keys).  In TRAINING on bf16 channels-last CUDA
+    activations (the autocast encoder) the batch statistics, the normalisation and the backward run on the repository's own
+    bandwidth-bound kernels (dpf_channel_stats, dpf_affine_act, dpf_bn_bwd_reduce / _apply -- the train-mode BatchNorm of the 3-D
+    path, which is shape-agnostic over [pixels, C]); ATen's channels-last BatchNorm kernels took 22 % of a StereoDPNet training
+    step at C = 32..128.  Everything else (eval, fp32, NCHW) is nn.BatchNorm2d."""
+
+    fused_training = True
+
+    def forward(self, x):
+        if (self.training and self.fused_training and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and self.affine
+                and self.track_running_stats and x.shape[1] % 8 == 0 and x.shape[1] <= 256 and 256 % (x.shape[1] // 8) == 0
+                and x.is_contiguous(memory_format=torch.channels_last)):
+            from .train_ops import BN2dTrainFn
+            return BN2dTrainFn.apply(x, self.weight, self.bias, self)
+        return super().forward(x)
+
+
 def _cb2(cin, cout, k, stride, pad, dil):
     """conv + BN pair with the reference's padding rule (src/module/asm/basics.py:17-22)."""
-    return nn.Sequential(nn.Conv2d(cin, cout, k, stride, dil if dil > 1 else pad, dil, bias=False), nn.BatchNorm2d(cout))
+    return nn.Sequential(nn.Conv2d(cin, cout, k, stride, dil if dil > 1 else pad, dil, bias=False), EncoderBatchNorm2d(cout))
 
 
 def _cb3(cin, cout, stride=1):
@@ -70,7 +88,7 @@ class _SepConv(nn.Module):
         super().__init__()
         self.depthwise = nn.Conv2d(c, c, 3, padding=1, groups=c, bias=False)
         self.pointwise = nn.Conv2d(c, c, 1, bias=False)
-        self.bn = nn.BatchNorm2d(c)
+        self.bn = EncoderBatchNorm2d(c)
         self.prelu = nn.PReLU(init=0.05)
 
     def forward(self, x):
@@ -170,7 +188,7 @@ class PSMFeatureExtraction(nn.Module):
     def _stack(self, planes, blocks, stride, pad, dil):
         down = None
         if stride != 1 or self._in != planes:
-            down = nn.Sequential(nn.Conv2d(self._in, planes, 1, stride, bias=False), nn.BatchNorm2d(planes))
+            down = nn.Sequential(nn.Conv2d(self._in, planes, 1, stride, bias=False), EncoderBatchNorm2d(planes))
         mods = [_ResBlock(self._in, planes, stride, down, pad, dil)]
         self._in = planes
         mods += [_ResBlock(planes, planes, 1, None, pad, dil) for _ in range(1, blocks)]

@@ -84,8 +84,8 @@ def _teacher(bn, y):
     return t.clone()
 
 
-def _affine_act(z, scale, bias, res, slope):
-    y = torch.empty_like(z)
+def _affine_act(z, scale, bias, res, slope, out=None):
+    y = torch.empty_like(z) if out is None else out
     _lib.check(ops.lib().dpf_affine_act(ops._p(z), ops._p(scale), ops._p(bias), ops._p(res), ops._p(y), _npix(z), z.shape[-1],
                                         float(slope), ops._stream()), "dpf_affine_act")
     return y
@@ -165,6 +165,38 @@ class ConvBNAct(Function):
         dx = _dgrad(dz, weight, cfg.kind) if ctx.needs_input_grad[0] else None
         dw = _wgrad(x, dz, weight, cfg.kind)
         return dx, dw, dgamma, dbeta, dres, None
+
+
+class BN2dTrainFn(Function):
+    """Train-mode BatchNorm2d on an NCHW-shaped, channels-last bf16 activation (modules.EncoderBatchNorm2d): batch statistics,
+    normalisation and backward on the kernels of the 3-D path; running statistics updated as nn.BatchNorm2d does (momentum,
+    unbiased variance).  With SyncBN switched on (set_sync_bn) the partial sums are all-reduced like those of the 3-D layers."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn):
+        xh = x.permute(0, 2, 3, 1)                                   # [N,H,W,C] view of the channels-last memory
+        assert xh.is_contiguous()
+        mean, var, n = batch_stats(xh)
+        inv_std = torch.rsqrt(var + bn.eps)
+        a = (gamma.float() * inv_std).contiguous()
+        b = (beta.float() - mean * a).contiguous()
+        y = torch.empty_like(x)                                      # NCHW-shaped, channels-last: a fresh tensor, not a view (the
+        _affine_act(xh, a, b, None, 1.0, out=y.permute(0, 2, 3, 1))  # in-place ReLU / PReLU that follows needs a non-view output)
+        with torch.no_grad():
+            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
+            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+            bn.running_var.mul_(1 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
+            bn.num_batches_tracked += 1
+        ctx.save_for_backward(x, a, mean, inv_std)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, a, mean, inv_std = ctx.saved_tensors
+        xh = x.permute(0, 2, 3, 1)
+        dyh = dy.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+        dz, _, dgamma, dbeta = _bn_bwd(dyh, None, xh, a, mean, inv_std, False, False)
+        return dz.permute(0, 3, 1, 2), dgamma, dbeta, None
 
 
 class HeadConv(Function):

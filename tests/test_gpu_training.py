@@ -127,3 +127,31 @@ def test_psmnet_training_step_matches_reference():
         r = ((got - want).norm() / want.norm()).item()
         print(f"   grad {key}: cosine {cos:.4f}, relative L2 error {r:.4f}")
         assert cos > floor[key] and r < 0.35
+
+
+@pytest.mark.parametrize("c,hw", [(32, (37, 50)), (64, (20, 28)), (128, (9, 13))])
+def test_encoder_batchnorm_train_matches_torch(c, hw):
+    """modules.EncoderBatchNorm2d (train mode, bf16 channels-last: the repository's BatchNorm kernels) == nn.BatchNorm2d in fp32 on
+    the same bf16 input: output, running statistics, input / weight / bias gradients."""
+    from dualpixelface_b200.modules import EncoderBatchNorm2d
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = (torch.randn(3, c, *hw, device="cuda", generator=g) * 1.5 + 0.3).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(3, c, *hw, device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    ours, ref = EncoderBatchNorm2d(c).cuda().train(), torch.nn.BatchNorm2d(c).cuda().train()
+    with torch.no_grad():
+        for m in (ours, ref):
+            m.weight.copy_(torch.linspace(0.5, 1.5, c)); m.bias.copy_(torch.linspace(-0.2, 0.2, c))
+    xo = x.clone().requires_grad_(True)
+    yo = ours(xo)
+    assert yo.dtype == torch.bfloat16 and yo.is_contiguous(memory_format=torch.channels_last)
+    yo.backward(dy)
+    xr = x.float().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(dy.float())
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-9))
+    print(f"BN2d C={c}: y {rel(yo, yr):.2e}, dx {rel(xo.grad, xr.grad):.2e}, dgamma {rel(ours.weight.grad, ref.weight.grad):.2e}, "
+          f"dbeta {rel(ours.bias.grad, ref.bias.grad):.2e}, running var {rel(ours.running_var, ref.running_var):.2e}")
+    assert rel(yo, yr) < 5e-3 and rel(xo.grad, xr.grad) < 8e-3                       # bf16 rounding of y / dx
+    assert rel(ours.weight.grad, ref.weight.grad) < 2e-3 and rel(ours.bias.grad, ref.bias.grad) < 2e-3
+    assert rel(ours.running_mean, ref.running_mean) < 1e-4 and rel(ours.running_var, ref.running_var) < 1e-4
+    assert int(ours.num_batches_tracked) == 1
