@@ -311,6 +311,24 @@ def config5_block(dev, rank, world, steps):
                 out.update(ms_per_pair=round(t.item(), 3), mode=f"row tiles over {world} GPUs, per-layer halo exchange (NCCL p2p) in the 3-D path, "
                            "overlap-recompute encoder", rows_rank0=list(tm.t.tiles[0]), halo_bytes_sent_rank0=int(sent), exchanges_per_pair=int(nex),
                            d3d_halo_rows=tm._hd, d3d_reach_ok=bool(tm.check_reach()))
+                # the tiled forward is launch-bound (35 exchanges + ~500 kernels for a few ms of GPU work per rank): the same pass
+                # captured in a CUDA graph, NCCL halo exchanges included (tiled.TiledStereoDPNet.capture)
+                try:
+                    replay, _static, _sout = tm.capture(batch)
+                    replay(); replay()
+                    torch.cuda.synchronize()
+                    torch.distributed.barrier()
+                    e0.record()
+                    for _ in range(n):
+                        replay()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    tg = torch.tensor([e0.elapsed_time(e1) / n], device=dev, dtype=torch.float64)
+                    torch.distributed.all_reduce(tg, op=torch.distributed.ReduceOp.MAX)
+                    out["ms_per_pair_cuda_graph"] = round(tg.item(), 3)
+                    del replay, _static, _sout
+                except Exception as e:  # noqa: BLE001
+                    out["cuda_graph_error"] = f"{type(e).__name__}: {str(e)[:200]}"
         del model, batch
         torch.cuda.empty_cache()
         return out

@@ -66,25 +66,28 @@ __global__ void __launch_bounds__(kTX* kTY) regress_fwd_kernel(const float* __re
   const size_t plane = static_cast<size_t>(H4loc) * W4;
   float c[D];
   plane_values<D>(cost + static_cast<size_t>(b) * D * plane, plane, W4, ay, ax, c);
+  // The 4*D bins are linear interpolants of the D knots, so their maximum is a knot: the softmax shift m needs D compares, not
+  // 4*D (the softmax is shift-invariant; any m >= max keeps the exponentials in range).  Knots go to the log2 domain once
+  // (c <- (c - m) * log2 e), each bin is then one FFMA + one EX2, and the expectation uses sum_k k * e_k with immediate k.
+  float m = c[0];
+#pragma unroll
+  for (int d = 1; d < D; ++d) m = fmaxf(m, c[d]);
+#pragma unroll
+  for (int d = 0; d < D; ++d) c[d] = (c[d] - m) * 1.4426950408889634f;
   float v[4 * D];
-  float m = -INFINITY;
+  float se = 0.f, sek = 0.f;
 #pragma unroll
   for (int k = 0; k < 4 * D; ++k) {
     const float src = sd * static_cast<float>(k);
     const int d0 = static_cast<int>(src);
     const int d1 = d0 + ((d0 < D - 1) ? 1 : 0);
     const float l1 = src - static_cast<float>(d0);
-    v[k] = (1.0f - l1) * c[d0] + l1 * c[d1];
-    m = fmaxf(m, v[k]);
-  }
-  float se = 0.f, sed = 0.f;
-#pragma unroll
-  for (int k = 0; k < 4 * D; ++k) {
-    const float e = __expf(v[k] - m);
+    const float e = exp2f(fmaf(l1, c[d1] - c[d0], c[d0]));
     v[k] = e;
     se += e;
-    sed = fmaf(e, mindisp + step * static_cast<float>(k), sed);
+    sek = fmaf(e, static_cast<float>(k), sek);
   }
+  const float sed = fmaf(step, sek, mindisp * se);
   const float inv = 1.0f / se;
   disp[(static_cast<size_t>(b) * Hout + yl) * W + x] = sed * inv;
   if (prob != nullptr) {
