@@ -138,6 +138,7 @@ def test_encoder_batchnorm_train_matches_torch(c, hw):
     x = (torch.randn(3, c, *hw, device="cuda", generator=g) * 1.5 + 0.3).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     dy = torch.randn(3, c, *hw, device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     ours, ref = EncoderBatchNorm2d(c).cuda().train(), torch.nn.BatchNorm2d(c).cuda().train()
+    ours.min_pixels = 0                                   # the size threshold is a performance heuristic; test the kernels
     with torch.no_grad():
         for m in (ours, ref):
             m.weight.copy_(torch.linspace(0.5, 1.5, c)); m.bias.copy_(torch.linspace(-0.2, 0.2, c))
