@@ -63,8 +63,8 @@ struct Tap {
   signed char dd;        // input plane relative to the work item's base plane
   unsigned char cls;     // accumulator class (transposed: rh*2+rw; else 0)
   unsigned short aoff;   // start offset inside a slot chunk-plane, in 16-byte units
-  unsigned short widx;   // weight tile index
-  unsigned short pad;
+  unsigned short widx;   // weight tile index (first tap slot of a fused group)
+  unsigned short ncls;   // accumulator classes fed by ONE MMA (N = ncls * NPAD): transposed kind only, else 1
 };
 
 struct ConvKParams {
@@ -284,6 +284,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
           const uint32_t b0 = (wbase + tp.widx * C::W_TAP_BYTES) >> 4;
           const uint32_t acc0 = tmem_base + (as * C::NCLS + tp.cls) * C::NBLK * NPAD;
           if (leader && !(p.debug & 2)) {
+            if (GEO == GEO_T2 && C::NBLK == 1) {
+              // transposed kind: the taps of the (up to 4) parity classes that read the SAME input shift are one MMA with
+              // N = ncls * NPAD -- their accumulators are adjacent TMEM columns and their weight tiles one [Cin x N] operand --
+              // so the A window is read 15 instead of 27 times per pair of output planes
+              const uint32_t ng = tp.ncls * NPAD;
+              const uint32_t idg = umma_idesc_bf16_f32(128, static_cast<int>(ng));
+              const uint64_t bhi = umma_desc_nosw(0, ng * 16, 128);
+#pragma unroll
+              for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                const uint64_t bdesc = bhi | static_cast<uint64_t>(b0 + ks * 2 * ng);
+                const uint64_t adesc = adesc_hi | static_cast<uint64_t>(a0 + ks * 2 * (C::CH_STRIDE >> 4));
+                umma_bf16(acc0, adesc, bdesc, idg, true);
+              }
+            } else {
 #pragma unroll
             for (int ks = 0; ks < C::KSTEPS; ++ks) {
               // (shared-memory addresses >> 4 are < 2^14: the start-address field cannot overflow, no masking needed)
@@ -295,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const __grid_con
                   umma_bf16(acc0 + blk * NPAD, adesc, bdesc, idesc, true);
                 }
               }
+            }
             }
           }
         }
@@ -938,7 +953,7 @@ inline Tap mk_tap(int dd, int cls, int dh, int dw, int widx) {
   t.cls = static_cast<unsigned char>(cls);
   t.aoff = static_cast<unsigned short>((dh << 8) | dw);
   t.widx = static_cast<unsigned short>(widx);
-  t.pad = 0;
+  t.ncls = 1;
   return t;
 }
 
@@ -1011,17 +1026,25 @@ extern "C" int dpf_conv3d_fwd(const dpf_conv3d_args* a, void* stream) {
     const int ks[2][2] = {{1, -1}, {0, 2}};
     const int os[2][2] = {{0, 0}, {1, 0}};
     const int nk[2] = {1, 2};
-    for (int rd = 0; rd < 2; ++rd) {
-      int n = 0;
-      for (int id = 0; id < nk[rd]; ++id)
-        for (int rh = 0; rh < 2; ++rh)
-          for (int ih = 0; ih < nk[rh]; ++ih)
-            for (int rw = 0; rw < 2; ++rw)
-              for (int iw = 0; iw < nk[rw]; ++iw, ++n) {
-                const int kd = ks[rd][id], kh = ks[rh][ih], kw = ks[rw][iw];
-                kp.taps[rd][n] = mk_tap(os[rd][id], rh * 2 + rw, os[rh][ih], os[rw][iw], (kd * 3 + kh) * 3 + kw);
-              }
-      kp.ntaps[rd] = n;
+    // Fused groups: for every (output-plane parity rd, depth tap id) and every in-plane input shift (oh, ow), the parity classes
+    // (rh, rw) with rh in R(oh), rw in R(ow), R(0) = {0, 1}, R(1) = {1}, read the same A window; runs of ADJACENT classes
+    // (cls = 2 rh + rw) are one MMA.  Group order = weight-slot order of the packed tensor (dpf_conv3d_t2_weight_order below /
+    // ops.fuse_t2_weight): (0,0) -> classes 0..3; (0,1) -> {1}, {3}; (1,0) -> {2, 3}; (1,1) -> {3}.
+    {
+      int slot = 0;
+      for (int rd = 0; rd < 2; ++rd) {
+        int n = 0;
+        for (int id = 0; id < nk[rd]; ++id) {
+          const int runs[5][4] = {{0, 0, 0, 4}, {0, 1, 1, 1}, {0, 1, 3, 1}, {1, 0, 2, 2}, {1, 1, 3, 1}};   // oh, ow, first class, ncls
+          for (int r = 0; r < 5; ++r, ++n) {
+            Tap tp = mk_tap(os[rd][id], runs[r][2], runs[r][0], runs[r][1], slot);
+            tp.ncls = static_cast<unsigned short>(runs[r][3]);
+            kp.taps[rd][n] = tp;
+            slot += runs[r][3];
+          }
+        }
+        kp.ntaps[rd] = n;
+      }
     }
     kp.nw = 27;
     kp.Mh = a->H; kp.Mw = a->W; kp.items = kp.Do;

@@ -87,7 +87,7 @@ class TCConv3d:
             hi = min(cin, ln.x_coff + ln.cin)
             if hi > ln.x_coff:
                 wk[:, : hi - ln.x_coff] = w[ln.y_coff: ln.y_coff + ln.cout, ln.x_coff: hi].float()
-            self.packed.append(ops.pack_conv_weight(wk))
+            self.packed.append(ops.pack_conv_weight(wk, kind=kind))
 
     def out_shape(self, x: torch.Tensor) -> Tuple[int, ...]:
         b, d, h, w, _ = x.shape

@@ -89,11 +89,36 @@ def npad_for(cout: int) -> int:
     return 16 if cout <= 16 else (32 if cout <= 32 else 64)
 
 
-def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None, transposed: bool = False) -> torch.Tensor:
+# Transposed kind (KIND_T2 = 2): weight-slot order of the fused groups, as dpf_conv3d_fwd builds its tap table (conv3d_tc.cu):
+# out[2q + r] += in[q + o] * W[k] per dimension with r = 0 -> (k 1, o 0); r = 1 -> (k 0, o 1), (k 2, o 0).  For every (output-plane
+# parity rd, depth tap) and every in-plane input shift (oh, ow), runs of adjacent parity classes cls = 2 rh + rw share one MMA:
+_T2_DEPTH = ((0, 1), (1, 0), (1, 2))                          # (rd, kd) in issue order
+_T2_RUNS = ((0, 0, (0, 1, 2, 3)), (0, 1, (1,)), (0, 1, (3,)), (1, 0, (2, 3)), (1, 1, (3,)))     # (oh, ow, classes of the run)
+
+
+def _t2_k(r: int, o: int) -> int:
+    return 1 if r == 0 else (0 if o == 1 else 2)
+
+
+def fuse_t2_weight(wp: torch.Tensor) -> torch.Tensor:
+    """Plain packed weights [27][Cin/8][Npad][8] -> the transposed kind's fused-group layout (same size, same shape): 15 groups of
+    1, 2 or 4 tap matrices, each stored as ONE operand [Cin/8][ncls * Npad][8]."""
+    groups = []
+    for _rd, kd in _T2_DEPTH:
+        for oh, ow, classes in _T2_RUNS:
+            taps = [(kd * 3 + _t2_k(c >> 1, oh)) * 3 + _t2_k(c & 1, ow) for c in classes]
+            groups.append(torch.cat([wp[t] for t in taps], 1).reshape(-1))          # [Cin/8][ncls*Npad][8]
+    return torch.cat(groups).reshape(wp.shape).contiguous()
+
+
+def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None, transposed: bool = False, kind: Optional[int] = None) -> torch.Tensor:
     """nn.Conv3d weight [Cout,Cin,kd,kh,kw] (or ConvTranspose3d [Cin,Cout,...]) -> packed bf16 [taps][Cin/8][Npad][8].
 
     Tap order is (kd, kh, kw) row-major; output channels are zero-padded to Npad in {16,32,64}, input channels to cin_pad.
+    kind = KIND_T2: the fused-group layout the transposed kind of dpf_conv3d_fwd expects (fuse_t2_weight).
     """
+    if kind == KIND_T2:
+        return fuse_t2_weight(pack_conv_weight(w, cin_pad, transposed))
     if transposed:
         w = w.transpose(0, 1)
     cout, cin = w.shape[:2]

@@ -79,7 +79,9 @@ int dpf_channel_stats(const void* x, float* stats, float* ws, int B, long long P
  *       y = relu?( conv(x, w) * scale[c] + shift[c] + residual )
  *     kind: 0 = 3x3x3 stride 1 pad 1; 1 = 3x3x3 stride 2 pad 1; 2 = transposed 3x3x3 stride 2 pad 1 out_pad 1;
  *           3 = 1x3x3 (per-plane) pad (0,1,1); 4 = 1x1x1.
- *     x [B,D,H,W,Cin] bf16; w packed by dpf_conv3d_weight_elems / the host packer (layout [tap][Cin/8][Npad][8]);
+ *     x [B,D,H,W,Cin] bf16; w packed by dpf_conv3d_weight_elems / the host packer (layout [tap][Cin/8][Npad][8]; kind 2: the
+ *     same 27 tap matrices regrouped into 15 operands of 1, 2 or 4 taps [Cin/8][ncls*Npad][8] -- the taps of the output-parity
+ *     classes that read the same input shift are one MMA -- in the order of ops.fuse_t2_weight / the table in dpf_conv3d_fwd);
  *     y [B,Do,Ho,Wo,y_cstride] bf16 (or fp32 when y_f32), written at channel offset y_coff;
  *     residual has y's layout (bf16, or fp32 when y_f32).  scale/shift may be NULL (1 / 0).
  *     stats (optional, fp32 [2*Cout], NOT zeroed by the call) accumulates sum / sum-of-squares of the raw

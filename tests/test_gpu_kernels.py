@@ -113,7 +113,7 @@ def conv_case(ops, cin, cout, kind, shape, seed, with_affine=True, residual=Fals
         want = want + res.float()
     if relu:
         want = F.relu(want)
-    got = ops.conv3d(ndhwc(x).cuda(), ops.pack_conv_weight(wt.cuda()), kind, cout,
+    got = ops.conv3d(ndhwc(x).cuda(), ops.pack_conv_weight(wt.cuda(), kind=kind), kind, cout,
                      scale.cuda() if with_affine else None, shift.cuda() if with_affine else None,
                      ndhwc(res).cuda() if residual else None, relu, out_f32=out_f32)
     torch.cuda.synchronize()
