@@ -373,7 +373,9 @@ def run_reference(args):
         "impl": "reference", "metric": "StereoDPNet DP-pairs/sec", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "batch_per_gpu": B, "height": H, "width": W},
-        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "extrapolated: a 448x672 pair scaled by pixel count to 1120x1680-pair equivalents; the reference has no CPU "
+                                 "path of its own (its deformable conv is CUDA-only) and cannot be installed here, so the oracle port is timed"},
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
