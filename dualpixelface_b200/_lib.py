@@ -51,8 +51,8 @@ SIGNATURES = {
     "dpf_bias_act": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_float, c_void_p]),
     "dpf_anm_tail": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dpf_affine_act": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_void_p]),
-    "dpf_bn_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]),
-    "dpf_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]),
+    "dpf_bn_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_void_p]),
+    "dpf_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_void_p]),
     "dpf_asm_blend_bwd": (c_int, [c_void_p] * 7 + [c_int] * 10 + [c_void_p]),
     "dpf_asm_sample_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dpf_conv3d_wgrad": (c_int, [c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p]),

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const __nv_bfloat16* __
 // sums [2][C]: S1 = sum g, S2 = sum g*z.  grid (chunks), block 256 = (256/c8n) position lanes x c8n pieces.
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                                             const __nv_bfloat16* __restrict__ z, float* __restrict__ sums,
-                                                            long long npix, int C, int relu) {
+                                                            long long npix, int C, int relu, float slope) {
   extern __shared__ float red[];   // [2][C]
   const int c8n = C >> 3;
   const int piece = threadIdx.x % c8n, lanes = blockDim.x / c8n, pl = threadIdx.x / c8n;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
         float yy[8];
         unpack8(ld_nc_v4(y + off), yy);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) g[k] = yy[k] > 0.f ? g[k] : 0.f;
+        for (int k = 0; k < 8; ++k) g[k] = yy[k] > 0.f ? g[k] : slope * g[k];
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) { s1[k] += g[k]; s2[k] = fmaf(g[k], zz[k], s2[k]); }
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                                            const __nv_bfloat16* __restrict__ z, const float* __restrict__ coef,
                                                            __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ dres,
-                                                           long long npix, int C, int relu) {
+                                                           long long npix, int C, int relu, float slope) {
   const int c8n = C >> 3;
   const long long total = npix * c8n;
   for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < total;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
       float yy[8];
       unpack8(ld_nc_v4(y + q * 8), yy);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] = yy[k] > 0.f ? g[k] : 0.f;
+      for (int k = 0; k < 8; ++k) g[k] = yy[k] > 0.f ? g[k] : slope * g[k];
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -134,7 +134,7 @@ extern "C" int dpf_affine_act(const void* x, const float* scale, const float* bi
 }
 
 extern "C" int dpf_bn_bwd_reduce(const void* dy, const void* y, const void* z, float* sums, long long npix, int C, int relu,
-                                 void* stream) {
+                                 float slope, void* stream) {
   DPF_REQUIRE(dy && z && sums && (!relu || y), "dpf_bn_bwd_reduce: null pointer");
   DPF_REQUIRE(C >= 8 && C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0 && npix > 0, "dpf_bn_bwd_reduce: bad shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -144,16 +144,16 @@ extern "C" int dpf_bn_bwd_reduce(const void* dy, const void* y, const void* z, f
   const int chunks = static_cast<int>(std::min<long long>((npix + lanes * 8 - 1) / (lanes * 8), static_cast<long long>(dpf::sm_count()) * 8));
   bn_bwd_reduce_kernel<<<chunks, 256, 2 * C * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
                                                                    reinterpret_cast<const __nv_bfloat16*>(y),
-                                                                   reinterpret_cast<const __nv_bfloat16*>(z), sums, npix, C, relu);
+                                                                   reinterpret_cast<const __nv_bfloat16*>(z), sums, npix, C, relu, slope);
   return dpf::after_launch("dpf_bn_bwd_reduce");
 }
 
 extern "C" int dpf_bn_bwd_apply(const void* dy, const void* y, const void* z, const float* coef, void* dz, void* dres,
-                                long long npix, int C, int relu, void* stream) {
+                                long long npix, int C, int relu, float slope, void* stream) {
   DPF_REQUIRE(dy && z && coef && dz && (!relu || y), "dpf_bn_bwd_apply: null pointer");
   DPF_REQUIRE(C >= 8 && C % 8 == 0 && npix > 0, "dpf_bn_bwd_apply: bad shape");
   bn_bwd_apply_kernel<<<nblocks(npix * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(z),
-      coef, reinterpret_cast<__nv_bfloat16*>(dz), reinterpret_cast<__nv_bfloat16*>(dres), npix, C, relu);
+      coef, reinterpret_cast<__nv_bfloat16*>(dz), reinterpret_cast<__nv_bfloat16*>(dres), npix, C, relu, slope);
   return dpf::after_launch("dpf_bn_bwd_apply");
 }

@@ -10,7 +10,9 @@ entries, pinned by tests/golden/state_keys_stereonet.json).  What runs where, in
   BasicBlocks of the encoder / the refinement (3x3, dil 1..8)   dpf_conv2d_tc_fwd with y = LeakyReLU(BN(conv x)) + x fused
   5x5 stride-2 stem, the 4 -> 32 conv, bilinear resizes         cuDNN / ATen (adjacent 2-D ops with 3-4 input channels)
 
-Training of this model is not built (the LeakyReLU backward of the 3-D path is missing): forward in train mode raises.
+Training: the 3-D path (difference volume, the four convbn_3d + LeakyReLU layers, the head) runs forward AND backward on the same
+kernels through the autograd Functions of train_ops.py (CostVolumeFn, ConvBNAct with slope 0.2, HeadConv); the 2-D encoder and
+refinement and the 1/8-resolution soft-argmin (a [B,8,h,w] tensor) go through PyTorch autograd, as the encoders of the other models do.
 """
 from __future__ import annotations
 
@@ -35,6 +37,9 @@ class BasicBlock(nn.Module):
         self.conv2 = _cb2(c, c, 3, 1, 1, dilation)
         self.dilation = dilation
 
+    def forward(self, x):                        # training path (PyTorch autograd over cuDNN); eval runs _run_block
+        return x + self.conv1(x)
+
 
 class FeatureExtraction(nn.Module):
     """src/model/stereonet/modules.py:32-61."""
@@ -46,6 +51,13 @@ class FeatureExtraction(nn.Module):
         self.residual_blocks = nn.ModuleList([BasicBlock(32, 1) for _ in range(6)])
         self.conv_alone = nn.Conv2d(32, 32, 3, 1, 1)
 
+    def forward(self, x):                        # training path
+        for conv in self.downsample:
+            x = conv(x)
+        for blk in self.residual_blocks:
+            x = blk(x)
+        return self.conv_alone(x)
+
 
 class EdgeAwareRefinement(nn.Module):
     """src/model/stereonet/modules.py:64-96."""
@@ -55,6 +67,15 @@ class EdgeAwareRefinement(nn.Module):
         self.conv2d_feature = nn.Sequential(_cb2(cin, 32, 3, 1, 1, 1), nn.LeakyReLU(0.2, inplace=True))
         self.residual_astrous_blocks = nn.ModuleList([BasicBlock(32, d) for d in (1, 2, 4, 8, 1, 1)])
         self.conv2d_out = nn.Conv2d(32, 1, 3, 1, 1)
+
+    def forward(self, low_disparity, rgb):       # training path
+        up = F.interpolate(low_disparity.unsqueeze(1), size=rgb.shape[-2:], mode="bilinear", align_corners=False)
+        if rgb.shape[-1] / low_disparity.shape[-1] >= 1.5:
+            up = up * 8
+        x = self.conv2d_feature(torch.cat([up, rgb], 1))
+        for blk in self.residual_astrous_blocks:
+            x = blk(x)
+        return torch.relu((up + self.conv2d_out(x).float()).squeeze(1))
 
 
 def _pack_block(blk: BasicBlock):
@@ -141,13 +162,43 @@ class STEREONET(_StereoBase):
         res = ops.conv2d_tc(x, wp, 1, 1, None, b)[..., 0].float()       # [B,H,W]; channels 1..7 of the 16-byte piece are zeros
         return torch.relu(up.squeeze(1) + res)
 
+    def _forward_train(self, batch, ref_img, tgt_img):
+        from .train_ops import ConvBNAct, CostVolumeFn, HeadConv, LayerCfg
+        cl = torch.channels_last
+        if not self.__dict__.get("_enc_channels_last", False):
+            self.feature_extraction.to(memory_format=cl)
+            self.edge_aware_refinements.to(memory_format=cl)
+            self.__dict__["_enc_channels_last"] = True
+        to_cl = lambda t: t.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.encoder_autocast):      # one encoder call per view (:84-98)
+            ref_fea = self.feature_extraction(ref_img.float().contiguous(memory_format=cl))
+            tgt_fea = self.feature_extraction(tgt_img.float().contiguous(memory_format=cl))
+        x = CostVolumeFn.apply(to_cl(ref_fea), to_cl(tgt_fea), self.shifts, "diff", 0)
+        for seq in self.filter:
+            conv, bn = seq[0][0], seq[0][1]
+            x = ConvBNAct.apply(x, conv.weight, bn.weight, bn.bias, None, LayerCfg(KIND_3x3x3, True, bn, 0.2))
+        cost = HeadConv.apply(x, self.conv3d_alone.weight, None).squeeze(-1) + self.conv3d_alone.bias.float().view(1, 1, 1, 1)
+        prob = F.softmax(cost, dim=1)
+        bins = torch.arange(self.level, device=cost.device, dtype=torch.float32) * ((self.maxdisp - self.mindisp) / float(self.level)) + self.mindisp
+        disp = (prob * bins.view(1, -1, 1, 1)).sum(1)
+        right = batch["right"].float()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.encoder_autocast):
+            refined = self.edge_aware_refinements[0](disp, right.contiguous(memory_format=cl))
+        coarse = F.interpolate((disp * (right.shape[-1] / disp.shape[-1])).unsqueeze(1), size=right.shape[-2:], mode="bilinear",
+                               align_corners=False).squeeze(1)
+        results = {"pred_depth": torch.stack([coarse, refined.float()], 1), "prob_depth": prob.unsqueeze(1), "pred_normal": None,
+                   "ref_feature": ref_fea.detach().amax(1).float()}
+        if "disp" in batch:
+            results.update(self.loss_model.forward(results, batch))
+        return results
+
     def forward(self, batch):
         if not batch["left"].is_cuda:
             raise RuntimeError("the sm_100a hot path needs CUDA tensors; there is no CPU implementation")
-        if self.training:
-            raise NotImplementedError("STEREONET: the training path (LeakyReLU backward on the 3-D engine) is not built; eval only")
         self.check_input_size(*batch["left"].shape[-2:])
         ref_img, tgt_img = self._select_views(batch)
+        if self.training:
+            return self._forward_train(batch, ref_img, tgt_img)
         p = self._build()
         b = ref_img.shape[0]
         self._mark("start")

@@ -83,7 +83,7 @@ class AsmBlendFn(Function):
         dbeta = torch.zeros(c, device=samples.device, dtype=torch.float32)
         sums = torch.empty(2 * c, device=samples.device, dtype=torch.float32)
         for i in range(b):
-            _lib.check(ops.lib().dpf_bn_bwd_reduce(ops._p(dlhat[i]), None, ops._p(logits[i]), ops._p(sums), n, c, 0, ops._stream()),
+            _lib.check(ops.lib().dpf_bn_bwd_reduce(ops._p(dlhat[i]), None, ops._p(logits[i]), ops._p(sums), n, c, 0, 0.0, ops._stream()),
                        "dpf_bn_bwd_reduce")
             s1, s2 = sums[:c], sums[c:]
             centred = s2 - mean[i] * s1
@@ -91,7 +91,7 @@ class AsmBlendFn(Function):
             dbeta += s1
             coef = torch.cat([a[i], s1 / n, inv_std[i] * inv_std[i] * centred / n, mean[i]]).contiguous()
             _lib.check(ops.lib().dpf_bn_bwd_apply(ops._p(dlhat[i]), None, ops._p(logits[i]), ops._p(coef), ops._p(dlogits[i]), None, n, c,
-                                                  0, ops._stream()), "dpf_bn_bwd_apply")
+                                                  0, 0.0, ops._stream()), "dpf_bn_bwd_apply")
         return dsamples, dlogits, dgamma, dbeta, None
 
 

@@ -91,10 +91,10 @@ def _affine_act(z, scale, bias, res, slope, out=None):
     return y
 
 
-def _bn_bwd(dy, y, z, a, mean, inv_std, relu, want_dres):
+def _bn_bwd(dy, y, z, a, mean, inv_std, relu, want_dres, slope=0.0):
     c, n = z.shape[-1], _npix(z)
     sums = torch.empty(2 * c, device=z.device, dtype=torch.float32)
-    _lib.check(ops.lib().dpf_bn_bwd_reduce(ops._p(dy), ops._p(y), ops._p(z), ops._p(sums), n, c, int(relu), ops._stream()),
+    _lib.check(ops.lib().dpf_bn_bwd_reduce(ops._p(dy), ops._p(y), ops._p(z), ops._p(sums), n, c, int(relu), float(slope), ops._stream()),
                "dpf_bn_bwd_reduce")
     # SyncBN: the mean-gradient terms of dz are sums over the GLOBAL batch; dgamma / dbeta stay LOCAL sums (the gradient
     # all-reduce averages them like every other parameter gradient -- the convention of torch.nn.SyncBatchNorm)
@@ -107,7 +107,7 @@ def _bn_bwd(dy, y, z, a, mean, inv_std, relu, want_dres):
     dz = torch.empty_like(z)
     dres = torch.empty_like(z) if want_dres else None
     _lib.check(ops.lib().dpf_bn_bwd_apply(ops._p(dy), ops._p(y), ops._p(z), ops._p(coef), ops._p(dz), ops._p(dres), n, c, int(relu),
-                                          ops._stream()), "dpf_bn_bwd_apply")
+                                          float(slope), ops._stream()), "dpf_bn_bwd_apply")
     return dz, dres, dgamma, dbeta
 
 
@@ -132,6 +132,7 @@ class LayerCfg:
     kind: int
     relu: bool
     bn: Optional[torch.nn.BatchNorm3d]      # running statistics are updated in place (momentum, unbiased variance)
+    slope: float = 0.0                      # negative-side slope of the activation when relu (0 = ReLU; StereoNet's filter: 0.2)
 
 
 class ConvBNAct(Function):
@@ -145,7 +146,7 @@ class ConvBNAct(Function):
         inv_std = torch.rsqrt(var + eps)
         a = (gamma.float() * inv_std).contiguous()
         b = (beta.float() - mean * a).contiguous()
-        y = _teacher(cfg.bn, _affine_act(z, a, b, residual, 0.0 if cfg.relu else 1.0))
+        y = _teacher(cfg.bn, _affine_act(z, a, b, residual, cfg.slope if cfg.relu else 1.0))
         if cfg.bn is not None and cfg.bn.track_running_stats:
             m = cfg.bn.momentum
             cfg.bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
@@ -161,7 +162,7 @@ class ConvBNAct(Function):
         x, weight, z, y, a, mean, inv_std = ctx.saved_tensors
         cfg = ctx.cfg
         dy = dy.to(torch.bfloat16).contiguous()
-        dz, dres, dgamma, dbeta = _bn_bwd(dy, y, z, a, mean, inv_std, cfg.relu, ctx.has_res)
+        dz, dres, dgamma, dbeta = _bn_bwd(dy, y, z, a, mean, inv_std, cfg.relu, ctx.has_res, cfg.slope)
         dx = _dgrad(dz, weight, cfg.kind) if ctx.needs_input_grad[0] else None
         dw = _wgrad(x, dz, weight, cfg.kind)
         return dx, dw, dgamma, dbeta, dres, None

@@ -270,14 +270,16 @@ int dpf_anm_tail_tile(const void* x, float* out, int B, int K, int H4loc, int W4
  * (8) Training-mode BatchNorm3d around the convolution (batch statistics; convbn_3d of src/module/asm/basics.py:32-36).
  *     With z the raw conv output [npix, C] bf16 and statistics from dpf_channel_stats:
  *       dpf_affine_act   : y = act(z*scale[c] + bias[c] + res)                       (forward normalise + residual + ReLU)
- *       dpf_bn_bwd_reduce: sums[0:C] = sum g, sums[C:2C] = sum g*z, g = dy*[y>0] (relu) or dy   (zeroes sums itself)
+ *       dpf_bn_bwd_reduce: sums[0:C] = sum g, sums[C:2C] = sum g*z, g = dy * (y > 0 ? 1 : slope) (relu; slope 0 = ReLU,
+ *                          0.2 = the LeakyReLU of StereoNet's 3-D filter) or dy                  (zeroes sums itself)
  *       dpf_bn_bwd_apply : dz = A*(g - K1 - (z - MU)*K2) with coef = [A | K1 | K2 | MU] (fp32 [4C]); dres = g if non-NULL
  * ------------------------------------------------------------------------------------------------- */
 int dpf_affine_act(const void* x, const float* scale, const float* bias, const void* res, void* y, long long npix, int C,
                    float slope, void* stream);
-int dpf_bn_bwd_reduce(const void* dy, const void* y, const void* z, float* sums, long long npix, int C, int relu, void* stream);
+int dpf_bn_bwd_reduce(const void* dy, const void* y, const void* z, float* sums, long long npix, int C, int relu, float slope,
+                      void* stream);
 int dpf_bn_bwd_apply(const void* dy, const void* y, const void* z, const float* coef, void* dz, void* dres, long long npix,
-                     int C, int relu, void* stream);
+                     int C, int relu, float slope, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * (9) Backward of the ASM volume pieces (autograd of src/module/asm/asm.py:87-127,160-171 in the reference).
