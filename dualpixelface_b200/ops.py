@@ -488,3 +488,26 @@ def conv3d_head(x: torch.Tensor, w_packed: torch.Tensor, residual: Optional[torc
     check(lib().dpf_conv3d_head_fwd(_p(x), _p(w_packed), _p(out), _p(residual), float(shift), b, d, h, w, cx, _stream()), "dpf_conv3d_head_fwd")
     _timing_end(tm, "conv3d_head 32->1", float(b * d * h * w * (32 * 2 + 4 + (4 if residual is not None else 0))), "byte")
     return out
+
+
+def pack_stem_weight(w: torch.Tensor) -> torch.Tensor:
+    """[32, Cin <= 8, 3, 3] (BatchNorm scale already folded in) -> bf16 [80][32], k = (kh*3 + kw)*8 + ci, zero rows elsewhere."""
+    cout, cin, kh, kw = w.shape
+    assert cout == 32 and cin <= 8 and (kh, kw) == (3, 3), w.shape
+    buf = torch.zeros(10, 8, 32, device=w.device, dtype=torch.float32)
+    buf[:9, :cin] = w.detach().float().permute(2, 3, 1, 0).reshape(9, cin, 32)
+    return buf.reshape(80, 32).to(torch.bfloat16).contiguous()
+
+
+def stem_conv(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True) -> torch.Tensor:
+    """Encoder stem (dpf_stem_conv_fwd): x [N,H,W,8] bf16 channels-last -> [N,ceil(H/2),ceil(W/2),32] bf16, 3x3 stride 2 pad 1 + bias + ReLU."""
+    _req(x, torch.bfloat16, "x"); _req(w_packed, torch.bfloat16, "w_packed")
+    n, h, w, c = x.shape
+    assert c == 8 and tuple(w_packed.shape) == (80, 32)
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+    y = torch.empty(n, (h + 1) // 2, (w + 1) // 2, 32, device=x.device, dtype=torch.bfloat16)
+    tm = _timing_begin()
+    check(lib().dpf_stem_conv_fwd(_p(x), _p(w_packed), _p(bias), _p(y), n, h, w, int(relu), _stream()), "dpf_stem_conv_fwd")
+    _timing_end(tm, "stem_conv 3->32 s2", float(x.numel() * 2 + y.numel() * 2), "byte")
+    return y

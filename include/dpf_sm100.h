@@ -238,6 +238,14 @@ int dpf_conv3d_s2_fwd(const void* x, const void* w, void* y, const float* scale,
 int dpf_conv3d_head_fwd(const void* x, const void* w, float* y, const float* residual, float shift, int B, int D, int H, int W,
                         int x_cstride, void* stream);
 
+/* Encoder stem: 3x3 / stride 2 / pad 1 convolution from an 8-channel (3 real + zero padding) channels-last bf16 image to 32
+ * channels + bias + ReLU: `convbn(input_channel, 32, 3, 2, 1, 1)` + ReLU with the BatchNorm folded, the first layer of both
+ * encoders (src/model/stereodpnet/modules.py:66-68, src/model/psmnet/modules.py:72-74).  Bandwidth-bound (K = 27): warp-level
+ * mma.sync on a shared-memory window, coalesced 64-byte pixel rows out (stem_conv.cu).
+ * x [N,H,W,8] bf16; w [80][32] bf16 row-major with k = (kh*3 + kw)*8 + ci (rows 72..79 and ci >= Cin are zero);
+ * bias fp32 [32] or NULL; y [N,ceil(H/2),ceil(W/2),32] bf16. */
+int dpf_stem_conv_fwd(const void* x, const void* w, const float* bias, void* y, int N, int H, int W, int relu, void* stream);
+
 /* 2-D 3x3 convolution, stride 1, ANY dilation (pad = dil), Cin in {32, 64, 96}, Cout <= 96 in ONE launch, on a dedicated tcgen05
  * implicit-GEMM kernel (conv2d_tc.cu: dilation by residue-class sub-images, input channels consumed in 32 / 48-channel windows
  * that accumulate in TMEM, N = Cout).  Replaces the six bias-free Conv2d + LeakyReLU(0.1) `convtext` layers of ANM

@@ -443,3 +443,23 @@ def test_conv3d_head_vs_torch(shape):
     got2 = layer(x, shift=torch.tensor([0.25], device="cuda"), residual=res, out_f32=True)
     assert (got2 - (want + 0.25 + res)).abs().max().item() < 2e-4 * max(1.0, want.abs().max().item())
     assert torch.equal(layer(x, out_f32=True), got)                       # deterministic
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 96), (1, 37, 131), (3, 16, 16)])
+def test_stem_conv_vs_torch(shape):
+    """dpf_stem_conv_fwd (3x3 stride 2 pad 1, 8-channel padded input, bias + ReLU) == F.conv2d in fp32 on the same bf16 operands,
+    incl. odd sizes and tiles that cross the image border."""
+    import torch.nn.functional as F
+    from dualpixelface_b200 import ops
+    n, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.zeros(n, h, w, 8, device="cuda", dtype=torch.bfloat16)
+    x[..., :3] = torch.randn(n, h, w, 3, device="cuda", generator=g).to(torch.bfloat16)
+    wt = (torch.randn(32, 3, 3, 3, device="cuda", generator=g) * 0.2).to(torch.bfloat16).float()
+    bias = torch.randn(32, device="cuda", generator=g) * 0.1
+    got = ops.stem_conv(x, ops.pack_stem_weight(wt), bias, relu=True)
+    want = F.relu(F.conv2d(x[..., :3].float().permute(0, 3, 1, 2), wt, bias, stride=2, padding=1)).permute(0, 2, 3, 1)
+    assert got.shape == want.shape
+    err = (got.float() - want).abs().max().item()
+    print(f"stem {shape}: max abs err {err:.2e} (output max {want.max():.2f})")
+    assert err < 8e-3 * max(1.0, want.max().item())              # bf16 rounding of the output
