@@ -63,7 +63,8 @@ if __name__ == "__main__":
     caps = {"dcn3d_kernel<64>": "dcn3d", "costvol_fwd": "costvol", "regress_fwd": "regress", "conv3d_s2 32->64": "conv_s2",
             "conv3d kind0 64->32": "conv_kdfused_64x32", "conv3d kind0 32->32": "conv_kdfused_32x32", "conv2d_tc 64->96 d1": "conv2d",
             "conv3d_head 32->1": "head", "conv3d kind2 64->32": "conv_t2"}
-    tr = {}
+    tr = json.loads((OUT / "r02_traffic.json").read_text()) if (OUT / "r02_traffic.json").is_file() else {}   # keep captures of earlier calls
+    caps["stem_conv 3->32 s2"] = "stem"
     for key, name in caps.items():
         rep = Path(f"gpurun_out/{tag}_{name}.ncu-rep")
         if not rep.is_file():
