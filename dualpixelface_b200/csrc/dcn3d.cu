@@ -34,7 +34,11 @@ constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kProdWarps = 16;
 constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;   // 672
-constexpr int kVoxPerPass = kProdWarps * 32 / 4;              // 4 threads (32 bytes = two channel chunks each) per voxel
+#ifndef DPF_DCN_GROUPS
+#define DPF_DCN_GROUPS 2
+#endif
+constexpr int kGroups = DPF_DCN_GROUPS;                       // producer groups: group i gathers the taps t = i (mod kGroups)
+static_assert(kGroups == 1 || kGroups == 2, "one or two producer groups (every group needs a pipeline stage of its own in flight)");
 constexpr int kNOut = 64;
 #ifndef DPF_DCN_BLOCKS
 #define DPF_DCN_BLOCKS 1
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&bar_full[i], kProdWarps + 1);       // gather warps + the weight-copy issuer (expect_tx)
+      mbar_init(&bar_full[i], kProdWarps / (STAGED ? 1 : kGroups) + 1);   // the gather warps of one group + the weight-copy issuer (expect_tx)
       mbar_init(&bar_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -190,9 +194,17 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
 
   if (warp > kMmaWarp) {
     // ======================= producers: trilinear gather -> bf16 A tile; weight tile by TMA ==================
-    const int ptid = threadIdx.x - (kMmaWarp + 1) * 32;      // 0..511
+    // Producer groups: the 16 gather warps are split into NG groups; group i produces the taps t = i (mod NG) of every unit, each
+    // of its threads covering PASSES = NG voxel rows per tap.  A stage then needs only the warps of ONE group (the per-tap coupling
+    // of all 16 warps is gone: while one group waits for its gathered lines the other one blends), and the two voxel rows of a
+    // thread are independent gathers the compiler can overlap.
+    constexpr int NG = STAGED ? 1 : kGroups;
+    constexpr int kVoxPerPass = kProdWarps * 32 / 4 / NG;    // 4 threads (32 bytes = two channel chunks each) per voxel
+    const int ptid_all = threadIdx.x - (kMmaWarp + 1) * 32;  // 0..511
+    const int grp = ptid_all / (kProdWarps * 32 / NG);
+    const int ptid = ptid_all - grp * (kProdWarps * 32 / NG); // thread index inside the group
     const int cq = ptid & 3;                                  // which pair of 16-byte channel chunks
-    const int vsub = ptid >> 2;                              // 0..127
+    const int vsub = ptid >> 2;
     // 4 lanes per voxel, 32 bytes (two 16-byte channel chunks) each: one LDG.256 per corner per lane, a voxel's 128-byte
     // line is touched exactly once per corner, and the per-(voxel,tap) coordinate / weight arithmetic is replicated
     // 4x instead of 8x.  All addresses are 32-bit byte offsets from the (uniform) tensor base.
@@ -203,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
     const bool lane_live = (2 * cq) < C::NCH;
     const char* xbytes = reinterpret_cast<const char*>(p.x);
     const uint32_t lane_off = (lane_live ? cq : 0) * 32u;
-    uint32_t g = 0;
+    uint32_t gbase = 0;
     if (STAGED && unit_lo < unit_hi) {                       // both halves of the first unit
       stage_offsets<kOffPiecesA, 0, kOffPitchA>(p, unit_lo, ptid, s_offA);
       stage_offsets<kOffPiecesB, 3 * kSplitTap, kOffPitchB>(p, unit_lo, ptid, s_offB);
@@ -246,17 +258,19 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
             ob4[ps] = reinterpret_cast<const float4*>(obase[ps]) + min(cq, 2);
             oblk[ps] = __ldg(ob4[ps]);
           } else {
-            onext[ps][0] = __ldg(obase[ps] + 0); onext[ps][1] = __ldg(obase[ps] + 1); onext[ps][2] = __ldg(obase[ps] + 2);
+            onext[ps][0] = __ldg(obase[ps] + 3 * grp + 0); onext[ps][1] = __ldg(obase[ps] + 3 * grp + 1);
+            onext[ps][2] = __ldg(obase[ps] + 3 * grp + 2);
           }
         }
       }
-      for (int tap = 0; tap < kTaps; ++tap, ++g) {
+      for (int tap = grp; tap < kTaps; tap += NG) {
+        const uint32_t g = gbase + tap;
         const int stage = g % kStages;
         const uint32_t ph = (g / kStages) & 1u;
         float ocur[PASSES][3];
         if (VECOFF) {
           const int j = tap & 3;
-          if (j == 0 && tap + 4 < kTaps) {                             // next block (taps tap+4 .. tap+7) while this one is used
+          if (j == grp && (tap - j) + 4 < kTaps) {                     // this group's first tap of a 4-tap block: request the next block
 #pragma unroll
             for (int ps = 0; ps < PASSES; ++ps) onxt[ps] = __ldg(ob4[ps] + 3 * ((tap >> 2) + 1));
           }
@@ -273,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
             }
           }
 #undef DPF_OFF_PICK
-          if (j == 3) {
+          if (j == 4 - NG + grp) {                                     // this group's last tap of the block
 #pragma unroll
             for (int ps = 0; ps < PASSES; ++ps) oblk[ps] = onxt[ps];
           }
@@ -295,8 +309,8 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
 #pragma unroll
           for (int ps = 0; ps < PASSES; ++ps) {
             ocur[ps][0] = onext[ps][0]; ocur[ps][1] = onext[ps][1]; ocur[ps][2] = onext[ps][2];
-            if (tap + 1 < kTaps) {
-              const float* on = obase[ps] + (tap + 1) * 3;
+            if (tap + NG < kTaps) {
+              const float* on = obase[ps] + (tap + NG) * 3;
               onext[ps][0] = __ldg(on + 0); onext[ps][1] = __ldg(on + 1); onext[ps][2] = __ldg(on + 2);
             }
           }
@@ -400,6 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn3d_kernel(const __grid_constan
         prod_barrier();
         stage_offsets<kOffPiecesB, 3 * kSplitTap, kOffPitchB>(p, unit + 1, ptid, s_offB);
       }
+      gbase += kTaps;
     }
   } else if (warp == kMmaWarp) {
     // ======================================= MMA issuer =====================================================
