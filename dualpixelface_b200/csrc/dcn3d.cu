@@ -50,6 +50,7 @@ constexpr int kUnitVox = 128 * kBlocks;
 #define DPF_DCN_STAGES 3
 #endif
 constexpr int kStages = DPF_DCN_STAGES;
+static_assert(kStages >= kGroups + 1, "every producer group needs a stage of its own in flight next to the one the MMA reads");
 constexpr int kTaps = 27;
 // staged offsets: half A = taps 0..11 (36 floats per voxel), half B = taps 12..26 (45 floats, copied as 48 and padded to 52)
 constexpr int kSplitTap = 12;
