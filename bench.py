@@ -295,9 +295,17 @@ def config5_block(dev, rank, world, steps):
                 tm = TiledStereoDPNet(model, h, rank, world)
                 tm(batch); tm(batch)
                 tm.t.bytes_exchanged = tm.t.exchanges = 0
+                tm.t.log = []
                 tm(batch)
                 torch.cuda.synchronize()
                 sent, nex = tm.t.bytes_exchanged, tm.t.exchanges
+                by_layer = {}                                  # halo traffic of rank 0 per exchanged tensor class
+                for shape, dt, rows, nbytes in tm.t.log:
+                    k = f"{'x'.join(map(str, shape))} {dt}, rows {rows[0]}+{rows[1]}"
+                    e = by_layer.setdefault(k, [0, 0])
+                    e[0] += 1
+                    e[1] += nbytes
+                tm.t.log = None
                 torch.distributed.barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 n = max(steps, 3)
@@ -310,7 +318,8 @@ def config5_block(dev, rank, world, steps):
                 torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
                 out.update(ms_per_pair=round(t.item(), 3), mode=f"row tiles over {world} GPUs, per-layer halo exchange (NCCL p2p) in the 3-D path, "
                            "overlap-recompute encoder", rows_rank0=list(tm.t.tiles[0]), halo_bytes_sent_rank0=int(sent), exchanges_per_pair=int(nex),
-                           d3d_halo_rows=tm._hd, d3d_reach_ok=bool(tm.check_reach()))
+                           d3d_halo_rows=tm._hd, d3d_reach_ok=bool(tm.check_reach()),
+                           halo_by_tensor_rank0={k: {"exchanges": v[0], "bytes_sent": v[1]} for k, v in by_layer.items()})
                 # the tiled forward is launch-bound (35 exchanges + ~500 kernels for a few ms of GPU work per rank): the same pass
                 # captured in a CUDA graph, NCCL halo exchanges included (tiled.TiledStereoDPNet.capture)
                 try:

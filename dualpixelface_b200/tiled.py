@@ -51,6 +51,7 @@ class RowTiling:
         self.first, self.last = rank == 0, rank == world - 1
         self.bytes_exchanged = 0          # halo bytes this rank sent (reported by bench.py)
         self.exchanges = 0
+        self.log = None                   # a list -> every exchange appends (tensor shape, (top, bottom) rows, bytes sent)
 
     def rows(self, div: int) -> Tuple[int, int]:
         return self.y0 // div, self.y1 // div
@@ -91,6 +92,9 @@ class RowTiling:
             p2p.append(dist.P2POp(dist.irecv, dn_buf, dn, self.group))
         if p2p:
             self.exchanges += 1
+            if self.log is not None:
+                sent = sum(op.tensor.numel() * op.tensor.element_size() for op in p2p if op.op is dist.isend)
+                self.log.append((tuple(x.shape), str(x.dtype).replace("torch.", ""), (top, bottom), int(sent)))
             for w in dist.batch_isend_irecv(p2p):
                 w.wait()
         return up_buf, dn_buf
