@@ -244,10 +244,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
       const int nblk = max(0, min(C::NBLK, (Ws - tw * WT + 7) >> 3));
       const int hs = th * 16 + hrow;
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+      // narrow layers (N <= 32): the residual of the tile is requested before the accumulator wait (it does not depend on the MMAs;
+      // fetched inside the store loop it is one dependent global round trip per block on the four epilogue warps)
+      constexpr bool kPref = (NPAD <= 32);
+      constexpr int PCH = kPref ? NPAD / 16 : 1;
+      uint4 rr[kPref ? C::NBLK : 1][PCH][2];
+      const bool res_pref = kPref && (p.residual != nullptr) && wide && (p.cout % 16 == 0);
+      if (kPref && res_pref) {
+#pragma unroll
+        for (int blk = 0; blk < C::NBLK; ++blk) {
+          const int ws = tw * WT + blk * 8 + wcol;
+          const bool ok = (blk < nblk) && (hs < Hs) && (ws < Ws);
+          const size_t pix = (static_cast<size_t>(n) * H + (ok ? hs * d + rh : 0)) * W + (ok ? ws * d + rw : 0);
+#pragma unroll
+          for (int q = 0; q < PCH; ++q) {
+            rr[kPref ? blk : 0][q][0] = make_uint4(0u, 0u, 0u, 0u);
+            rr[kPref ? blk : 0][q][1] = rr[kPref ? blk : 0][q][0];
+            if (ok && q * 16 < p.cout)
+              ld_global_v8(p.residual + pix * p.y_cstride + p.y_coff + q * 16, rr[kPref ? blk : 0][q][0], rr[kPref ? blk : 0][q][1]);
+          }
+        }
+      }
       mbar_wait(&bar_tfull[as], aph);
       tc_fence_after_sync();
-#pragma unroll 1
-      for (int blk = 0; blk < nblk; ++blk) {
+#pragma unroll(kPref ? C::NBLK : 1)
+      for (int blk = 0; blk < (kPref ? C::NBLK : nblk); ++blk) {
+        if (kPref && blk >= nblk) continue;
         const int ws = tw * WT + blk * 8 + wcol;
         const bool ok = (hs < Hs) && (ws < Ws);
         const size_t pix = (static_cast<size_t>(n) * H + (ok ? hs * d + rh : 0)) * W + (ok ? ws * d + rw : 0);
@@ -272,8 +294,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
           }
           if (p.residual != nullptr) {
             const __nv_bfloat16* ro = p.residual + pix * p.y_cstride + p.y_coff + c0;
-            uint4 r0 = *reinterpret_cast<const uint4*>(ro), r1 = make_uint4(0u, 0u, 0u, 0u);
-            if (nst > 8) r1 = *reinterpret_cast<const uint4*>(ro + 8);
+            uint4 r0, r1 = make_uint4(0u, 0u, 0u, 0u);
+            if (kPref && res_pref) {
+              r0 = rr[kPref ? blk : 0][kPref ? (c0 >> 4) : 0][0];
+              r1 = rr[kPref ? blk : 0][kPref ? (c0 >> 4) : 0][1];
+            } else {
+              r0 = *reinterpret_cast<const uint4*>(ro);
+              if (nst > 8) r1 = *reinterpret_cast<const uint4*>(ro + 8);
+            }
             f[0] += bf16_lo(r0.x); f[1] += bf16_hi(r0.x); f[2] += bf16_lo(r0.y); f[3] += bf16_hi(r0.y);
             f[4] += bf16_lo(r0.z); f[5] += bf16_hi(r0.z); f[6] += bf16_lo(r0.w); f[7] += bf16_hi(r0.w);
             f[8] += bf16_lo(r1.x); f[9] += bf16_hi(r1.x); f[10] += bf16_lo(r1.y); f[11] += bf16_hi(r1.y);
