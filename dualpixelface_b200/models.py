@@ -17,6 +17,58 @@ from .runner import LightningModule, optimizer_selector, scheduler_selector
 from .synthetic import synthetic_batch
 
 
+import os as _os
+_GENERIC_TC = _os.environ.get("DPF_ENC_GENERIC_TC", "1") != "0"
+
+
+class TCConv2dEval(nn.Module):
+    """Eval-mode stand-in for a BN-folded nn.Conv2d (3x3, stride 1, padding = dilation) on channels-last bf16 activations:
+    one dpf_conv2d_tc_fwd launch with the bias (and an immediately following ReLU) in its epilogue."""
+
+    def __init__(self, conv: nn.Conv2d, relu: bool):
+        super().__init__()
+        self.weight = nn.Parameter(conv.weight.detach().clone(), requires_grad=False)
+        self.bias = nn.Parameter(conv.bias.detach().clone(), requires_grad=False) if conv.bias is not None else None
+        self.cout, self.dil, self.relu = conv.out_channels, conv.dilation[0], relu
+        self._packed = None
+
+    def forward(self, x):
+        if self._packed is None or self._packed[0].device != x.device:
+            self._packed = (ops.pack_conv2d_tc_weight(self.weight.detach().float().to(x.device)),
+                            self.bias.detach().float().to(x.device).contiguous() if self.bias is not None else None)
+        xh = x.permute(0, 2, 3, 1)
+        y = ops.conv2d_tc(xh if xh.is_contiguous() else xh.contiguous(), self._packed[0], self.cout, self.dil, None, self._packed[1],
+                          relu=self.relu)
+        return y.permute(0, 3, 1, 2)
+
+
+def _tc_eligible(m) -> bool:
+    return (isinstance(m, nn.Conv2d) and tuple(m.kernel_size) == (3, 3) and tuple(m.stride) == (1, 1) and m.groups == 1
+            and m.dilation[0] == m.dilation[1] and tuple(m.padding) == tuple(m.dilation) and m.in_channels in (32, 64, 96)
+            and m.out_channels % 8 == 0 and m.out_channels <= 96)
+
+
+def route_convs_to_tc(mod: nn.Module) -> int:
+    """Replace the eligible convolutions of an eval-mode, BN-folded encoder copy (in place); returns how many were replaced.
+    Pattern handled: Sequential(conv, Identity[folded BN]) optionally followed by nn.ReLU in the parent Sequential."""
+    n = 0
+    for _, child in list(mod.named_children()):
+        if isinstance(child, nn.Sequential):
+            items = list(child.named_children())
+            for i, (name, sub) in enumerate(items):
+                if isinstance(sub, nn.Sequential) and len(sub) >= 1 and _tc_eligible(sub[0]) and all(isinstance(t, nn.Identity) for t in list(sub)[1:]):
+                    relu = i + 1 < len(items) and isinstance(items[i + 1][1], nn.ReLU)
+                    sub[0] = TCConv2dEval(sub[0], relu)
+                    if relu:
+                        setattr(child, items[i + 1][0], nn.Identity())
+                    n += 1
+            if len(child) >= 1 and _tc_eligible(child[0]) and all(isinstance(t, nn.Identity) for t in list(child)[1:]):
+                child[0] = TCConv2dEval(child[0], False)         # a bare (conv, folded BN) pair, e.g. _ResBlock.conv2
+                n += 1
+        n += route_convs_to_tc(child)
+    return n
+
+
 class _StereoBase(LightningModule):
     predict_normal = False
     train_supported = False
@@ -65,6 +117,10 @@ class _StereoBase(LightningModule):
                     walk(child)
 
             walk(enc)
+            # every BN-folded 3x3 / stride-1 convolution with 32, 64 or 96 input and <= 96 output channels (PSMNet: firstconv 2-3,
+            # layer1, layer2 = 39 of its 3x3 convs) runs on the repository's 2-D tcgen05 kernel, a directly following ReLU fused
+            if _GENERIC_TC:
+                route_convs_to_tc(enc)
             enc = enc.to(device=next(self.parameters()).device, dtype=torch.bfloat16, memory_format=torch.channels_last)
             self.__dict__["_enc_fused"] = enc
         return enc

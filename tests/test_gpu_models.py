@@ -69,6 +69,28 @@ def test_cpu_input_fails_loudly():
         model(synthetic_batch(1, 256, 256))
 
 
+def test_psmnet_default_path_bf16_encoder_on_tc_kernels():
+    """PSMNet as benchmarked: BN-folded bf16 encoder whose 39 eligible 3x3 convolutions run on dpf_conv2d_tc_fwd (models.route_convs_to_tc)."""
+    from dualpixelface_b200.models import TCConv2dEval
+    batch = synthetic_batch(2, 256, 256, training=True, seed=0)
+    st, fwd = calibrated_state("psmnet", batch)
+    with torch.no_grad():
+        want = fwd(dict(batch), st, False)
+    model = build("psmnet")
+    model.load_state_dict(st, strict=False)
+    model.cuda().eval()
+    with torch.no_grad():
+        got = model(to_cuda(batch))
+    import os
+    if os.environ.get("DPF_ENC_GENERIC_TC", "1") != "0":
+        assert sum(isinstance(m, TCConv2dEval) for m in model._fused_encoder().modules()) == 39
+    err = (got["pred_depth"].float().cpu() - want["pred_depth"]).abs()
+    print(f"psmnet bf16 encoder: disparity max err {err.max():.4f} mean {err.mean():.5f}")
+    # the 50-layer bf16 encoder is the error source here (cuDNN bf16 on the same layers: mean 0.173 / max 1.36 px; these kernels:
+    # 0.164 / 1.22); thresholds <= 2x measured.  The fp32-encoder tests above isolate the hot path (mean 0.010 px).
+    assert err.mean().item() < 0.33 and err.max().item() < 2.5
+
+
 def test_model_default_path_bf16_encoder():
     """The bench configuration: BN-folded bf16 cuDNN encoder in front of the sm_100a hot path."""
     batch = synthetic_batch(2, 128, 160, training=True, seed=0)
