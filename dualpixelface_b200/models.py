@@ -32,7 +32,12 @@ class TCConv2dEval(nn.Module):
         self.cout, self.dil, self.relu = conv.out_channels, conv.dilation[0], relu
         self._packed = None
 
+    min_pixels = 100_000          # below this a launch is latency-bound and cuDNN's small-problem kernels win (PSMNet 1 x 448 x 448)
+
     def forward(self, x):
+        if x.shape[0] * x.shape[2] * x.shape[3] < self.min_pixels:
+            y = torch.nn.functional.conv2d(x, self.weight, self.bias, 1, self.dil, self.dil)
+            return torch.relu_(y) if self.relu else y
         if self._packed is None or self._packed[0].device != x.device:
             self._packed = (ops.pack_conv2d_tc_weight(self.weight.detach().float().to(x.device)),
                             self.bias.detach().float().to(x.device).contiguous() if self.bias is not None else None)
