@@ -65,6 +65,7 @@ if __name__ == "__main__":
             "conv3d_head 32->1": "head", "conv3d kind2 64->32": "conv_t2"}
     tr = json.loads((OUT / "r02_traffic.json").read_text()) if (OUT / "r02_traffic.json").is_file() else {}   # keep captures of earlier calls
     caps["stem_conv 3->32 s2"] = "stem"
+    caps["conv2d_tc 96->32 d1"] = "conv2d_96x32"
     for key, name in caps.items():
         rep = Path(f"gpurun_out/{tag}_{name}.ncu-rep")
         if not rep.is_file():
