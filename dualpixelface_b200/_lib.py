@@ -75,6 +75,8 @@ SIGNATURES = {
     "dpf_anm_gather_bwd": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
     "dpf_conv3d_head_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 5 + [c_void_p]),
     "dpf_stem_conv_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dpf_bn_fwd_coefs": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "dpf_bn_bwd_coefs": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "dpf_softargmin_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_float, c_float, c_void_p]),
 }
 

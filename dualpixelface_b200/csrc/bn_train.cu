@@ -116,6 +116,45 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
   }
 }
 
+// Per-channel coefficients of a train-mode BatchNorm in ONE launch (the ~14 tiny element-wise launches this replaces cost more
+// host time than the two bandwidth kernels around them): stats [C][2] = (sum z, sum z^2) over n elements per channel ->
+// out [4][C] = a = gamma * inv_std | b = beta - mean * a | mean | inv_std; running statistics updated in place (momentum, unbiased var).
+__global__ void bn_fwd_coefs_kernel(const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    float n, float eps, float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                    float* __restrict__ out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = stats[2 * c] / n;
+  const float var = fmaxf(stats[2 * c + 1] / n - mean * mean, 0.f);
+  const float inv = rsqrtf(var + eps);
+  const float a = (gamma ? gamma[c] : 1.f) * inv;
+  out[c] = a;
+  out[C + c] = (beta ? beta[c] : 0.f) - mean * a;
+  out[2 * C + c] = mean;
+  out[3 * C + c] = inv;
+  if (running_mean != nullptr) {
+    running_mean[c] = running_mean[c] * (1.f - momentum) + momentum * mean;
+    running_var[c] = running_var[c] * (1.f - momentum) + momentum * var * (n / fmaxf(n - 1.f, 1.f));
+  }
+}
+
+// Backward coefficients: sums [2][C] = (S1 = sum g, S2 = sum g z) -> dgamma = inv_std (S2 - mean S1), dbeta = S1,
+// coef [4][C] = a | S1 / n | inv_std^2 (S2 - mean S1) / n | mean   (the argument of dpf_bn_bwd_apply).
+__global__ void bn_bwd_coefs_kernel(const float* __restrict__ sums, const float* __restrict__ fwd /*[4][C] of the forward*/, float n,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float s1 = sums[c], s2 = sums[C + c];
+  const float a = fwd[c], mean = fwd[2 * C + c], inv = fwd[3 * C + c];
+  const float centred = s2 - mean * s1;
+  dgamma[c] = inv * centred;
+  dbeta[c] = s1;
+  coef[c] = a;
+  coef[C + c] = s1 / n;
+  coef[2 * C + c] = inv * inv * centred / n;
+  coef[3 * C + c] = mean;
+}
+
 inline int nblocks(long long total) {
   return static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(dpf::sm_count()) * 16));
 }
@@ -156,4 +195,20 @@ extern "C" int dpf_bn_bwd_apply(const void* dy, const void* y, const void* z, co
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(z),
       coef, reinterpret_cast<__nv_bfloat16*>(dz), reinterpret_cast<__nv_bfloat16*>(dres), npix, C, relu, slope);
   return dpf::after_launch("dpf_bn_bwd_apply");
+}
+
+extern "C" int dpf_bn_fwd_coefs(const float* stats, const float* gamma, const float* beta, float n, float eps, float momentum,
+                                float* running_mean, float* running_var, float* out, int C, void* stream) {
+  DPF_REQUIRE(stats && out && C > 0 && n > 0.f, "dpf_bn_fwd_coefs: bad arguments");
+  DPF_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "dpf_bn_fwd_coefs: running_mean and running_var go together");
+  bn_fwd_coefs_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(stats, gamma, beta, n, eps, momentum, running_mean,
+                                                                                      running_var, out, C);
+  return dpf::after_launch("dpf_bn_fwd_coefs");
+}
+
+extern "C" int dpf_bn_bwd_coefs(const float* sums, const float* fwd, float n, float* dgamma, float* dbeta, float* coef, int C,
+                                void* stream) {
+  DPF_REQUIRE(sums && fwd && dgamma && dbeta && coef && C > 0 && n > 0.f, "dpf_bn_bwd_coefs: bad arguments");
+  bn_bwd_coefs_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, fwd, n, dgamma, dbeta, coef, C);
+  return dpf::after_launch("dpf_bn_bwd_coefs");
 }

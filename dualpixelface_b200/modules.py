@@ -16,6 +16,8 @@ train_anm.py (batch-statistics BatchNorm, backward kernels); configurations that
 """
 from __future__ import annotations
 
+import os
+
 from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -51,8 +53,9 @@ class EncoderBatchNorm2d(nn.BatchNorm2d):
     step at C = 32..128.  Everything else (eval, fp32, NCHW) is nn.BatchNorm2d."""
 
     fused_training = True
-    min_pixels = 1_800_000        # below this the layer is launch-bound and ATen's two kernels win over the ~30 small launches here
-                                  # (PSMNet at 512x768 crops: 77.6 vs 84.0 ms per step with / without the threshold)
+    # size threshold below which ATen's kernels are used: with the coefficient arithmetic in one launch each way (dpf_bn_fwd_coefs /
+    # dpf_bn_bwd_coefs) the fused path wins at every layer size (StereoDPNet config 3: 287 -> 267 ms, PSMNet config 4: 77 -> 69 ms)
+    min_pixels = int(os.environ.get("DPF_ENC_BN_MIN_PIXELS", "0"))
 
     def forward(self, x):
         if (self.training and self.fused_training and x.is_cuda and x.numel() // max(x.shape[1], 1) >= self.min_pixels and x.dtype == torch.bfloat16 and x.dim() == 4 and self.affine

@@ -108,7 +108,13 @@ def asm_volume_train(cv, ref_feat, tar_feat):
         for feat, direction in ((ref_feat, "forward"), (tar_feat, "backward")):
             smp = cv.sample(feat, cv._tab(h, w, disp, direction, feat.device), train=True)
             m = ConvBNAct.apply(smp, conv1.weight, bn1.weight, bn1.bias, None, LayerCfg(KIND_1x3x3, True, bn1))
-            stats.append(bn1.__dict__.get("_dpf_last_stats"))
+            last = bn1.__dict__.get("_dpf_last_fwd")                          # (a | b | mean | inv_std, n) of the call above
+            if last is not None:
+                fwd_c, n_el = last
+                var_b = (1.0 / (fwd_c[3] * fwd_c[3]) - bn1.eps).clamp_min(0.0)
+                stats.append((fwd_c[2].clone(), var_b * (n_el / max(n_el - 1, 1))))
+            else:
+                stats.append(None)
             logits = ConvOnly.apply(m, conv2.weight, KIND_1x1x1)
             halves.append(AsmBlendFn.apply(smp, logits, inorm.weight, inorm.bias, inorm.eps))
         y = torch.cat(halves, -1).unsqueeze(1)                           # [B,1,H,W,2C]

@@ -67,6 +67,45 @@ def batch_stats(z: torch.Tensor):
     return mean, var, n
 
 
+def bn_train_coefs(z: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bn) -> tuple:
+    """Train-mode BatchNorm coefficients of a channels-last bf16 activation in three launches (two-pass statistics +
+    dpf_bn_fwd_coefs): returns (fwd [4,C] fp32 = a | b | mean | inv_std, n).  The running statistics of `bn` are updated in place
+    by the kernel (momentum, unbiased variance), `num_batches_tracked` by one tiny add."""
+    c, n = z.shape[-1], _npix(z)
+    st = _sync_sums(ops.channel_stats(z.view(1, n, c))[0])                      # [C,2] = sum z, sum z^2
+    n = n * _sync_world()
+    fwd = torch.empty(4, c, device=z.device, dtype=torch.float32)
+    track = bn is not None and bn.track_running_stats and bn.running_mean is not None
+    mom = 0.0
+    if track:
+        mom = bn.momentum if bn.momentum is not None else 1.0 / float(int(bn.num_batches_tracked) + 1)
+    _lib.check(ops.lib().dpf_bn_fwd_coefs(ops._p(st), ops._p(gamma), ops._p(beta), float(n), float(bn.eps if bn is not None else 1e-5),
+                                          float(mom), ops._p(bn.running_mean) if track else None, ops._p(bn.running_var) if track else None,
+                                          ops._p(fwd), c, ops._stream()), "dpf_bn_fwd_coefs")
+    if track:
+        bn.num_batches_tracked += 1
+    return fwd, n
+
+
+def bn_train_bwd(dy, y, z, fwd, relu, want_dres, slope=0.0):
+    """Backward of act(BN_train(z) [+ res]): (dz, dres, dgamma, dbeta) with dpf_bn_bwd_reduce -> dpf_bn_bwd_coefs -> dpf_bn_bwd_apply
+    (SyncBN keeps the element-wise path: it needs the local AND the all-reduced sums)."""
+    if _sync_world() > 1:
+        return _bn_bwd(dy, y, z, fwd[0], fwd[2], fwd[3], relu, want_dres, slope)
+    c, n = z.shape[-1], _npix(z)
+    sums = torch.empty(2 * c, device=z.device, dtype=torch.float32)
+    _lib.check(ops.lib().dpf_bn_bwd_reduce(ops._p(dy), ops._p(y), ops._p(z), ops._p(sums), n, c, int(relu), float(slope), ops._stream()),
+               "dpf_bn_bwd_reduce")
+    out = torch.empty(6, c, device=z.device, dtype=torch.float32)                 # dgamma | dbeta | coef [4,C]
+    _lib.check(ops.lib().dpf_bn_bwd_coefs(ops._p(sums), ops._p(fwd), float(n), ops._p(out[0]), ops._p(out[1]), ops._p(out[2:]), c,
+                                          ops._stream()), "dpf_bn_bwd_coefs")
+    dz = torch.empty_like(z)
+    dres = torch.empty_like(z) if want_dres else None
+    _lib.check(ops.lib().dpf_bn_bwd_apply(ops._p(dy), ops._p(y), ops._p(z), ops._p(out[2:]), ops._p(dz), ops._p(dres), n, c, int(relu),
+                                          float(slope), ops._stream()), "dpf_bn_bwd_apply")
+    return dz, dres, out[0], out[1]
+
+
 # Test hook (tests/test_gpu_teacher_forced.py): {id(BatchNorm module): the ORACLE's output of that layer, channels-last bf16}.
 # A layer found here still runs its full forward on the kernels, but hands the oracle's activation downstream and to its own
 # backward (ReLU mask), so that a gradient comparison isolates the backward kernels from bf16-induced ReLU-mask flips and from
@@ -141,28 +180,20 @@ class ConvBNAct(Function):
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, residual, cfg: LayerCfg):
         z = TCConv3d(weight, cfg.kind, transposed=cfg.kind == KIND_T2)(x)
-        mean, var, n = batch_stats(z)
-        eps = cfg.bn.eps if cfg.bn is not None else 1e-5
-        inv_std = torch.rsqrt(var + eps)
-        a = (gamma.float() * inv_std).contiguous()
-        b = (beta.float() - mean * a).contiguous()
-        y = _teacher(cfg.bn, _affine_act(z, a, b, residual, cfg.slope if cfg.relu else 1.0))
+        fwd, n = bn_train_coefs(z, gamma, beta, cfg.bn)                     # a | b | mean | inv_std; running statistics updated
+        y = _teacher(cfg.bn, _affine_act(z, fwd[0], fwd[1], residual, cfg.slope if cfg.relu else 1.0))
         if cfg.bn is not None and cfg.bn.track_running_stats:
-            m = cfg.bn.momentum
-            cfg.bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-            cfg.bn.running_var.mul_(1 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
-            cfg.bn.num_batches_tracked += 1
-            cfg.bn.__dict__["_dpf_last_stats"] = (mean, var * (n / max(n - 1, 1)))
-        ctx.save_for_backward(x, weight, z, y, a, mean, inv_std)
+            cfg.bn.__dict__["_dpf_last_fwd"] = (fwd, n)                       # train_asm replays the momentum update from these
+        ctx.save_for_backward(x, weight, z, y, fwd)
         ctx.cfg, ctx.has_res = cfg, residual is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, z, y, a, mean, inv_std = ctx.saved_tensors
+        x, weight, z, y, fwd = ctx.saved_tensors
         cfg = ctx.cfg
         dy = dy.to(torch.bfloat16).contiguous()
-        dz, dres, dgamma, dbeta = _bn_bwd(dy, y, z, a, mean, inv_std, cfg.relu, ctx.has_res, cfg.slope)
+        dz, dres, dgamma, dbeta = bn_train_bwd(dy, y, z, fwd, cfg.relu, ctx.has_res, cfg.slope)
         dx = _dgrad(dz, weight, cfg.kind) if ctx.needs_input_grad[0] else None
         dw = _wgrad(x, dz, weight, cfg.kind)
         return dx, dw, dgamma, dbeta, dres, None
@@ -177,26 +208,18 @@ class BN2dTrainFn(Function):
     def forward(ctx, x, gamma, beta, bn):
         xh = x.permute(0, 2, 3, 1)                                   # [N,H,W,C] view of the channels-last memory
         assert xh.is_contiguous()
-        mean, var, n = batch_stats(xh)
-        inv_std = torch.rsqrt(var + bn.eps)
-        a = (gamma.float() * inv_std).contiguous()
-        b = (beta.float() - mean * a).contiguous()
+        fwd, _n = bn_train_coefs(xh, gamma, beta, bn)
         y = torch.empty_like(x)                                      # NCHW-shaped, channels-last: a fresh tensor, not a view (the
-        _affine_act(xh, a, b, None, 1.0, out=y.permute(0, 2, 3, 1))  # in-place ReLU / PReLU that follows needs a non-view output)
-        with torch.no_grad():
-            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
-            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-            bn.running_var.mul_(1 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
-            bn.num_batches_tracked += 1
-        ctx.save_for_backward(x, a, mean, inv_std)
+        _affine_act(xh, fwd[0], fwd[1], None, 1.0, out=y.permute(0, 2, 3, 1))   # in-place ReLU / PReLU that follows needs a non-view)
+        ctx.save_for_backward(x, fwd)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, a, mean, inv_std = ctx.saved_tensors
+        x, fwd = ctx.saved_tensors
         xh = x.permute(0, 2, 3, 1)
         dyh = dy.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
-        dz, _, dgamma, dbeta = _bn_bwd(dyh, None, xh, a, mean, inv_std, False, False)
+        dz, _, dgamma, dbeta = bn_train_bwd(dyh, None, xh, fwd, False, False)
         return dz.permute(0, 3, 1, 2), dgamma, dbeta, None
 
 

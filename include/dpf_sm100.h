@@ -284,6 +284,13 @@ int dpf_anm_tail_tile(const void* x, float* out, int B, int K, int H4loc, int W4
  * ------------------------------------------------------------------------------------------------- */
 int dpf_affine_act(const void* x, const float* scale, const float* bias, const void* res, void* y, long long npix, int C,
                    float slope, void* stream);
+/* Per-channel coefficient arithmetic of the train-mode BatchNorm in one launch each (replaces ~25 tiny element-wise launches per
+ * layer and step): dpf_bn_fwd_coefs: stats [C][2] (sum z, sum z^2 over n elements) -> out [4][C] = a | b | mean | inv_std and the
+ * running statistics (NULL: not tracked) updated in place with `momentum` (unbiased variance), as nn.BatchNorm does;
+ * dpf_bn_bwd_coefs: sums [2][C] (dpf_bn_bwd_reduce) + the forward's out -> dgamma, dbeta [C] and coef [4][C] for dpf_bn_bwd_apply. */
+int dpf_bn_fwd_coefs(const float* stats, const float* gamma, const float* beta, float n, float eps, float momentum,
+                     float* running_mean, float* running_var, float* out, int C, void* stream);
+int dpf_bn_bwd_coefs(const float* sums, const float* fwd, float n, float* dgamma, float* dbeta, float* coef, int C, void* stream);
 int dpf_bn_bwd_reduce(const void* dy, const void* y, const void* z, float* sums, long long npix, int C, int relu, float slope,
                       void* stream);
 int dpf_bn_bwd_apply(const void* dy, const void* y, const void* z, const float* coef, void* dz, void* dres, long long npix,
