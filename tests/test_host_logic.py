@@ -273,3 +273,40 @@ def test_lightning_style_checkpoint_loads(tmp_path):
     torch.save({"weights": sd}, plain)
     with pytest.raises(NotImplementedError):
         load_checkpoint_state(plain)
+
+
+def test_fuse_t2_weight_layout():
+    """Transposed kind: the 27 tap matrices regrouped into 15 operands (runs of parity classes that read the same input shift)."""
+    import torch
+    from dualpixelface_b200.ops import _T2_DEPTH, _T2_RUNS, _t2_k, fuse_t2_weight, pack_conv_weight
+    w = torch.arange(32 * 64 * 27, dtype=torch.float32).reshape(32, 64, 3, 3, 3) % 251            # [Cout,Cin,kd,kh,kw], bf16-exact values
+    plain = pack_conv_weight(w)                                                                   # [27][8][32][8]
+    fused = fuse_t2_weight(plain)
+    assert fused.shape == plain.shape and torch.equal(fused.flatten().sort().values, plain.flatten().sort().values)
+    flat, pos, ngroups, nslots = fused.flatten(), 0, 0, 0
+    for _rd, kd in _T2_DEPTH:
+        for oh, ow, classes in _T2_RUNS:
+            n = len(classes) * 32
+            grp = flat[pos: pos + 8 * n * 8].reshape(8, n, 8)                                     # [Cin/8][ncls*Npad][8]
+            for i, c in enumerate(classes):
+                tap = (kd * 3 + _t2_k(c >> 1, oh)) * 3 + _t2_k(c & 1, ow)
+                assert torch.equal(grp[:, 32 * i: 32 * (i + 1)], plain[tap])
+            pos += 8 * n * 8
+            ngroups += 1
+            nslots += len(classes)
+    assert (ngroups, nslots, pos) == (15, 27, fused.numel())
+    # out[2q + r] += in[q + o] * W[k]:  r = 0 -> (k 1, o 0);  r = 1 -> (k 0, o 1), (k 2, o 0)
+    assert [_t2_k(0, 0), _t2_k(1, 1), _t2_k(1, 0)] == [1, 0, 2]
+
+
+def test_pack_head_and_stem_weights():
+    import torch
+    from dualpixelface_b200.ops import pack_head_weight, pack_stem_weight
+    w = torch.randn(1, 32, 3, 3, 3).to(torch.bfloat16).float()
+    p = pack_head_weight(w)                                                                       # [4][32 taps][8]
+    assert p.shape == (4, 32, 8) and p[:, 27:].abs().sum() == 0
+    assert float(p[2, 13, 5]) == float(w[0, 2 * 8 + 5, 1, 1, 1])                                  # tap 13 = (1,1,1), channel 21
+    ws = torch.randn(32, 3, 3, 3).to(torch.bfloat16).float()
+    q = pack_stem_weight(ws)                                                                      # [80][32], k = tap*8 + ci
+    assert q.shape == (80, 32) and q[72:].abs().sum() == 0 and q.reshape(10, 8, 32)[:, 3:].abs().sum() == 0
+    assert float(q[(2 * 3 + 1) * 8 + 2, 17]) == float(ws[17, 2, 2, 1])                            # tap (kh 2, kw 1), ci 2, output 17
