@@ -310,3 +310,46 @@ def test_pack_head_and_stem_weights():
     q = pack_stem_weight(ws)                                                                      # [80][32], k = tap*8 + ci
     assert q.shape == (80, 32) and q[72:].abs().sum() == 0 and q.reshape(10, 8, 32)[:, 3:].abs().sum() == 0
     assert float(q[(2 * 3 + 1) * 8 + 2, 17]) == float(ws[17, 2, 2, 1])                            # tap (kh 2, kw 1), ci 2, output 17
+
+
+def test_psmnet_encoder_routing_finds_the_eligible_convs():
+    """models.route_convs_to_tc on a BN-folded copy of PSMNet's encoder: firstconv 2-3, layer1 (6) and layer2 (31) = 39 3x3
+    stride-1 convolutions with <= 96 channels are replaced, a directly following ReLU is fused; the rest stays nn.Conv2d."""
+    import copy
+    import torch.nn as nn
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+    from conftest import ROOT
+    from dualpixelface_b200 import models as MM
+    from dualpixelface_b200.runner import load_config, model_selector
+    model = model_selector(load_config("eval_faceDP_psmnet", "t", root=ROOT, make_dirs=False), root=ROOT).eval()
+    enc = copy.deepcopy(model.feature_extraction).eval()
+
+    def fold(mod):
+        for _, ch in list(mod.named_children()):
+            if isinstance(ch, nn.Sequential) and len(ch) >= 2 and isinstance(ch[0], nn.Conv2d) and isinstance(ch[1], nn.BatchNorm2d):
+                ch[0], ch[1] = fuse_conv_bn_eval(ch[0], ch[1]), nn.Identity()
+            fold(ch)
+
+    fold(enc)
+    n_conv_before = sum(isinstance(m, nn.Conv2d) for m in enc.modules())
+    assert MM.route_convs_to_tc(enc) == 39
+    tc = [m for m in enc.modules() if isinstance(m, MM.TCConv2dEval)]
+    assert len(tc) == 39 and sum(isinstance(m, nn.Conv2d) for m in enc.modules()) == n_conv_before - 39
+    assert sum(m.relu for m in tc) == 2 + 3 + 15                       # firstconv 2-3, conv1 of layer1 (3) and of layer2 (15: its first block is stride 2)
+    assert all(m.cout in (32, 64) and m.dil == 1 for m in tc)
+    assert isinstance(enc.firstconv[0][0], nn.Conv2d) and enc.firstconv[0][0].stride == (2, 2)      # the stem stays
+    assert isinstance(enc.layer3[0].conv1[0][0], nn.Conv2d)                                         # 128-channel layers stay
+
+
+def test_encoder_batchnorm_is_plain_batchnorm_off_the_fused_path():
+    """EncoderBatchNorm2d == nn.BatchNorm2d wherever the fused training path does not apply (CPU, eval, fp32)."""
+    import torch
+    from dualpixelface_b200.modules import EncoderBatchNorm2d
+    torch.manual_seed(0)
+    a, b = EncoderBatchNorm2d(16), torch.nn.BatchNorm2d(16)
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(2, 16, 5, 7)
+    for mode in (True, False):
+        a.train(mode); b.train(mode)
+        assert torch.equal(a(x), b(x))
+    assert set(a.state_dict()) == set(b.state_dict())
