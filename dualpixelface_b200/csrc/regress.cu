@@ -104,10 +104,12 @@ __global__ void __launch_bounds__(kTX* kTY) regress_bwd_kernel(const float* __re
                                                                const float* __restrict__ ddisp, float* __restrict__ dcost,
                                                                int H4, int W4, float mindisp, float step) {
   constexpr int CX = kTX / 4 + 2, CY = kTY / 4 + 2;          // quarter-res cells a tile can touch
-  __shared__ float acc[D][CY][CX];
+  // one accumulator copy per warp (= per pixel row of the tile): shared-memory atomics then only contend inside a warp (~4 lanes
+  // per cell) instead of across all 256 threads of the block
+  __shared__ float acc[kTY][D][CY][CX];
   const int H = 4 * H4, W = 4 * W4;
   const int tid = threadIdx.y * kTX + threadIdx.x;
-  for (int i = tid; i < D * CY * CX; i += kTX * kTY) (&acc[0][0][0])[i] = 0.f;
+  for (int i = tid; i < kTY * D * CY * CX; i += kTX * kTY) (&acc[0][0][0][0])[i] = 0.f;
   __syncthreads();
   const int x = blockIdx.x * kTX + threadIdx.x;
   const int y = blockIdx.y * kTY + threadIdx.y;
@@ -160,10 +162,10 @@ __global__ void __launch_bounds__(kTX* kTY) regress_bwd_kernel(const float* __re
     const int ly0 = ay.i0 - cy0, ly1 = ay.i1 - cy0, lx0 = ax.i0 - cx0, lx1 = ax.i1 - cx0;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      atomicAdd(&acc[d][ly0][lx0], dc[d] * ay.l0 * ax.l0);
-      atomicAdd(&acc[d][ly0][lx1], dc[d] * ay.l0 * ax.l1);
-      atomicAdd(&acc[d][ly1][lx0], dc[d] * ay.l1 * ax.l0);
-      atomicAdd(&acc[d][ly1][lx1], dc[d] * ay.l1 * ax.l1);
+      atomicAdd(&acc[threadIdx.y][d][ly0][lx0], dc[d] * ay.l0 * ax.l0);
+      atomicAdd(&acc[threadIdx.y][d][ly0][lx1], dc[d] * ay.l0 * ax.l1);
+      atomicAdd(&acc[threadIdx.y][d][ly1][lx0], dc[d] * ay.l1 * ax.l0);
+      atomicAdd(&acc[threadIdx.y][d][ly1][lx1], dc[d] * ay.l1 * ax.l1);
     }
   }
   __syncthreads();
@@ -172,7 +174,9 @@ __global__ void __launch_bounds__(kTX* kTY) regress_bwd_kernel(const float* __re
     const int r = (i / CX) % CY;
     const int cc = i % CX;
     const int gy = cy0 + r, gx = cx0 + cc;
-    const float val = acc[d][r][cc];
+    float val = 0.f;
+#pragma unroll
+    for (int wy = 0; wy < kTY; ++wy) val += acc[wy][d][r][cc];        // fixed order over the block's rows
     if (gy < H4 && gx < W4 && val != 0.f) atomicAdd(dcost + (static_cast<size_t>(b) * D + d) * plane + static_cast<size_t>(gy) * W4 + gx, val);
   }
 }
