@@ -44,6 +44,7 @@ SIGNATURES = {
     "dpf_conv3d_fwd": (c_int, [C.POINTER(ConvArgs), c_void_p]),
     "dpf_conv3d_weight_elems": (c_ll, [c_int, c_int, c_int]),
     "dpf_regress_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
+    "dpf_regress_fwd_halfpixel": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "dpf_regress_fwd_tile": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_float, c_float, c_void_p]),
     "dpf_regress_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "dpf_anm_select": (c_int, [c_void_p, c_void_p, c_void_p, c_float_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

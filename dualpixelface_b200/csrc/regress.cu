@@ -29,6 +29,17 @@ __device__ __forceinline__ Axis src_index(int dst, float scale, int in_size) {
   return a;
 }
 
+// ATen's area_pixel_compute_source_index(align_corners=false) for a x4 scale_factor: src = max(0.25 * (dst + 0.5) - 0.5, 0)
+__device__ __forceinline__ Axis src_index_half(int dst, int in_size) {
+  Axis a;
+  const float src = fmaxf(0.25f * (static_cast<float>(dst) + 0.5f) - 0.5f, 0.f);
+  a.i0 = min(static_cast<int>(src), in_size - 1);
+  a.i1 = a.i0 + ((a.i0 < in_size - 1) ? 1 : 0);
+  a.l1 = src - static_cast<float>(a.i0);
+  a.l0 = 1.0f - a.l1;
+  return a;
+}
+
 template <int D>
 __device__ __forceinline__ void plane_values(const float* __restrict__ cost, size_t plane, int W4, const Axis& ay,
                                              const Axis& ax, float (&c)[D]) {
@@ -46,7 +57,8 @@ __device__ __forceinline__ void plane_values(const float* __restrict__ cost, siz
 // Row tiles (BASELINE config 5): `cost` holds the quarter-resolution rows q_row0 .. q_row0+H4loc-1 of an image that is H4 rows
 // tall, `disp` / `prob` the full-resolution rows y_row0 .. y_row0+Hout-1; the source coordinates use the GLOBAL align_corners
 // scale, so the tiles reproduce the untiled result exactly.  Untiled: H4loc = H4, q_row0 = y_row0 = 0, Hout = 4*H4.
-template <int D>
+// HALF: half-pixel (align_corners=False) coordinates on all three axes -- NNet's up-sampling (src/model/nnet/mainmodel.py:149-151).
+template <int D, bool HALF = false>
 __global__ void __launch_bounds__(kTX* kTY) regress_fwd_kernel(const float* __restrict__ cost, float* __restrict__ disp,
                                                                float* __restrict__ prob, int H4, int W4, float mindisp,
                                                                float step, int H4loc, int q_row0, int Hout, int y_row0) {
@@ -59,8 +71,8 @@ __global__ void __launch_bounds__(kTX* kTY) regress_fwd_kernel(const float* __re
   const float sh = static_cast<float>(H4 - 1) / static_cast<float>(H - 1);
   const float sw = static_cast<float>(W4 - 1) / static_cast<float>(W - 1);
   const float sd = static_cast<float>(D - 1) / static_cast<float>(4 * D - 1);
-  Axis ay = src_index(y, sh, H4);
-  const Axis ax = src_index(x, sw, W4);
+  Axis ay = HALF ? src_index_half(y, H4) : src_index(y, sh, H4);
+  const Axis ax = HALF ? src_index_half(x, W4) : src_index(x, sw, W4);
   ay.i0 = min(max(ay.i0 - q_row0, 0), H4loc - 1);             // global quarter-res rows -> rows of the local tile
   ay.i1 = min(max(ay.i1 - q_row0, 0), H4loc - 1);
   const size_t plane = static_cast<size_t>(H4loc) * W4;
@@ -78,8 +90,8 @@ __global__ void __launch_bounds__(kTX* kTY) regress_fwd_kernel(const float* __re
   float se = 0.f, sek = 0.f;
 #pragma unroll
   for (int k = 0; k < 4 * D; ++k) {
-    const float src = sd * static_cast<float>(k);
-    const int d0 = static_cast<int>(src);
+    const float src = HALF ? fmaxf(0.25f * (static_cast<float>(k) + 0.5f) - 0.5f, 0.f) : sd * static_cast<float>(k);
+    const int d0 = min(static_cast<int>(src), D - 1);
     const int d1 = d0 + ((d0 < D - 1) ? 1 : 0);
     const float l1 = src - static_cast<float>(d0);
     const float e = exp2f(fmaf(l1, c[d1] - c[d0], c[d0]));
@@ -230,6 +242,17 @@ extern "C" int dpf_regress_fwd_tile(const float* cost, float* disp, float* prob,
 extern "C" int dpf_regress_fwd(const float* cost, float* disp, float* prob, int B, int D, int H4, int W4, float mindisp,
                                float step, void* stream) {
   return dpf_regress_fwd_tile(cost, disp, prob, B, D, H4, W4, H4, 0, 4 * H4, 0, mindisp, step, stream);
+}
+
+extern "C" int dpf_regress_fwd_halfpixel(const float* cost, float* disp, float* prob, int B, int D, int H4, int W4, float mindisp,
+                                         float step, void* stream) {
+  DPF_REQUIRE(cost && disp, "dpf_regress_fwd_halfpixel: null pointer");
+  DPF_REQUIRE(B > 0 && B <= 65535 && H4 > 1 && W4 > 1, "dpf_regress_fwd_halfpixel: bad shape B=%d H4=%d W4=%d", B, H4, W4);
+  DPF_REQUIRE(D == 8, "dpf_regress_fwd_halfpixel: D=%d (only 8 levels)", D);
+  dim3 grid((4 * W4 + kTX - 1) / kTX, (4 * H4 + kTY - 1) / kTY, B), block(kTX, kTY);
+  regress_fwd_kernel<8, true><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(cost, disp, prob, H4, W4, mindisp, step, H4, 0,
+                                                                                      4 * H4, 0);
+  return dpf::after_launch("dpf_regress_fwd_halfpixel");
 }
 
 extern "C" int dpf_regress_bwd(const float* cost, const float* ddisp, float* dcost, int B, int D, int H4, int W4,

@@ -197,13 +197,15 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, kind: int, cout: int, scale:
 # ----------------------------------------------------------------------------------------------------------
 # fused upsample + soft-argmin
 # ----------------------------------------------------------------------------------------------------------
-def regress_fwd(cost: torch.Tensor, mindisp: float, step: float, want_prob: bool = False):
+def regress_fwd(cost: torch.Tensor, mindisp: float, step: float, want_prob: bool = False, align_corners: bool = True):
+    """align_corners=False: half-pixel coordinates on all three axes (NNet, dpf_regress_fwd_halfpixel)."""
     _req(cost, torch.float32, "cost")
     b, d, h4, w4 = cost.shape
     disp = torch.empty(b, 4 * h4, 4 * w4, device=cost.device, dtype=torch.float32)
     prob = torch.empty(b, 4 * d, 4 * h4, 4 * w4, device=cost.device, dtype=torch.float32) if want_prob else None
     tm = _timing_begin()
-    check(lib().dpf_regress_fwd(_p(cost), _p(disp), _p(prob), b, d, h4, w4, float(mindisp), float(step), _stream()), "dpf_regress_fwd")
+    fn = lib().dpf_regress_fwd if align_corners else lib().dpf_regress_fwd_halfpixel
+    check(fn(_p(cost), _p(disp), _p(prob), b, d, h4, w4, float(mindisp), float(step), _stream()), "dpf_regress_fwd")
     _timing_end(tm, "regress_fwd", cost.numel() * 4.0 + disp.numel() * 4.0 + (prob.numel() * 4.0 if prob is not None else 0.0), "byte")
     return disp, prob
 

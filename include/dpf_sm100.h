@@ -120,6 +120,11 @@ long long dpf_conv3d_weight_elems(int kind, int Cin, int Cout);
  * ------------------------------------------------------------------------------------------------- */
 int dpf_regress_fwd(const float* cost, float* disp, float* prob, int B, int D, int H4, int W4, float mindisp, float step,
                     void* stream);
+/* dpf_regress_fwd with HALF-PIXEL (align_corners=False) coordinates on all three axes: NNet's F.interpolate(scale_factor=4,
+ * 'trilinear', align_corners=False) + disp_regression (src/model/nnet/mainmodel.py:149-152, src/model/nnet/modules.py:191-217).
+ * D = 8 only. */
+int dpf_regress_fwd_halfpixel(const float* cost, float* disp, float* prob, int B, int D, int H4, int W4, float mindisp, float step,
+                              void* stream);
 /* Soft-argmin WITHOUT up-sampling (StereoNet's disp_regression, src/model/stereonet/modules.py:99-120): cost [B,D,P] fp32 ->
  * disp [B,P] = sum_d softmax_d(cost) * (mindisp + d*step); prob (optional, may be NULL) [B,D,P] = the softmax.  D <= 64. */
 int dpf_softargmin_fwd(const float* cost, float* disp, float* prob, int B, int D, long long P, float mindisp, float step, void* stream);

@@ -563,8 +563,11 @@ def _psm_layer(x, st: State, p: str, blocks: int, stride: int, dil: int, has_dow
     return x
 
 
-def psm_encoder(img: torch.Tensor, st: State, p: str, training: bool, inplanes: int = 32, stats=None):
-    """feature_extraction.forward (PSMNet SPP), src/model/psmnet/modules.py:145-171 -> [B,32,H/4,W/4]."""
+def psm_encoder(img: torch.Tensor, st: State, p: str, training: bool, inplanes: int = 32, stats=None,
+                branch_align_corners: bool = True):
+    """feature_extraction.forward (PSMNet SPP), src/model/psmnet/modules.py:145-171 -> [B,32,H/4,W/4].
+    NNet's copy of the encoder (src/model/nnet/modules.py:46-139) differs only in up-sampling its four pooled branches with
+    align_corners=False (:115-124): ``branch_align_corners=False``."""
     x = img
     for i, s in zip((0, 2, 4), (2, 1, 1)):
         x = F.relu(_convbn2(x, st, f"{p}.firstconv.{i}", s, 1, 1, training, stats))
@@ -577,7 +580,7 @@ def psm_encoder(img: torch.Tensor, st: State, p: str, training: bool, inplanes: 
                     ("branch4", inplanes // 4)):
         y = F.avg_pool2d(skip, (k, k), stride=(k, k))
         y = F.relu(_convbn2(y, st, f"{p}.{name}.1", 1, 0, 1, training, stats))
-        branches.append(F.interpolate(y, size=skip.shape[-2:], mode="bilinear", align_corners=True))
+        branches.append(F.interpolate(y, size=skip.shape[-2:], mode="bilinear", align_corners=branch_align_corners))
     f = torch.cat([raw, skip, branches[3], branches[2], branches[1], branches[0]], dim=1)
     f = F.relu(_convbn2(f, st, p + ".lastconv.0", 1, 1, 1, training, stats))
     return F.conv2d(f, st[p + ".lastconv.2.weight"], None)
@@ -762,6 +765,79 @@ def stereonet_forward(batch: dict, st: State, training: bool, cfg: dict = STN_CF
         l1 = smooth_l1_multi(res["pred_depth"], batch["disp"], batch.get("mask"), cfg["loss_weight"])
         res["smoothL1_loss"] = l1
         res["final_loss"] = cfg["lambdas"][0] * l1
+    return res
+
+
+NNET_CFG = dict(mindisp=-4, maxdisp=12, level=8, inplanes=32, loss_weight=(1.0, 1.0), lambdas=(1.0, 1.0))
+
+
+def _convtext(x, st: State, key: str, dil: int):
+    """convtext(), src/model/nnet/modules.py:37-43: bias-free 3x3 conv with padding = dilation, LeakyReLU(0.1)."""
+    return F.leaky_relu(_conv2(x, st, key + ".0", pad=dil, dil=dil), 0.1)
+
+
+NNET_CONTEXT_DILATIONS = (1, 2, 4, 8, 16, 1, 1)       # both `convs` (mainmodel.py:48-56) and `n_convs` (normal_module_.py:34-42)
+
+
+def nnet_context(x, st: State, p: str):
+    for i, dil in enumerate(NNET_CONTEXT_DILATIONS):
+        x = _convtext(x, st, f"{p}.{i}", dil)
+    return x
+
+
+def nnet_normal_module(cost_in: torch.Tensor, k_mat: torch.Tensor, abvalue: torch.Tensor, st: State, p: str,
+                       crange: Sequence[float], training: bool, stats=None) -> torch.Tensor:
+    """NormalModule.forward, src/model/nnet/normal_module_.py:84-118: world-coordinate volume of the 8 cost levels themselves
+    (grid_maker_3d :46-82, the arithmetic of ANM's -- K[:2]/4, K^-1 [u,v,1], depth = a/(d-b), per-sample min/max normalisation),
+    cat with cost_in -> 67 channels, two convbn_3d + ReLU, three (2,3,3)/stride (2,1,1)/pad (0,1,1) convbn_3d + ReLU that fold the
+    8 levels to 1, the 7 dilated `n_convs` per remaining slice (summed), bilinear x4 (align_corners=True), F.normalize."""
+    b, ch, d, h, w = cost_in.shape
+    disp_range = torch.tensor(np.asarray(crange), dtype=torch.float32).view(1, -1, 1, 1).expand(b, -1, h, w).to(cost_in)
+    wc = anm_coord_volume(disp_range, k_mat, abvalue).permute(0, 2, 1, 3, 4)            # [B,3,D,h,w]
+    x = torch.cat([wc, cost_in], 1)
+    x = F.relu(_convbn3(x, st, p + ".wc0.0", 1, training, stats))
+    x = F.relu(_convbn3(x, st, p + ".wc0.2", 1, training, stats))
+    for name in ("pool1", "pool2", "pool3"):
+        y = F.conv3d(x, st[f"{p}.{name}.0.0.weight"], None, stride=(2, 1, 1), padding=(0, 1, 1))
+        x = F.relu(_bn(y, st, f"{p}.{name}.0.1", training, stats_out=stats))
+    nmap = sum(nnet_context(x[:, :, i], st, p + ".n_convs") for i in range(x.shape[2]))
+    nmap = F.interpolate(nmap, scale_factor=4, mode="bilinear", align_corners=True)
+    return F.normalize(nmap, dim=1)
+
+
+def nnet_forward(batch: dict, st: State, training: bool, cfg: dict = NNET_CFG, flip_lr: bool = True,
+                 stages: Optional[dict] = None, stats: Optional[dict] = None):
+    """NNET.forward, src/model/nnet/mainmodel.py:113-177: PSMNet-style SPP encoder, concat volume over int(costrange) row shifts
+    (modules.py:169-188), dres0 (two convbn_3d + ReLU), four residual pairs dres1-4 (no ReLU after the add), classify (convbn_3d,
+    ReLU, 32 -> 1 conv), a per-level 2-D context refinement `convs` on cat(ref features, cost slice) added back to the slice
+    (:142-146), BOTH volumes up-sampled x4 trilinear with align_corners=False (:149-151) and regressed -> pred_depth [B,2,H,W]
+    (raw, refined); the normal module takes cat(dres0 output, dres4 output) (:141,155)."""
+    crange = cost_range(cfg["mindisp"], cfg["maxdisp"], cfg["level"])
+    bins = disparity_bins(cfg["mindisp"], cfg["maxdisp"], cfg["level"])
+    ref_img, tgt_img = _pick_ref_target(batch, flip_lr, training)
+    ref = psm_encoder(ref_img, st, "feature_extraction", training, cfg["inplanes"], stats, branch_align_corners=False)
+    tgt = psm_encoder(tgt_img, st, "feature_extraction", training, cfg["inplanes"], stats, branch_align_corners=False)
+    vol = psm_concat_volume(ref, tgt, crange)
+    c0 = F.relu(_convbn3(vol, st, "dres0.0", 1, training, stats))
+    c0 = F.relu(_convbn3(c0, st, "dres0.2", 1, training, stats))
+    cost_in0 = c0
+    for k in (1, 2, 3, 4):
+        c0 = _convbn3(F.relu(_convbn3(c0, st, f"dres{k}.0", 1, training, stats)), st, f"dres{k}.2", 1, training, stats) + c0
+    cost_in = torch.cat([cost_in0, c0], 1)
+    costs = _conv3(F.relu(_convbn3(c0, st, "classify.0", 1, training, stats)), st, "classify.2")       # [B,1,D,h,w]
+    refined = torch.stack([nnet_context(torch.cat([ref, costs[:, :, i]], 1), st, "convs") + costs[:, :, i]
+                           for i in range(costs.shape[2])], 2)
+    up = lambda c: F.interpolate(c, scale_factor=4, mode="trilinear", align_corners=False).squeeze(1)
+    disps, probs = zip(*[regression(up(c), bins) for c in (costs, refined)])
+    normal = nnet_normal_module(cost_in, batch["K"], batch["abvalue"], st, "normal_module", crange, training, stats).unsqueeze(1)
+    res = {"pred_depth": torch.stack(disps, 1), "prob_depth": torch.stack(probs, 1), "pred_normal": normal,
+           "ref_feature": ref.max(1)[0]}
+    if stages is not None:
+        stages.update(ref=ref, tgt=tgt, volume=vol, cost_in=cost_in, costs=costs, refined=refined)
+    if training and "disp" in batch:
+        l1 = smooth_l1_multi(res["pred_depth"], batch["disp"], batch.get("mask"), cfg["loss_weight"])
+        lc = cosine_normal_loss(res["pred_normal"], batch["normal"], batch["mask"])
+        res.update(smoothL1_loss=l1, cosine_loss=lc, final_loss=cfg["lambdas"][0] * l1 + cfg["lambdas"][1] * lc)
     return res
 
 
