@@ -86,18 +86,37 @@ __global__ void __launch_bounds__(kTX* kTY) regress_fwd_kernel(const float* __re
   for (int d = 1; d < D; ++d) m = fmaxf(m, c[d]);
 #pragma unroll
   for (int d = 0; d < D; ++d) c[d] = (c[d] - m) * 1.4426950408889634f;
-  float v[4 * D];
-  float se = 0.f, sek = 0.f;
-#pragma unroll
-  for (int k = 0; k < 4 * D; ++k) {
+  // bin k in the log2 domain (d0, d1, l1 fold to constants once the loops below are unrolled)
+  auto bin = [&](int k) {
     const float src = HALF ? fmaxf(0.25f * (static_cast<float>(k) + 0.5f) - 0.5f, 0.f) : sd * static_cast<float>(k);
     const int d0 = min(static_cast<int>(src), D - 1);
     const int d1 = d0 + ((d0 < D - 1) ? 1 : 0);
     const float l1 = src - static_cast<float>(d0);
-    const float e = exp2f(fmaf(l1, c[d1] - c[d0], c[d0]));
+    return fmaf(l1, c[d1] - c[d0], c[d0]);
+  };
+  float v[4 * D];
+  float se = 0.f, sek = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4 * D; ++k) {
+    const float e = exp2f(bin(k));
     v[k] = e;
     se += e;
     sek = fmaf(e, static_cast<float>(k), sek);
+  }
+  if (!(se >= 1e-30f)) {
+    // Degenerate costs (adjacent levels > ~100 apart, e.g. an uncalibrated network): interior knots are never hit exactly by a bin,
+    // so every bin can underflow against the maximum KNOT.  Redo the sums against the maximum BIN, as torch's softmax does.
+    float mb = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4 * D; ++k) mb = fmaxf(mb, bin(k));
+    se = 0.f; sek = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4 * D; ++k) {
+      const float e = exp2f(bin(k) - mb);
+      v[k] = e;
+      se += e;
+      sek = fmaf(e, static_cast<float>(k), sek);
+    }
   }
   const float sed = fmaf(step, sek, mindisp * se);
   const float inv = 1.0f / se;

@@ -255,13 +255,14 @@ class _StereoBase(LightningModule):
     @staticmethod
     def convert_checkpoint_keys(state_dict):
         """Key layout of the released checkpoints (README.md:95-101 of the reference) -> this torch / torchvision:
-        * `normal_estimator.grid` is registered lazily by the reference (normal_module.py:91-99) and rebuilt here;
+        * `normal_estimator.grid` (NNet: `normal_module.grid`) is registered lazily by the reference (normal_module.py:91-99,
+          nnet/normal_module_.py:57-65) and rebuilt here;
         * torchvision <= 0.14 FeaturePyramidNetwork stored plain convs (`fpn.inner_blocks.N.weight`), current torchvision wraps
           them in Conv2dNormActivation (`fpn.inner_blocks.N.0.weight`)."""
         import re
         out = {}
         for k, v in state_dict.items():
-            if k.endswith("normal_estimator.grid"):
+            if k.endswith(("normal_estimator.grid", "normal_module.grid")):
                 continue
             k = re.sub(r"(\.fpn\.(?:inner|layer)_blocks\.\d+)\.(weight|bias)$", r"\1.0.\2", k)
             out[k] = v

@@ -173,6 +173,7 @@ class _ResBlock(nn.Module):
 
 class PSMFeatureExtraction(nn.Module):
     """feature_extraction of PSMNet (SPP), src/model/psmnet/modules.py:64-171 -> [B,32,H/4,W/4]."""
+    branch_align_corners = True          # NNet's copy of this encoder up-samples its pooled branches with False (nnet/modules.py:115-124)
 
     def __init__(self, option):
         super().__init__()
@@ -203,7 +204,7 @@ class PSMFeatureExtraction(nn.Module):
         raw = self.layer2(self.layer1(self.firstconv(x)))
         skip = self.layer4(self.layer3(raw))
         size = skip.shape[-2:]
-        br = [F.interpolate(getattr(self, f"branch{i}")(skip), size=size, mode="bilinear", align_corners=True) for i in (1, 2, 3, 4)]
+        br = [F.interpolate(getattr(self, f"branch{i}")(skip), size=size, mode="bilinear", align_corners=self.branch_align_corners) for i in (1, 2, 3, 4)]
         return self.lastconv(torch.cat([raw, skip, br[3], br[2], br[1], br[0]], 1))
 
 

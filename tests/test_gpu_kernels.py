@@ -94,6 +94,36 @@ def test_regress_fwd_bwd(ops, shape):
     assert rel_err(dcost, cost.grad) < 1e-3
 
 
+@pytest.mark.parametrize("shape", [(1, 8, 16, 24), (2, 8, 37, 53)])
+def test_regress_fwd_halfpixel(ops, shape):
+    """dpf_regress_fwd_halfpixel == F.interpolate(scale_factor=4, 'trilinear', align_corners=False) + softmax + expectation (NNet,
+    src/model/nnet/mainmodel.py:149-152)."""
+    g = torch.Generator().manual_seed(52)
+    cost = torch.randn(*shape, generator=g) * 2.0
+    bins = O.disparity_bins(-4, 12, 8)
+    full = F.interpolate(cost.unsqueeze(1), scale_factor=4, mode="trilinear", align_corners=False).squeeze(1)
+    want_d, want_p = O.regression(full, bins)
+    disp, prob = ops.regress_fwd(cost.cuda(), -4.0, 0.5, want_prob=True, align_corners=False)
+    assert (disp.cpu() - want_d).abs().max().item() < 1e-3 * 11.5
+    assert (prob.cpu() - want_p).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("align", [True, False])
+def test_regress_fwd_degenerate_costs(ops, align):
+    """Adjacent levels thousands apart (an uncalibrated network): no bin lands exactly on an interior knot, so every bin underflows
+    against the maximum knot -- the kernel then redoes its sums against the maximum bin, as torch's softmax does (finite output)."""
+    g = torch.Generator().manual_seed(53)
+    cost = torch.randn(1, 8, 9, 12, generator=g) * 3.0e4
+    bins = O.disparity_bins(-4, 12, 8)
+    full = F.interpolate(cost.unsqueeze(1), scale_factor=4, mode="trilinear", align_corners=align).squeeze(1)
+    want_d, want_p = O.regression(full, bins)
+    disp, prob = ops.regress_fwd(cost.cuda(), -4.0, 0.5, want_prob=True, align_corners=align)
+    assert torch.isfinite(disp).all() and torch.isfinite(prob).all()
+    # interpolated bins of such costs carry ~1e-2 absolute fp32 round-off, which the softmax turns into percent-level probability
+    # differences where two bins tie; away from ties the winner-takes-all result is exact
+    assert (disp.cpu() - want_d).abs().median().item() < 1e-3 and (disp.cpu() - want_d).abs().max().item() < 0.5
+
+
 # ------------------------------------------------------------------------------------------------ convolution
 def conv_case(ops, cin, cout, kind, shape, seed, with_affine=True, residual=False, relu=True, out_f32=False):
     b, d, h, w = shape

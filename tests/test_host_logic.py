@@ -353,3 +353,59 @@ def test_encoder_batchnorm_is_plain_batchnorm_off_the_fused_path():
         a.train(mode); b.train(mode)
         assert torch.equal(a(x), b(x))
     assert set(a.state_dict()) == set(b.state_dict())
+
+
+def test_nnet_contract_and_eval_plan():
+    """NNET: the reference's state_dict layout (473 keys), its input-size rule, the lazily registered pixel grid of
+    released checkpoints, and the host-side weight re-layouts of the eval plan -- the 67-channel first layer of the normal module with
+    its input channels reordered to [cost_in | coordinates | zero pad], the depth-halving (2,3,3) convolutions folded to 2-D
+    64-channel ones, the 33 -> 40 channel pad of the first context layer."""
+    from dualpixelface_b200.nnet import NNET, CONTEXT_DILATIONS
+    from dualpixelface_b200.runner import load_config, model_selector
+    shapes = {k: tuple(v) for k, v in json.loads((GOLDEN / "state_keys_nnet.json").read_text()).items()}
+    model = model_selector(load_config("eval_faceDP_nnet", "t", root=ROOT, make_dirs=False), root=ROOT).eval()
+    assert isinstance(model, NNET)
+    sd = model.state_dict()
+    assert set(sd) == set(shapes) and len(sd) == 473
+    assert all(tuple(sd[k].shape) == shapes[k] for k in shapes)
+    assert sd["normal_module.costrange"].flatten().tolist() == [-1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0, 2.5]
+    assert model.cost_volume.shifts == [-1, 0, 0, 0, 1, 1, 2, 2]
+    assert model.convert_checkpoint_keys({"normal_module.grid": 1, "dres0.0.0.weight": 2}) == {"dres0.0.0.weight": 2}
+    model.check_input_size(256, 256)
+    with pytest.raises(ValueError):
+        model.check_input_size(128, 256)                    # the encoder's 64 x 64 average pool
+    assert not model.feature_extraction.branch_align_corners
+    p = model._build()
+    w = model.normal_module.wc0[0][0].weight
+    conv0 = p["wc0.0"][0]
+    assert conv0.cin == 96 and [(ln.x_coff, ln.cin) for ln in conv0.plan] == [(0, 32), (32, 32), (64, 32)]
+    assert [tuple(wt.shape[:2]) + (d,) for wt, d in p["ctx_cudnn"]] == [(128, 40, 1), (128, 128, 2), (128, 128, 4), (96, 128, 8)]
+    assert torch.equal(p["ctx_cudnn"][0][0][:, 33:].float(), torch.zeros(128, 7, 3, 3))
+    assert [(c, d) for _, c, d in p["ctx_tc"]] == [(64, 16), (32, 1), (1, 1)]
+    assert [(c, d) for _, c, d in p["n_convs"]] == list(zip((96, 96, 96, 64, 64, 32, 3), CONTEXT_DILATIONS))
+    # depth-pair folding: conv3d over (kd, kh, kw) == conv2d over channels (kd * C + c)
+    pool = model.normal_module.pool1[0][0]
+    x = torch.randn(1, 32, 4, 6, 7)
+    want = pool(x)                                           # [1,32,2,6,7]
+    w2 = pool.weight.detach().permute(0, 2, 1, 3, 4).reshape(32, 64, 3, 3)
+    pairs = x.permute(0, 2, 3, 4, 1).reshape(1, 2, 2, 6, 7, 32).permute(0, 1, 3, 4, 2, 5).reshape(2, 6, 7, 64)
+    got = F.conv2d(pairs.permute(0, 3, 1, 2), w2, None, 1, 1).view(1, 2, 32, 6, 7).permute(0, 2, 1, 3, 4)
+    assert torch.allclose(got, want, atol=1e-5)
+    assert p["pools"][0][0].shape == (9, 8, 32, 8)          # 64 input channels in 8-channel pieces, 32 outputs
+    # plans are dropped with the weights they were packed from
+    model.train()
+    assert model._plan is None
+
+
+def test_nnet_coord_volume_matches_oracle():
+    from dualpixelface_b200.nnet import NormalModule
+    from dualpixelface_b200.runner import load_config
+    from oracle import dpf_oracle as O
+    opt = load_config("eval_faceDP_nnet", "t", root=ROOT, make_dirs=False)
+    nm = NormalModule(opt, -4, 12)
+    batch = synthetic_batch(2, 64, 96, training=False, seed=0)
+    got = nm.coord_volume(batch["K"], batch["abvalue"], 16, 24)
+    cr = torch.tensor(np.asarray(O.cost_range(-4, 12, 8)), dtype=torch.float32).view(1, -1, 1, 1).expand(2, -1, 16, 24)
+    want = O.anm_coord_volume(cr, batch["K"], batch["abvalue"]).permute(0, 2, 1, 3, 4)
+    assert got.shape == want.shape == (2, 3, 8, 16, 24)
+    assert (got - want).abs().max().item() < 1e-5

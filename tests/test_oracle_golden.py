@@ -219,3 +219,33 @@ def test_oracle_stereonet_grads():
     for key in [k[len("train/grad/"):] for k in gold.files if k.startswith("train/grad/")]:
         close(gold[f"train/grad/{key}"], st[key].grad, 1e-4)
     assert st["feature_extraction.residual_blocks.0.conv2.0.weight"].grad is None      # constructed but never applied (modules.py:23)
+
+
+# ---- NNet, fixtures from tests/golden/make_golden_nnet.py (the unmodified reference) ----
+def _nnet_shapes():
+    import json
+    return {k: tuple(v) for k, v in json.loads((GOLDEN / "state_keys_nnet.json").read_text()).items()}
+
+
+def test_oracle_nnet_forward_and_grads():
+    """Oracle == the reference's NNET: train mode (batch statistics, both losses, ten parameter gradients spread over the encoder,
+    the 3-D trunk, the context refinement and the normal module) and eval mode with calibrated statistics."""
+    gold = np.load(GOLDEN / "model_nnet.npz")
+    st0 = synth_state(_nnet_shapes(), seed=1)
+    batch = synthetic_batch(2, 256, 256, training=True, seed=0)
+    st = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v) for k, v in st0.items()}
+    stats = {}
+    res_t = O.nnet_forward(dict(batch), st, True, stats=stats)
+    res_t["final_loss"].backward()
+    close(gold["train/pred_depth_s2"], res_t["pred_depth"][..., ::2, ::2].detach(), 2e-5)
+    close(gold["train/pred_normal_s2"], res_t["pred_normal"][..., ::2, ::2].detach(), 2e-5)
+    for key in ("smoothL1_loss", "cosine_loss", "final_loss"):
+        close(gold[f"train/{key}"], res_t[key].detach(), 2e-5)
+    for key in [k[len("train/grad/"):] for k in gold.files if k.startswith("train/grad/")]:
+        close(gold[f"train/grad/{key}"], st[key].grad, 1e-4)
+    with torch.no_grad():
+        res_e = O.nnet_forward(dict(batch), O.calibrate_running_stats(st0, stats), False)
+    for key in ("pred_depth", "pred_normal", "ref_feature"):
+        close(gold[f"eval/{key}"], res_e[key], 2e-5)
+    close(gold["eval/prob_depth_s8"], res_e["prob_depth"][..., ::8, ::8], 2e-5)
+    assert res_e["pred_depth"].shape == (2, 2, 256, 256) and res_e["pred_normal"].shape == (2, 1, 3, 256, 256)
