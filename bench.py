@@ -255,6 +255,32 @@ def psmnet_block(dev, rank, world, steps):
     return out
 
 
+def other_models_block(dev, steps):
+    """the two other cost-volume models of the reference on the same kernels -- eval forward of 4 x 1120x1680 pairs
+    on this GPU (synthetic 'calibrated' weights), with the time of each stage."""
+    from dualpixelface_b200.synthetic import synthetic_batch
+    out = {}
+    for name in ("nnet", "stereonet"):
+        model = batch = None
+        try:
+            model = build_model(dev, f"eval_faceDP_{name}", name)
+            batch = {k: v.to(dev) for k, v in synthetic_batch(4, H, W, seed=0).items()}
+            with torch.no_grad():
+                ms = _time_ms(lambda: model(batch), max(steps, 5), 3)
+                model.stage_events = []
+                model(batch)
+                torch.cuda.synchronize()
+                ev = model.stage_events
+                model.stage_events = None
+            out[name] = {"ms_per_step": round(ms, 3), "pairs_per_s": round(4 / (ms * 1e-3), 1), "shape": [4, H, W],
+                         "stage_ms": {n: round(a.elapsed_time(b_), 3) for (_, a), (n, b_) in zip(ev[:-1], ev[1:])}}
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        del model, batch
+        torch.cuda.empty_cache()
+    return out
+
+
 def gpu_eager_oracle_block(dev):
     """Context line: the oracle's own PyTorch code (= the reference's algorithm, restated) executed on the SAME B200 in fp32
     eager mode with cuDNN (TF32 off), StereoDPNet eval forward of ONE 1120x1680 pair.  Not a baseline to beat by itself (it is
@@ -580,6 +606,8 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             line["costvol"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
         line["gpu_eager_oracle"] = gpu_eager_oracle_block(dev)
+        if args.model == "stereodpnet" and (H, W) == (1120, 1680):
+            line["other_models"] = other_models_block(dev, max(3, min(args.steps, 5)))
     if world == 1 and not args.no_cpu:
         val, sec, cores, sample = cpu_reference_pairs_per_s(3, 1)
         line["cpu_baseline"] = {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample,
