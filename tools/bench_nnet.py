@@ -1,6 +1,5 @@
 #!/usr/bin/env python
-"""NNet on one B200: eval time per stage at the StereoDPNet bench shape (B x 1120 x 1680), the same forward of the
-oracle in PyTorch eager on the same GPU for scale, and one training step.  Prints one JSON object."""
+"""NNet on one B200: eval time per stage at the StereoDPNet bench shape (B x 1120 x 1680), and one training step.  Prints one JSON object."""
 import argparse
 import json
 import sys
@@ -34,7 +33,6 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--size", type=int, nargs=2, default=(1120, 1680))
     ap.add_argument("--train-batch", type=int, default=2)
-    ap.add_argument("--eager", action="store_true", help="also time the oracle (PyTorch eager, fp32, TF32 off) on this GPU, 1 pair")
     args = ap.parse_args()
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -56,12 +54,6 @@ if __name__ == "__main__":
                 stage[name] = stage.get(name, 0.0) + a.elapsed_time(b_) / 5
         model.stage_events = None
         out["eval_stage_ms"] = {k: round(v, 3) for k, v in stage.items()}
-        if args.eager:
-            from oracle import dpf_oracle as O                      # the checker, timed beside the product (never on its path)
-            st = {k: v.detach().float() for k, v in model.state_dict().items()}
-            b1 = {k: v[:1] for k, v in batch.items()}
-            ms_e = timed(lambda: O.nnet_forward(dict(b1), st, False), 1, 2)
-            out["gpu_eager_oracle_ms_per_pair"] = ms_e
     del batch
     torch.cuda.empty_cache()
     model.train()
