@@ -130,6 +130,9 @@ class NNET(_StereoBase):
         super().__init__()
         self._common_init(option)
         c = option.model.inplanes
+        if c != 32 or int(option.model.level) != 8:
+            raise NotImplementedError(f"NNET on the sm_100a kernels is built for inplanes = 32 and level = 8 (the reference's shipped "
+                                      f"setting, src/model/nnet/config.json), got inplanes = {c}, level = {option.model.level}")
         self.predict_normal = bool(option.model.predict_normal)
         self.feature_extraction = NNetFeatureExtraction(option)
         self.cost_volume = CostVolume(option, self.mindisp, self.maxdisp)
