@@ -33,17 +33,25 @@ class TCConv2dEval(nn.Module):
         self._packed = None
 
     min_pixels = 100_000          # below this a launch is latency-bound and cuDNN's small-problem kernels win (PSMNet 1 x 448 x 448)
+    fuses_residual = True         # forward(x, residual): the skip connection of a residual block rides in the conv epilogue
 
-    def forward(self, x):
+    def forward(self, x, residual=None):
+        assert residual is None or not self.relu          # y = conv + bias + residual (BasicBlock: no activation after the add)
         if x.shape[0] * x.shape[2] * x.shape[3] < self.min_pixels:
             y = torch.nn.functional.conv2d(x, self.weight, self.bias, 1, self.dil, self.dil)
+            if residual is not None:
+                y = y + residual
             return torch.relu_(y) if self.relu else y
         if self._packed is None or self._packed[0].device != x.device:
             self._packed = (ops.pack_conv2d_tc_weight(self.weight.detach().float().to(x.device)),
                             self.bias.detach().float().to(x.device).contiguous() if self.bias is not None else None)
         xh = x.permute(0, 2, 3, 1)
+        rh = None
+        if residual is not None:
+            rh = residual.permute(0, 2, 3, 1)
+            rh = rh if rh.is_contiguous() else rh.contiguous()
         y = ops.conv2d_tc(xh if xh.is_contiguous() else xh.contiguous(), self._packed[0], self.cout, self.dil, None, self._packed[1],
-                          relu=self.relu)
+                          residual=rh, relu=self.relu)
         return y.permute(0, 3, 1, 2)
 
 
@@ -53,23 +61,70 @@ def _tc_eligible(m) -> bool:
             and m.out_channels % 8 == 0 and m.out_channels <= 96)
 
 
+class CudnnConvBiasAct(nn.Module):
+    """Eval-mode stand-in for a BN-folded nn.Conv2d that stays on cuDNN (strided, 1x1, 128-channel layers): the convolution runs
+    bias-free and ONE dpf_bias_act pass applies the folded bias, the ReLU that follows and the skip connection of a residual
+    block.  (cuDNN's own bias is a separate broadcast add that ATen runs on its non-vectorised element-wise kernel: 21 such passes
+    were 13 % of an NNet / PSMNet encoder forward, the ReLU and the skip add two more passes each.)"""
+    fuses_residual = True
+
+    def __init__(self, conv: nn.Conv2d, relu: bool):
+        super().__init__()
+        self.weight = nn.Parameter(conv.weight.detach().clone(), requires_grad=False)
+        self.__dict__["_bias32"] = conv.bias.detach().float().clone()          # kept in fp32 whatever dtype the module is moved to
+        self.stride, self.padding, self.dilation, self.relu = conv.stride, conv.padding, conv.dilation, relu
+        self.cout = conv.out_channels
+
+    def forward(self, x, residual=None):
+        assert residual is None or not self.relu          # y = conv + bias + residual (BasicBlock: no activation after the add)
+        y = torch.nn.functional.conv2d(x, self.weight, None, self.stride, self.padding, self.dilation)
+        b = self.__dict__["_bias32"]
+        if b.device != y.device:
+            b = self.__dict__["_bias32"] = b.to(y.device)
+        if not (y.is_cuda and y.dtype == torch.bfloat16):
+            y = y + b.to(y.dtype).view(1, -1, 1, 1)
+            if residual is not None:
+                y = y + residual
+            return torch.relu_(y) if self.relu else y
+        cl = torch.channels_last
+        y = y if y.is_contiguous(memory_format=cl) else y.contiguous(memory_format=cl)
+        if residual is not None and not residual.is_contiguous(memory_format=cl):
+            residual = residual.contiguous(memory_format=cl)
+        return ops.bias_act(y, b, 0.0 if self.relu else 1.0, res=residual)
+
+
+def _stand_in(conv, relu: bool):
+    """(replacement module | None, 1 if it runs on the repository's 2-D tcgen05 kernel else 0)."""
+    if _tc_eligible(conv):
+        return TCConv2dEval(conv, relu), 1
+    if isinstance(conv, nn.Conv2d) and conv.bias is not None and conv.groups == 1 and conv.out_channels % 8 == 0:
+        return CudnnConvBiasAct(conv, relu), 0
+    return None, 0
+
+
 def route_convs_to_tc(mod: nn.Module) -> int:
-    """Replace the eligible convolutions of an eval-mode, BN-folded encoder copy (in place); returns how many were replaced.
+    """Replace the convolutions of an eval-mode, BN-folded encoder copy (in place): the eligible 3x3 ones by TCConv2dEval (their
+    number is returned), the other biased ones by CudnnConvBiasAct.
     Pattern handled: Sequential(conv, Identity[folded BN]) optionally followed by nn.ReLU in the parent Sequential."""
     n = 0
     for _, child in list(mod.named_children()):
         if isinstance(child, nn.Sequential):
             items = list(child.named_children())
             for i, (name, sub) in enumerate(items):
-                if isinstance(sub, nn.Sequential) and len(sub) >= 1 and _tc_eligible(sub[0]) and all(isinstance(t, nn.Identity) for t in list(sub)[1:]):
+                if isinstance(sub, nn.Sequential) and len(sub) >= 1 and type(sub[0]) is nn.Conv2d and all(isinstance(t, nn.Identity) for t in list(sub)[1:]):
                     relu = i + 1 < len(items) and isinstance(items[i + 1][1], nn.ReLU)
-                    sub[0] = TCConv2dEval(sub[0], relu)
+                    rep, k = _stand_in(sub[0], relu)
+                    if rep is None:
+                        continue
+                    sub[0] = rep
                     if relu:
                         setattr(child, items[i + 1][0], nn.Identity())
-                    n += 1
-            if len(child) >= 1 and _tc_eligible(child[0]) and all(isinstance(t, nn.Identity) for t in list(child)[1:]):
-                child[0] = TCConv2dEval(child[0], False)         # a bare (conv, folded BN) pair, e.g. _ResBlock.conv2
-                n += 1
+                    n += k
+            if len(child) >= 1 and type(child[0]) is nn.Conv2d and all(isinstance(t, nn.Identity) for t in list(child)[1:]):
+                rep, k = _stand_in(child[0], False)               # a bare (conv, folded BN) pair, e.g. _ResBlock.conv2 / downsample
+                if rep is not None:
+                    child[0] = rep
+                    n += k
         n += route_convs_to_tc(child)
     return n
 

@@ -167,6 +167,9 @@ class _ResBlock(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
+        head = self.conv2[0]
+        if getattr(head, "fuses_residual", False):            # eval plan (models.route_convs_to_tc): the add rides in conv2's epilogue
+            return head(self.conv1(x), residual=self.downsample(x) if self.downsample is not None else x)
         y = self.conv2(self.conv1(x))
         return y + (self.downsample(x) if self.downsample is not None else x)
 

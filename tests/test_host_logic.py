@@ -314,7 +314,8 @@ def test_pack_head_and_stem_weights():
 
 def test_psmnet_encoder_routing_finds_the_eligible_convs():
     """models.route_convs_to_tc on a BN-folded copy of PSMNet's encoder: firstconv 2-3, layer1 (6) and layer2 (31) = 39 3x3
-    stride-1 convolutions with <= 96 channels are replaced, a directly following ReLU is fused; the rest stays nn.Conv2d."""
+    stride-1 convolutions with <= 96 channels go to the tcgen05 kernel, a directly following ReLU fused; the other biased ones
+    stay on cuDNN behind CudnnConvBiasAct."""
     import copy
     import torch.nn as nn
     from torch.nn.utils.fusion import fuse_conv_bn_eval
@@ -331,14 +332,19 @@ def test_psmnet_encoder_routing_finds_the_eligible_convs():
             fold(ch)
 
     fold(enc)
-    n_conv_before = sum(isinstance(m, nn.Conv2d) for m in enc.modules())
     assert MM.route_convs_to_tc(enc) == 39
     tc = [m for m in enc.modules() if isinstance(m, MM.TCConv2dEval)]
-    assert len(tc) == 39 and sum(isinstance(m, nn.Conv2d) for m in enc.modules()) == n_conv_before - 39
+    assert len(tc) == 39
     assert sum(m.relu for m in tc) == 2 + 3 + 15                       # firstconv 2-3, conv1 of layer1 (3) and of layer2 (15: its first block is stride 2)
     assert all(m.cout in (32, 64) and m.dil == 1 for m in tc)
-    assert isinstance(enc.firstconv[0][0], nn.Conv2d) and enc.firstconv[0][0].stride == (2, 2)      # the stem stays
-    assert isinstance(enc.layer3[0].conv1[0][0], nn.Conv2d)                                         # 128-channel layers stay
+    # every other biased convolution stays on cuDNN, bias-free, with ONE dpf_bias_act pass for bias + ReLU + skip connection:
+    # stem, layer2.0 conv1 (stride 2), the two 1x1 downsamples, layer3 / layer4 (12), the four SPP branches, lastconv.0 = 21
+    cd = [m for m in enc.modules() if isinstance(m, MM.CudnnConvBiasAct)]
+    assert len(cd) == 21 and sum(m.relu for m in cd) == 1 + 1 + 6 + 4 + 1
+    assert isinstance(enc.firstconv[0][0], MM.CudnnConvBiasAct) and enc.firstconv[0][0].stride == (2, 2)      # the stem
+    assert isinstance(enc.layer3[0].conv1[0][0], MM.CudnnConvBiasAct) and enc.layer3[0].conv1[0][0].cout == 128
+    left = [m for m in enc.modules() if isinstance(m, nn.Conv2d)]
+    assert len(left) == 1 and left[0] is enc.lastconv[2] and left[0].bias is None                            # the bias-free 1x1 output conv
 
 
 def test_encoder_batchnorm_is_plain_batchnorm_off_the_fused_path():
@@ -409,3 +415,46 @@ def test_nnet_coord_volume_matches_oracle():
     want = O.anm_coord_volume(cr, batch["K"], batch["abvalue"]).permute(0, 2, 1, 3, 4)
     assert got.shape == want.shape == (2, 3, 8, 16, 24)
     assert (got - want).abs().max().item() < 1e-5
+
+
+def test_routed_encoder_fuses_the_skip_connections():
+    """The BN-folded, routed copy of the SPP encoder (PSMNet / NNet) == the original encoder in eval mode: the 19 residual blocks
+    whose conv2 runs on dpf_conv2d_tc_fwd hand their skip connection to that launch (TCConv2dEval.forward(x, residual)), the 6
+    128-channel ones to the dpf_bias_act pass behind their cuDNN convolution (CudnnConvBiasAct); on CPU the stand-ins take their
+    plain PyTorch fallback, which checks the same wiring."""
+    import copy
+    import torch.nn as nn
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+    from dualpixelface_b200 import models as MM
+    from dualpixelface_b200.runner import load_config, model_selector
+    torch.manual_seed(3)
+    model = model_selector(load_config("eval_faceDP_nnet", "t", root=ROOT, make_dirs=False), root=ROOT).eval()
+    for m in model.feature_extraction.modules():                         # non-trivial running statistics
+        if isinstance(m, nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+    enc = copy.deepcopy(model.feature_extraction).eval()
+
+    def fold(mod):
+        for _, ch in list(mod.named_children()):
+            if isinstance(ch, nn.Sequential) and len(ch) >= 2 and isinstance(ch[0], nn.Conv2d) and isinstance(ch[1], nn.BatchNorm2d):
+                ch[0], ch[1] = fuse_conv_bn_eval(ch[0], ch[1]), nn.Identity()
+            fold(ch)
+
+    fold(enc)
+    assert MM.route_convs_to_tc(enc) == 39
+    blocks = [b for layer in (enc.layer1, enc.layer2, enc.layer3, enc.layer4) for b in layer]
+    assert len(blocks) == 25 and all(getattr(b.conv2[0], "fuses_residual", False) for b in blocks)
+    calls = []
+    orig = {c: c.forward for c in (MM.TCConv2dEval, MM.CudnnConvBiasAct)}
+    for c, f in orig.items():
+        c.forward = (lambda f: lambda self, x, residual=None: (calls.append(residual is not None), f(self, x, residual))[1])(f)
+    try:
+        x = torch.randn(1, 3, 256, 256)
+        with torch.no_grad():
+            got, want = enc(x), model.feature_extraction(x)
+    finally:
+        for c, f in orig.items():
+            c.forward = f
+    assert sum(calls) == 25 and len(calls) == 39 + 21
+    assert (got - want).abs().max().item() < 1e-4 * want.abs().max().item()
