@@ -120,7 +120,7 @@ class STEREONET(_StereoBase):
             fe, rf = self.feature_extraction, self.edge_aware_refinements[0]
             bf = lambda t: t.detach().to(torch.bfloat16)
             cl = lambda conv: bf(conv.weight).contiguous(memory_format=torch.channels_last)
-            p = {"stem": [(cl(c), bf(c.bias)) for c in fe.downsample],
+            p = {"stem": [(cl(c), c.bias.detach().float().contiguous()) for c in fe.downsample],
                  "enc_blocks": [_pack_block(b) for b in fe.residual_blocks],
                  "enc_out": (ops.pack_conv2d_tc_weight(fe.conv_alone.weight.detach().float()), fe.conv_alone.bias.detach().float().contiguous()),
                  "filter": [], "ref_blocks": [_pack_block(b) for b in rf.residual_astrous_blocks]}
@@ -139,7 +139,7 @@ class STEREONET(_StereoBase):
         """[N,3,H,W] -> [N,h,w,32] bf16 channels-last."""
         x = img.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         for w, b in p["stem"]:                                           # 5x5 stride-2 convs with bias, no activation (modules.py:37-46)
-            x = F.conv2d(x, w, b, 2, 2)
+            x = ops.bias_act(F.conv2d(x, w, None, 2, 2), b, 1.0)         # (cuDNN's own bias is a non-vectorised broadcast add in ATen)
         x = x.permute(0, 2, 3, 1)
         x = x if x.is_contiguous() else x.contiguous()
         for pk in p["enc_blocks"]:
